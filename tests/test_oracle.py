@@ -1,0 +1,108 @@
+"""The oracle (oracle/vap_oracle.py) against the reference's own outputs.
+
+The golden arrays were produced by the UNMODIFIED reference on CPU fp32
+(oracle/make_golden.py). The oracle uses the same ATen ops in the same order, so
+on the same torch build it is bit-identical; across builds we allow 2e-6.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import CASE_NAMES, golden_inputs, load_golden
+from oracle import ref_import, synth
+from oracle import vap_oracle as O
+
+TOL = 2e-6
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_oracle_matches_reference_golden(name):
+    if name == "lstm1_turns_T1000" and os.environ.get("VAP_FAST_TESTS"):
+        pytest.skip("fast mode")
+    recipe, g = load_golden(name)
+    sd, wav = golden_inputs(recipe, g)
+    stages = {}
+    fwd = O.forward(sd, wav, stages=stages)
+    assert (fwd["logits"] - g["logits"]).abs().max() <= 5e-5  # logits are O(1..10)
+    assert (fwd["vad"] - g["vad_logits"]).abs().max() <= 5e-5
+    out = O.probs(sd, wav)
+    assert list(out.keys()) == ["probs", "vad", "p_now", "p_future", "H", "loss"]
+    for k in ["probs", "vad", "p_now", "p_future"]:
+        if k in g:
+            assert out[k].shape == g[k].shape
+            assert (out[k] - g[k]).abs().max() <= TOL, k
+    assert (out["H"] - g["H"]).abs().max() <= 2e-5
+    assert out["loss"].shape == g["loss"].shape
+    assert (out["loss"] - g["loss"]).abs().max() <= 5e-5
+    # decisions are bit-exact
+    assert torch.equal(fwd["logits"].argmax(-1), g["logits"].argmax(-1))
+    assert torch.equal(out["vad"] >= 0.5, g["vad"] >= 0.5)
+    if recipe.get("stages"):
+        m = {"stage_conv": "conv_1", "stage_ar": "ar_1", "stage_enc": "enc_1", "stage_ch": "ch_1",
+             "stage_comb": "comb"}
+        for gk, sk in m.items():
+            assert (stages[sk][:1] - g[gk]).abs().max() <= 2e-5, gk
+        for l in range(3):
+            for c in (1, 2):
+                assert (stages[f"ar{l}_x{c}"][:1] - g[f"stage_ar{l}_x{c}"]).abs().max() <= 5e-5
+
+
+def test_oracle_session_stitching_matches_reference_golden():
+    recipe, g = load_golden("session_45s")
+    sd = synth.make_state_dict(recipe["seed"], recipe["ar_mode"], recipe["ar_layers"], recipe["gain"])
+    for tag in ("a", "b"):
+        n = int(g[f"{tag}_n_samples"])
+        wav = synth.make_waveform(1, n, recipe["wav_seed"], recipe["kind"])
+        out = O.step_extraction(sd, wav)
+        for k in ["vad", "p_now", "p_future"]:
+            assert out[k].shape == g[f"{tag}_{k}"].shape
+            assert (out[k] - g[f"{tag}_{k}"]).abs().max() <= TOL
+        assert (out["H"] - g[f"{tag}_H"]).abs().max() <= 2e-5
+        assert (out["loss"] - g[f"{tag}_loss"]).abs().max() <= 5e-5
+        assert torch.equal(out["probs"].argmax(-1).to(torch.uint8), g[f"{tag}_probs_argmax"])
+
+
+def test_recurrence_equations_match_aten():
+    for mode, layers in [("LSTM", 1), ("GRU", 1), ("LSTM", 2)]:
+        sd = synth.make_state_dict(11, mode, layers)
+        z = torch.randn(2, 40, 256, generator=torch.Generator().manual_seed(0))
+        assert (O.ar_net(sd, z) - O.ar_net_loop(sd, z)).abs().max() < 1e-5
+        assert O.ar_kind(sd) == (mode, layers)
+
+
+def test_frame_count_chain():
+    # SURVEY.md F10b probe table
+    assert O.n_frames(37392)[-2:] == [233, 117]
+    assert O.n_frames(160000)[-2:] == [1000, 500]
+    assert O.n_frames(320000) == [64000, 16000, 8000, 4000, 2000, 1000]
+    assert O.n_frames(400000)[-2:] == [2500, 1250]
+    assert O.n_frames(32159)[-1] == 101 and O.n_frames(32158)[-1] == 100
+
+
+def test_probs_raises_for_100_frames_or_fewer():
+    # reference vap/model.py:220-224 via objective.py:53 (unfold), SURVEY.md F6
+    sd = synth.make_state_dict(0)
+    wav = synth.make_waveform(1, 32000, 0)
+    with pytest.raises(RuntimeError):
+        O.probs(sd, wav)
+
+
+def test_codebook_and_alibi():
+    cv = O.code_vectors(8)
+    assert cv[1].tolist() == [1, 0, 0, 0, 0, 0, 0, 0]
+    assert cv[16].tolist() == [0, 0, 0, 0, 1, 0, 0, 0]
+    assert synth.alibi_slopes(4) == [0.25, 0.0625, 0.015625, 0.00390625]
+    m = O.alibi_mask(torch.tensor(synth.alibi_slopes(4)), 5)
+    assert m[0, 0, 2, 1] == 1.0 + 0.25 and m[0, 0, 1, 2] == float("-inf")
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present")
+def test_oracle_bit_identical_to_imported_reference():
+    sd = synth.make_state_dict(21, "LSTM", 1, 2.0)
+    model = ref_import.build_reference(sd)
+    wav = synth.make_waveform(1, 36000, 5, "turns")
+    ref = model.probs(wav)
+    mine = O.probs(sd, wav)
+    for k in ref:
+        assert torch.equal(ref[k], mine[k]), k
