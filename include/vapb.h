@@ -1,0 +1,136 @@
+/*
+ * vapb.h — C-ABI of the B200-native VAP stereo inference forward path.
+ *
+ * The reference (ErikEkstedt/VoiceActivityProjection) has no FFI layer: the
+ * boundary of this path is the Python nn.Module surface of `VapGPT`
+ * (vap/model.py:125-268). This library is what a binding for that surface
+ * calls; voiceactivityprojection_b200/model.py is that binding (ctypes), and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a negative VAPB_E_* code
+ * (vapb_last_error() gives the text). No exceptions, no allocation of caller
+ * visible memory across the ABI: the caller (PyTorch) owns every device buffer,
+ * including the workspace. All device work is enqueued on the caller's stream
+ * and is asynchronous. One handle per device; a handle may be used from several
+ * streams concurrently when the workspaces differ.
+ *
+ * There is no CPU implementation behind this interface.
+ */
+#ifndef VAPB_H_
+#define VAPB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct VapbHandle VapbHandle;
+
+enum {
+  VAPB_OK = 0,
+  VAPB_E_INVALID = -1,   /* bad argument / shape */
+  VAPB_E_STATE = -2,     /* state dict incomplete, unexpected key, wrong call order */
+  VAPB_E_CUDA = -3,      /* CUDA runtime / driver error */
+  VAPB_E_WORKSPACE = -4, /* workspace too small */
+  VAPB_E_UNSUPPORTED = -5
+};
+
+/* Arithmetic mode of the contractions.
+ * FP32: CUDA-core FMA, fp32 activations (parity mode; vap/model.py runs fp32).
+ * BF16: tcgen05 tensor cores, bf16 operands, fp32 accumulate / norms / softmax. */
+enum { VAPB_MODE_FP32 = 0, VAPB_MODE_BF16 = 1 };
+
+/* --- construction: replaces VapGPT.__init__ + load_state_dict (run.py:199-201) */
+
+/* Creates an empty model on CUDA device `device`. */
+int vapb_create(int device, VapbHandle** out);
+
+/* Offers one state-dict entry (reference key schema), host fp32,
+ * contiguous, in the reference's own layout. Copies the data. Unknown keys are
+ * an error (strict load), like nn.Module.load_state_dict (run.py:201). */
+int vapb_load_tensor(VapbHandle* h, const char* key, const float* data, int ndim,
+                     const int64_t* shape);
+
+/* Validates that the state dict is complete, infers the gAR cell (LSTM or GRU)
+ * and depth from the shapes (vap/encoder_components.py:384-391 takes them from
+ * the CPC checkpoint's config, which a VAP state dict does not carry), repacks
+ * the weights into kernel layouts and uploads them. */
+int vapb_finalize(VapbHandle* h);
+
+int vapb_destroy(VapbHandle* h);
+
+/* Text of the last error on this handle (or of the last vapb_create failure
+ * when h is NULL). Valid until the next call on the handle. */
+const char* vapb_last_error(const VapbHandle* h);
+
+/* Model facts after vapb_finalize: ar_kind 0 = LSTM, 1 = GRU. */
+int vapb_describe(const VapbHandle* h, int* ar_kind, int* ar_layers, int* channel_layers,
+                  int* cross_layers, int* num_heads);
+
+/* --- shapes: the zero-padded conv chain of vap/encoder_components.py:83-91 and
+ * the causal stride-2 conv of vap/encoder.py:24-30. frames100 = gAR length,
+ * frames50 = output frames T. */
+int vapb_frames(int64_t n_samples, int64_t* frames100, int64_t* frames50);
+
+/* Bytes of device workspace vapb_forward/vapb_probs need for this shape. */
+int vapb_workspace_bytes(const VapbHandle* h, int batch, int64_t n_samples, int mode,
+                         size_t* bytes);
+
+/* --- the hot path ---------------------------------------------------------- */
+
+/* VapGPT.forward(waveform) (vap/model.py:249-268, attention=False).
+ * wav:        device fp32 (batch, 2, n_samples), contiguous.
+ * logits:     device fp32 (batch, T, 256).
+ * vad_logits: device fp32 (batch, T, 2).
+ * `stream` is a cudaStream_t. */
+int vapb_forward(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples,
+                 int mode, void* workspace, size_t workspace_bytes, float* logits,
+                 float* vad_logits);
+
+/* VapGPT.probs(waveform, now_lims, future_lims) (vap/model.py:180-225), fused
+ * with the forward. Outputs, all device fp32:
+ *   probs (batch,T,256), vad (batch,T,2) = sigmoid, p_now (batch,T,2),
+ *   p_future (batch,T,2), H (batch,T), loss (batch,T-100).
+ * logits / vad_logits / loss may be NULL (skipped). `loss` follows the
+ * reference quirk that labels come from the model's own sigmoid(vad)
+ * (vap/model.py:190,220-224); T must be > 100 when loss is requested.
+ * argmax (nullable): device uint8 (batch,T), argmax class of probs. */
+int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples,
+               int mode, void* workspace, size_t workspace_bytes, int now_lo, int now_hi,
+               int fut_lo, int fut_hi, float* logits, float* vad_logits, float* probs,
+               float* vad, float* p_now, float* p_future, float* H, float* loss,
+               uint8_t* argmax);
+
+/* ObjectiveVAP.get_probs(logits) (vap/objective.py:249-281) and the post-forward
+ * half of VapGPT.probs on logits the caller already has: softmax, p_now,
+ * p_future, entropy, argmax over `rows` frames of 256 logits (device fp32).
+ * Any output may be NULL. */
+int vapb_probs_from_logits(VapbHandle* h, void* stream, const float* logits, int64_t rows, int now_lo,
+                           int now_hi, int fut_lo, int fut_hi, float* probs, float* p_now,
+                           float* p_future, float* H, uint8_t* argmax);
+
+/* --- diagnostics ----------------------------------------------------------- */
+
+/* Copies an intermediate activation of the LAST forward/probs run on
+ * `workspace` (same batch / n_samples / mode) to `out` as fp32.
+ * name: "conv" (2B,T100,256: CPC gEncoder output, channels last),
+ *       "ar" (2B,T100,256: gAR output), "enc" (2B,T,256: encoder output),
+ *       "ch" (2B,T,256: ar_channel output), "ar0".."arN" (2B,T,256: stereo
+ *       layer outputs), "comb" (B,T,256: combinator output).
+ * Sequence index is channel-major: row c*batch + b holds channel c of item b. */
+int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int64_t n_samples,
+                   int mode, void* workspace, size_t workspace_bytes, float* out,
+                   size_t out_elems);
+
+/* Number of kernels this handle has launched since creation. */
+int vapb_launch_count(const VapbHandle* h, uint64_t* launches);
+
+/* Library build facts: "sm_100a" etc. */
+const char* vapb_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAPB_H_ */

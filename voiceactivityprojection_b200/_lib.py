@@ -1,0 +1,70 @@
+"""ctypes binding of libvapb.so (include/vapb.h). There is no fallback: if the
+library has not been built, importing the product path fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvapb.so")
+
+MODE_FP32, MODE_BF16 = 0, 1
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+
+# every symbol include/vapb.h declares: name -> (restype, argtypes)
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+_fp = C.c_void_p  # device pointers travel as integers
+SYMBOLS = {
+    "vapb_create": (_i, [_i, C.POINTER(_vp)]),
+    "vapb_load_tensor": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(_i64)]),
+    "vapb_finalize": (_i, [_vp]),
+    "vapb_destroy": (_i, [_vp]),
+    "vapb_last_error": (C.c_char_p, [_vp]),
+    "vapb_describe": (_i, [_vp] + [C.POINTER(_i)] * 5),
+    "vapb_frames": (_i, [_i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "vapb_workspace_bytes": (_i, [_vp, _i, _i64, _i, C.POINTER(_sz)]),
+    "vapb_forward": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _fp, _fp]),
+    "vapb_probs": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _i, _i, _i, _i] + [_fp] * 9),
+    "vapb_probs_from_logits": (_i, [_vp, _vp, _fp, _i64, _i, _i, _i, _i] + [_fp] * 5),
+    "vapb_get_stage": (_i, [_vp, _vp, C.c_char_p, _i, _i64, _i, _vp, _sz, _fp, _sz]),
+    "vapb_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "vapb_build_info": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(python -m voiceactivityprojection_b200.build). There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class VapbError(RuntimeError):
+    pass
+
+
+def check(lib, handle, rc):
+    if rc != 0:
+        msg = lib.vapb_last_error(handle)
+        raise VapbError(f"vapb error {rc}: {msg.decode() if msg else ''}")
+
+
+def frames(n_samples: int):
+    """(frames @100 Hz, frames @50 Hz) for n_samples (vapb_frames)."""
+    lib = load()
+    a, b = _i64(), _i64()
+    rc = lib.vapb_frames(n_samples, C.byref(a), C.byref(b))
+    if rc != 0:
+        raise VapbError(f"n_samples={n_samples} is too short for the encoder")
+    return a.value, b.value

@@ -1,0 +1,525 @@
+// C-ABI of the library (include/vapb.h): handle, strict state-dict loading and
+// weight repacking, shape arithmetic, and the forward / probs entry points.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+
+#include "../../include/vapb.h"
+#include "model.h"
+
+using namespace vapb;
+
+struct VapbHandle {
+  Model m;
+};
+
+static thread_local std::string g_create_err;
+
+namespace vapb {
+
+int make_geometry(int batch, long long n, Geometry* g) {
+  // vap/encoder_components.py:83-91 (k,s,p) chain, floor division; then the
+  // causal k5 s2 conv with 4 left pad frames (vap/encoder.py:24-30).
+  static const int ksp[5][3] = {{10, 5, 3}, {8, 4, 2}, {4, 2, 1}, {4, 2, 1}, {4, 2, 1}};
+  g->batch = batch;
+  g->nseq = 2 * batch;
+  g->S = n;
+  long long L = n;
+  for (int i = 0; i < 5; ++i) {
+    const long long num = L + 2 * ksp[i][2] - ksp[i][0];
+    if (num < 0) return -1;
+    L = num / ksp[i][1] + 1;
+    g->L[i] = L;
+  }
+  g->T = (L - 1) / 2 + 1;
+  return (L >= 1) ? 0 : -1;
+}
+
+}  // namespace vapb
+
+namespace {
+
+int fail(Model& m, int code, const std::string& msg) {
+  m.err = msg;
+  return code;
+}
+
+#define CUDA_OK(m, call)                                                                           \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail((m), VAPB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+struct Packer {
+  std::vector<char> host;
+  size_t add(const void* src, size_t bytes) {
+    const size_t off = (host.size() + 255) / 256 * 256;
+    host.resize(off + bytes);
+    memcpy(host.data() + off, src, bytes);
+    return off;
+  }
+  size_t add_f(const std::vector<float>& v) { return add(v.data(), v.size() * sizeof(float)); }
+};
+
+// Linear weight (out, in) -> [in][out]
+std::vector<float> transpose_linear(const HostTensor& t) {
+  const int64_t n = t.shape[0], k = t.shape[1];
+  std::vector<float> o((size_t)n * k);
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t j = 0; j < k; ++j) o[(size_t)j * n + i] = t.data[(size_t)i * k + j];
+  return o;
+}
+// several Linear weights side by side along N: [in][sum out]
+std::vector<float> concat_linear(std::vector<const HostTensor*> ts) {
+  const int64_t k = ts[0]->shape[1];
+  int64_t ntot = 0;
+  for (auto* t : ts) ntot += t->shape[0];
+  std::vector<float> o((size_t)ntot * k);
+  int64_t n0 = 0;
+  for (auto* t : ts) {
+    const int64_t n = t->shape[0];
+    for (int64_t i = 0; i < n; ++i)
+      for (int64_t j = 0; j < k; ++j) o[(size_t)j * ntot + n0 + i] = t->data[(size_t)i * k + j];
+    n0 += n;
+  }
+  return o;
+}
+// Conv1d weight (out, in, k) -> [(tap*in + cin)][out]: the GEMM K index runs over
+// a channels-last window of k frames.
+std::vector<float> pack_conv(const HostTensor& t) {
+  const int64_t co = t.shape[0], ci = t.shape[1], k = t.shape[2];
+  std::vector<float> o((size_t)co * ci * k);
+  for (int64_t n = 0; n < co; ++n)
+    for (int64_t c = 0; c < ci; ++c)
+      for (int64_t j = 0; j < k; ++j) o[((size_t)j * ci + c) * co + n] = t.data[((size_t)n * ci + c) * k + j];
+  return o;
+}
+
+std::string shape_str(const std::vector<int64_t>& s) {
+  std::string r = "(";
+  for (size_t i = 0; i < s.size(); ++i) r += (i ? "," : "") + std::to_string(s[i]);
+  return r + ")";
+}
+
+int count_keys(const Model& m, const char* fmt) {
+  int n = 0;
+  char buf[256];
+  for (;;) {
+    snprintf(buf, sizeof buf, fmt, n);
+    if (!m.staged.count(buf)) return n;
+    ++n;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vapb_build_info(void) { return "vapb sm_100a (cuda " "12.9" ") fp32=simt bf16=tcgen05"; }
+
+int vapb_create(int device, VapbHandle** out) {
+  if (!out) return VAPB_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n) {
+    g_create_err = e != cudaSuccess ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)
+                                    : "no such CUDA device " + std::to_string(device);
+    return VAPB_E_CUDA;
+  }
+  VapbHandle* h = new VapbHandle();
+  h->m.device = device;
+  cudaDeviceGetAttribute(&h->m.n_sm, cudaDevAttrMultiProcessorCount, device);
+  *out = h;
+  return VAPB_OK;
+}
+
+const char* vapb_last_error(const VapbHandle* h) { return h ? h->m.err.c_str() : g_create_err.c_str(); }
+
+int vapb_load_tensor(VapbHandle* h, const char* key, const float* data, int ndim, const int64_t* shape) {
+  if (!h || !key || !data || ndim < 0 || ndim > 4) return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (m.finalized) return fail(m, VAPB_E_STATE, "vapb_load_tensor after vapb_finalize");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(data, data + n);
+  m.staged[key] = std::move(t);
+  return VAPB_OK;
+}
+
+int vapb_finalize(VapbHandle* h) {
+  if (!h) return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (m.finalized) return fail(m, VAPB_E_STATE, "already finalized");
+  const std::string AR = "encoder.encoder.gAR.baseNet.";
+  const std::string GE = "encoder.encoder.gEncoder.";
+
+  // ---- structure from the keys / shapes
+  m.ar_layers = count_keys(m, (AR + "weight_ih_l%d").c_str());
+  m.channel_layers = count_keys(m, "ar_channel.layers.%d.ln_self_attn.weight");
+  m.cross_layers = count_keys(m, "ar.layers.%d.ln_self_attn.weight");
+  if (m.ar_layers < 1) return fail(m, VAPB_E_STATE, "missing key " + AR + "weight_ih_l0");
+  if (m.ar_layers > kMaxLayers || m.channel_layers > kMaxLayers || m.cross_layers > kMaxLayers)
+    return fail(m, VAPB_E_UNSUPPORTED, "too many layers");
+  {
+    const auto& s = m.staged[AR + "weight_ih_l0"].shape;
+    if (s.size() != 2 || s[1] != kDim || (s[0] != 4 * kDim && s[0] != 3 * kDim))
+      return fail(m, VAPB_E_STATE, AR + "weight_ih_l0 has shape " + shape_str(s) +
+                                       "; expected (1024,256) [LSTM] or (768,256) [GRU]");
+    m.ar_kind = s[0] == 4 * kDim ? 0 : 1;
+  }
+  const int64_t GH = (m.ar_kind == 0 ? 4 : 3) * kDim;
+  {
+    auto it = m.staged.find(m.channel_layers ? "ar_channel.layers.0.mha.m" : "ar.layers.0.mha.m");
+    m.num_heads = it == m.staged.end() || it->second.shape.size() != 1 ? 0 : (int)it->second.shape[0];
+    if (m.num_heads != 4)
+      return fail(m, VAPB_E_UNSUPPORTED, "num_heads must be 4 (head_dim 64); state dict has " +
+                                             std::to_string(m.num_heads));
+  }
+
+  // ---- strict key/shape check (nn.Module.load_state_dict(strict=True), run.py:201)
+  std::map<std::string, std::vector<int64_t>> want;
+  const int ck[5] = {10, 8, 4, 4, 4};
+  for (int i = 0; i < 5; ++i) {
+    const std::string n = std::to_string(i);
+    want[GE + "conv" + n + ".weight"] = {kDim, i == 0 ? 1 : kDim, ck[i]};
+    want[GE + "conv" + n + ".bias"] = {kDim};
+    want[GE + "batchNorm" + n + ".weight"] = {1, kDim, 1};
+    want[GE + "batchNorm" + n + ".bias"] = {1, kDim, 1};
+  }
+  for (int l = 0; l < m.ar_layers; ++l) {
+    const std::string n = std::to_string(l);
+    want[AR + "weight_ih_l" + n] = {GH, kDim};
+    want[AR + "weight_hh_l" + n] = {GH, kDim};
+    want[AR + "bias_ih_l" + n] = {GH};
+    want[AR + "bias_hh_l" + n] = {GH};
+  }
+  want["encoder.downsample.1.weight"] = {kDim, kDim, 5};
+  want["encoder.downsample.1.bias"] = {kDim};
+  want["encoder.downsample.2.ln.weight"] = {kDim};
+  want["encoder.downsample.2.ln.bias"] = {kDim};
+  auto want_layer = [&](const std::string& p, bool cross) {
+    for (const char* ln : {"ln_self_attn", "ln_ffnetwork", "ln_src_attn"}) {
+      if (!cross && !strcmp(ln, "ln_src_attn")) continue;
+      want[p + ln + ".weight"] = {kDim};
+      want[p + ln + ".bias"] = {kDim};
+    }
+    for (const char* a : {"mha", "mha_cross"}) {
+      if (!cross && !strcmp(a, "mha_cross")) continue;
+      want[p + a + ".m"] = {m.num_heads};
+      for (const char* w : {"key", "query", "value", "proj"}) want[p + a + "." + w + ".weight"] = {kDim, kDim};
+    }
+    want[p + "ffnetwork.0.weight"] = {kFfn, kDim};
+    want[p + "ffnetwork.3.weight"] = {kDim, kFfn};
+  };
+  for (int l = 0; l < m.channel_layers; ++l) want_layer("ar_channel.layers." + std::to_string(l) + ".", false);
+  for (int l = 0; l < m.cross_layers; ++l) want_layer("ar.layers." + std::to_string(l) + ".", true);
+  want["ar.combinator.h0_a.weight"] = {kDim, kDim};
+  want["ar.combinator.h0_b.weight"] = {kDim, kDim};
+  want["ar.combinator.ln.weight"] = {kDim};
+  want["ar.combinator.ln.bias"] = {kDim};
+  want["objective.codebook.emb.weight"] = {kClasses, 8};
+  want["va_classifier.weight"] = {1, kDim};
+  want["va_classifier.bias"] = {1};
+  want["vap_head.weight"] = {kClasses, kDim};
+  want["vap_head.bias"] = {kClasses};
+
+  std::string missing, unexpected, badshape;
+  for (auto& kv : want) {
+    auto it = m.staged.find(kv.first);
+    if (it == m.staged.end()) missing += " " + kv.first;
+    else if (it->second.shape != kv.second)
+      badshape += " " + kv.first + shape_str(it->second.shape) + "!=" + shape_str(kv.second);
+  }
+  for (auto& kv : m.staged)
+    if (!want.count(kv.first)) unexpected += " " + kv.first;
+  if (!missing.empty() || !unexpected.empty() || !badshape.empty()) {
+    std::string msg = "Error(s) in loading state_dict for VapGPT:";
+    if (!missing.empty()) msg += " Missing key(s):" + missing + ".";
+    if (!unexpected.empty()) msg += " Unexpected key(s):" + unexpected + ".";
+    if (!badshape.empty()) msg += " size mismatch:" + badshape + ".";
+    return fail(m, VAPB_E_STATE, msg);
+  }
+  {  // the kernels hard-code the codebook's bit semantics (vap/objective.py:93-110)
+    const auto& cb = m.staged["objective.codebook.emb.weight"].data;
+    for (int c = 0; c < kClasses; ++c)
+      for (int b = 0; b < 8; ++b)
+        if (cb[c * 8 + b] != (float)((c >> b) & 1))
+          return fail(m, VAPB_E_UNSUPPORTED, "objective.codebook.emb.weight is not the LSB-first bit table");
+  }
+
+  // ---- repack (fp32 path) into one arena
+  auto T = [&](const std::string& k) -> const HostTensor& { return m.staged[k]; };
+  Packer pk;
+  struct Fix { const void** slot; size_t off; };
+  std::vector<Fix> fixes;
+  auto put = [&](const void** slot, const std::vector<float>& v) { fixes.push_back({slot, pk.add_f(v)}); };
+  auto putf = [&](const float** slot, const std::vector<float>& v) {
+    fixes.push_back({reinterpret_cast<const void**>(slot), pk.add_f(v)});
+  };
+  Weights& w = m.w32;
+  {
+    const HostTensor& c0 = T(GE + "conv0.weight");  // (256,1,10) -> [10][256]
+    std::vector<float> v(10 * kDim);
+    for (int c = 0; c < kDim; ++c)
+      for (int k = 0; k < 10; ++k) v[k * kDim + c] = c0.data[c * 10 + k];
+    putf(&w.c0_w, v);
+    putf(&w.c0_b, T(GE + "conv0.bias").data);
+    putf(&w.c0_g, T(GE + "batchNorm0.weight").data);
+    putf(&w.c0_be, T(GE + "batchNorm0.bias").data);
+  }
+  for (int i = 1; i < 5; ++i) {
+    const std::string n = std::to_string(i);
+    put(&w.conv_w[i], pack_conv(T(GE + "conv" + n + ".weight")));
+    putf(&w.conv_b[i], T(GE + "conv" + n + ".bias").data);
+    putf(&w.conv_g[i], T(GE + "batchNorm" + n + ".weight").data);
+    putf(&w.conv_be[i], T(GE + "batchNorm" + n + ".bias").data);
+  }
+  for (int l = 0; l < m.ar_layers; ++l) {
+    const std::string n = std::to_string(l);
+    put(&w.rnn_wih[l], transpose_linear(T(AR + "weight_ih_l" + n)));
+    putf(&w.rnn_whh_t[l], transpose_linear(T(AR + "weight_hh_l" + n)));
+    const auto& bi = T(AR + "bias_ih_l" + n).data;
+    const auto& bh = T(AR + "bias_hh_l" + n).data;
+    std::vector<float> bx(GH), bhn(kDim, 0.f);
+    for (int64_t i = 0; i < GH; ++i) bx[i] = bi[i] + bh[i];
+    if (m.ar_kind == 1)
+      for (int j = 0; j < kDim; ++j) {
+        bx[2 * kDim + j] = bi[2 * kDim + j];  // n gate: b_hn stays inside r*(...)
+        bhn[j] = bh[2 * kDim + j];
+      }
+    putf(&w.rnn_bx[l], bx);
+    putf(&w.rnn_bhn[l], bhn);
+  }
+  put(&w.ds_w, pack_conv(T("encoder.downsample.1.weight")));
+  putf(&w.ds_b, T("encoder.downsample.1.bias").data);
+  putf(&w.ds_g, T("encoder.downsample.2.ln.weight").data);
+  putf(&w.ds_be, T("encoder.downsample.2.ln.bias").data);
+  auto pack_layer = [&](const std::string& p, bool cross, LayerW& lw) {
+    putf(&lw.ln_sa_g, T(p + "ln_self_attn.weight").data);
+    putf(&lw.ln_sa_b, T(p + "ln_self_attn.bias").data);
+    putf(&lw.ln_ffn_g, T(p + "ln_ffnetwork.weight").data);
+    putf(&lw.ln_ffn_b, T(p + "ln_ffnetwork.bias").data);
+    putf(&lw.slopes, T(p + "mha.m").data);
+    put(&lw.wqkv, concat_linear({&T(p + "mha.query.weight"), &T(p + "mha.key.weight"), &T(p + "mha.value.weight")}));
+    put(&lw.wproj, transpose_linear(T(p + "mha.proj.weight")));
+    if (cross) {
+      putf(&lw.ln_src_g, T(p + "ln_src_attn.weight").data);
+      putf(&lw.ln_src_b, T(p + "ln_src_attn.bias").data);
+      putf(&lw.slopes_cross, T(p + "mha_cross.m").data);
+      put(&lw.wq_c, transpose_linear(T(p + "mha_cross.query.weight")));
+      put(&lw.wkv_c, concat_linear({&T(p + "mha_cross.key.weight"), &T(p + "mha_cross.value.weight")}));
+      put(&lw.wproj_c, transpose_linear(T(p + "mha_cross.proj.weight")));
+    }
+    put(&lw.w1, transpose_linear(T(p + "ffnetwork.0.weight")));
+    put(&lw.w2, transpose_linear(T(p + "ffnetwork.3.weight")));
+  };
+  for (int l = 0; l < m.channel_layers; ++l) pack_layer("ar_channel.layers." + std::to_string(l) + ".", false, w.chan[l]);
+  for (int l = 0; l < m.cross_layers; ++l) pack_layer("ar.layers." + std::to_string(l) + ".", true, w.cross[l]);
+  put(&w.comb_a, transpose_linear(T("ar.combinator.h0_a.weight")));
+  put(&w.comb_b, transpose_linear(T("ar.combinator.h0_b.weight")));
+  putf(&w.comb_g, T("ar.combinator.ln.weight").data);
+  putf(&w.comb_be, T("ar.combinator.ln.bias").data);
+  putf(&w.va_w, T("va_classifier.weight").data);
+  putf(&w.va_b, T("va_classifier.bias").data);
+  put(&w.head_w, transpose_linear(T("vap_head.weight")));
+  putf(&w.head_b, T("vap_head.bias").data);
+
+  CUDA_OK(m, cudaSetDevice(m.device));
+  m.arena_bytes = pk.host.size();
+  CUDA_OK(m, cudaMalloc(&m.arena, m.arena_bytes));
+  CUDA_OK(m, cudaMemcpy(m.arena, pk.host.data(), m.arena_bytes, cudaMemcpyHostToDevice));
+  for (auto& f : fixes) *f.slot = static_cast<char*>(m.arena) + f.off;
+
+  const int rc = bf16_prepare(m);
+  if (rc != 0) return rc;
+  m.finalized = true;
+  m.staged.clear();
+  return VAPB_OK;
+}
+
+int vapb_destroy(VapbHandle* h) {
+  if (!h) return VAPB_OK;
+  bf16_release(h->m);
+  if (h->m.arena) cudaFree(h->m.arena);
+  delete h;
+  return VAPB_OK;
+}
+
+int vapb_describe(const VapbHandle* h, int* ar_kind, int* ar_layers, int* channel_layers, int* cross_layers,
+                  int* num_heads) {
+  if (!h || !h->m.finalized) return VAPB_E_STATE;
+  if (ar_kind) *ar_kind = h->m.ar_kind;
+  if (ar_layers) *ar_layers = h->m.ar_layers;
+  if (channel_layers) *channel_layers = h->m.channel_layers;
+  if (cross_layers) *cross_layers = h->m.cross_layers;
+  if (num_heads) *num_heads = h->m.num_heads;
+  return VAPB_OK;
+}
+
+int vapb_frames(int64_t n_samples, int64_t* frames100, int64_t* frames50) {
+  Geometry g;
+  if (n_samples < 1 || make_geometry(1, n_samples, &g) != 0) return VAPB_E_INVALID;
+  if (frames100) *frames100 = g.L[4];
+  if (frames50) *frames50 = g.T;
+  return VAPB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct Aux {  // api-level scratch appended to the path workspace
+  size_t logits, vad_sig, lse, bytes;
+};
+
+int plan_all(const Model& m, int batch, int64_t n_samples, int mode, Geometry* g, size_t* path_bytes, Aux* aux,
+             std::string* err) {
+  if (batch < 1 || batch > 16384) { *err = "batch out of range"; return VAPB_E_INVALID; }
+  if (mode != VAPB_MODE_FP32 && mode != VAPB_MODE_BF16) { *err = "unknown mode"; return VAPB_E_INVALID; }
+  if (n_samples < 1 || make_geometry(batch, n_samples, g) != 0 || g->T < 1) {
+    *err = "n_samples too small for the conv chain";
+    return VAPB_E_INVALID;
+  }
+  if ((long long)g->nseq * g->L[1] > 2000000000LL) { *err = "batch * n_samples too large for one call"; return VAPB_E_INVALID; }
+  *path_bytes = mode == VAPB_MODE_FP32 ? workspace_bytes_fp32(m, *g) : workspace_bytes_bf16(m, *g);
+  if (*path_bytes == 0) { *err = "mode not available in this build"; return VAPB_E_UNSUPPORTED; }
+  size_t off = (*path_bytes + 1023) / 1024 * 1024;
+  const size_t rows = (size_t)batch * g->T;
+  aux->logits = off;  off += (rows * kClasses * 4 + 1023) / 1024 * 1024;
+  aux->vad_sig = off; off += (rows * 2 * 4 + 1023) / 1024 * 1024;
+  aux->lse = off;     off += (rows * 4 + 1023) / 1024 * 1024;
+  aux->bytes = off;
+  return 0;
+}
+
+int run_forward(Model& m, cudaStream_t st, const float* wav, const Geometry& g, int mode, char* ws, float* logits,
+                float* vad_logits, float* vad_sig) {
+  const float* comb = nullptr;
+  return mode == VAPB_MODE_FP32 ? forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb)
+                                : forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vapb_workspace_bytes(const VapbHandle* h, int batch, int64_t n_samples, int mode, size_t* bytes) {
+  if (!h || !bytes) return VAPB_E_INVALID;
+  Model& m = const_cast<Model&>(h->m);
+  if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
+  Geometry g;
+  size_t pb;
+  Aux aux;
+  std::string err;
+  const int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  if (rc) return fail(m, rc, err);
+  *bytes = aux.bytes;
+  return VAPB_OK;
+}
+
+int vapb_forward(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples, int mode,
+                 void* workspace, size_t workspace_bytes, float* logits, float* vad_logits) {
+  if (!h || !wav || !workspace || !logits || !vad_logits) return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
+  Geometry g;
+  size_t pb;
+  Aux aux;
+  std::string err;
+  int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  if (rc) return fail(m, rc, err);
+  if (workspace_bytes < aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  CUDA_OK(m, cudaSetDevice(m.device));
+  rc = run_forward(m, (cudaStream_t)stream, wav, g, mode, (char*)workspace, logits, vad_logits, nullptr);
+  if (rc) return rc;
+  CUDA_OK(m, cudaPeekAtLastError());
+  return VAPB_OK;
+}
+
+int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples, int mode,
+               void* workspace, size_t workspace_bytes, int now_lo, int now_hi, int fut_lo, int fut_hi,
+               float* logits, float* vad_logits, float* probs, float* vad, float* p_now, float* p_future, float* H,
+               float* loss, uint8_t* argmax) {
+  if (!h || !wav || !workspace) return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
+  if (now_lo < 0 || now_hi > 3 || now_lo > now_hi || fut_lo < 0 || fut_hi > 3 || fut_lo > fut_hi)
+    return fail(m, VAPB_E_INVALID, "bin limits must satisfy 0 <= lo <= hi <= 3");
+  Geometry g;
+  size_t pb;
+  Aux aux;
+  std::string err;
+  int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  if (rc) return fail(m, rc, err);
+  if (workspace_bytes < aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  if (loss && g.T <= 100)
+    return fail(m, VAPB_E_INVALID, "loss needs more than 100 frames (maximum size for tensor at dimension 1 is " +
+                                       std::to_string(g.T - 1) + " but size is 100)");
+  CUDA_OK(m, cudaSetDevice(m.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* lg = logits ? logits : reinterpret_cast<float*>(ws + aux.logits);
+  float* vs = vad ? vad : reinterpret_cast<float*>(ws + aux.vad_sig);
+  float* lse = reinterpret_cast<float*>(ws + aux.lse);
+  rc = run_forward(m, st, wav, g, mode, ws, lg, vad_logits, vs);
+  if (rc) return rc;
+  const long long rows = (long long)batch * g.T;
+  m.launches += launch_probs(st, lg, rows, now_lo, now_hi, fut_lo, fut_hi, probs, p_now, p_future, H,
+                             loss ? lse : nullptr, argmax);
+  if (loss) m.launches += launch_loss(st, lg, vs, lse, batch, (int)g.T, loss);
+  CUDA_OK(m, cudaPeekAtLastError());
+  return VAPB_OK;
+}
+
+int vapb_probs_from_logits(VapbHandle* h, void* stream, const float* logits, int64_t rows, int now_lo, int now_hi,
+                           int fut_lo, int fut_hi, float* probs, float* p_now, float* p_future, float* H,
+                           uint8_t* argmax) {
+  if (!h || !logits || rows < 0) return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (now_lo < 0 || now_hi > 3 || now_lo > now_hi || fut_lo < 0 || fut_hi > 3 || fut_lo > fut_hi)
+    return fail(m, VAPB_E_INVALID, "bin limits must satisfy 0 <= lo <= hi <= 3");
+  if (rows == 0) return VAPB_OK;
+  CUDA_OK(m, cudaSetDevice(m.device));
+  m.launches += launch_probs((cudaStream_t)stream, logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs, p_now,
+                             p_future, H, nullptr, argmax);
+  CUDA_OK(m, cudaPeekAtLastError());
+  return VAPB_OK;
+}
+
+int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int64_t n_samples, int mode,
+                   void* workspace, size_t workspace_bytes, float* out, size_t out_elems) {
+  if (!h || !name || !workspace || !out) return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
+  Geometry g;
+  size_t pb;
+  Aux aux;
+  std::string err;
+  int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  if (rc) return fail(m, rc, err);
+  if (workspace_bytes < aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  StageRef ref{};
+  rc = mode == VAPB_MODE_FP32 ? stage_fp32(m, g, (char*)workspace, name, &ref)
+                              : stage_bf16(m, g, (char*)workspace, name, &ref);
+  if (rc) return fail(m, VAPB_E_INVALID, std::string("unknown stage ") + name);
+  if (out_elems < (size_t)ref.nseq * ref.rows_per_seq * kDim) return fail(m, VAPB_E_INVALID, "stage output too small");
+  CUDA_OK(m, cudaSetDevice(m.device));
+  m.launches += launch_to_f32((cudaStream_t)stream, ref.ptr, ref.is_bf16, ref.map, ref.nseq, ref.rows_per_seq, out);
+  CUDA_OK(m, cudaPeekAtLastError());
+  return VAPB_OK;
+}
+
+int vapb_launch_count(const VapbHandle* h, uint64_t* launches) {
+  if (!h || !launches) return VAPB_E_INVALID;
+  *launches = h->m.launches;
+  return VAPB_OK;
+}
+
+}  // extern "C"

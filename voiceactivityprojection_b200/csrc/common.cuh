@@ -1,0 +1,108 @@
+// Shared declarations of the vapb kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vapb {
+
+constexpr int kDim = 256;       // model dim == CPC hidden (vap/model.py:53)
+constexpr int kClasses = 256;   // 2^8 projection-window states (vap/objective.py:84)
+constexpr float kEps = 1e-5f;
+
+enum Norm { NORM_NONE = 0, NORM_CHANNEL = 1 /* unbiased var, /255 */, NORM_LAYER = 2 /* biased, /256 */ };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// Row addressing shared by every GEMM-shaped kernel: logical row m maps to
+// (seq, t) = (m / rows_per_seq, m % rows_per_seq) and the row's first element
+// lives at base + seq*seq_stride + t*row_stride (element units).
+struct RowMap {
+  long long seq_stride;
+  long long row_stride;
+};
+
+// Epilogue of a GEMM whose CTA tile spans the whole N=256 row.
+struct Epilogue {
+  const float* bias;   // [N] or null
+  int norm1;           // Norm applied to (acc + bias)
+  const float* g1;     // norm1 affine weight [256]
+  const float* b1;     // norm1 affine bias   [256]
+  int act;             // Act
+  const float* resid;  // fp32 residual rows or null
+  RowMap resid_map;
+  int accumulate;      // out1 += value (combinator's second branch)
+  void* out1;          // fp32 or bf16 (out1_bf16)
+  int out1_bf16;
+  RowMap out1_map;
+  int norm2;           // LayerNorm of the out1 value -> out2 (next op's input)
+  const float* g2;
+  const float* b2;
+  void* out2;
+  int out2_bf16;
+  RowMap out2_map;
+};
+
+struct GemmProblem {
+  const void* A;       // fp32 (SIMT path) or bf16 (tensor path), rows addressed by a_map
+  RowMap a_map;
+  const void* W;       // packed weights, [K][N] fp32 (SIMT path)
+  int M;               // logical rows = n_seq * rows_per_seq
+  int rows_per_seq;
+  int N;
+  int K;
+};
+
+// ---- launchers (each returns the number of kernels it launched) -------------
+int launch_conv0(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq,
+                 long long L0, const float* w /*[10][256]*/, const float* bias, const float* g,
+                 const float* b, void* out, int out_bf16, long long out_seq_stride /*elements*/,
+                 int out_pad_rows);
+
+int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
+
+int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
+                     long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence
+
+int launch_attention_f32(cudaStream_t st, const float* q, long long q_row_stride, const float* k,
+                         const float* v, long long kv_row_stride, float* out, int nseq, int T, int n_heads,
+                         const float* slopes, int kv_seq_xor_half /* cross: K/V of seq (s+nseq/2)%nseq */);
+
+int launch_rnn_f32(cudaStream_t st, int kind /*0 LSTM 1 GRU*/, const float* xproj /*[nseq][T][G*256]*/,
+                   const float* whh_t /*[256][G*256]*/, const float* bhn /*GRU b_hn [256] or null*/,
+                   float* out, long long out_seq_stride, int nseq, int T);
+
+int launch_vad_head(cudaStream_t st, const float* x /*[2B][T][256] channel-major*/, const float* w,
+                    const float* b, int batch, int T, float* vad_logits /*(B,T,2) or null*/,
+                    float* vad_sig /*(B,T,2) or null*/);
+
+int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
+                 int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse,
+                 uint8_t* argmax);
+
+int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, const float* lse, int batch,
+                int T, float* loss);
+
+int launch_to_f32(cudaStream_t st, const void* src, int src_bf16, RowMap src_map, int nseq,
+                  int rows_per_seq, float* dst);
+
+// ---- small device helpers ----------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU() default (exact erf)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_GELU) return gelu_erf(v);
+  return v;
+}
+
+}  // namespace vapb

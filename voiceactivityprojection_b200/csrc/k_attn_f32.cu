@@ -1,0 +1,168 @@
+// FP32 (parity mode) fused causal ALiBi attention, flash-style on CUDA cores.
+// Reference: vap/modules.py:82-110 (scores, softmax, PV), :169-202 (the bias that
+// is actually added: 1.0 + m_h * j on allowed positions, -inf above the diagonal;
+// SURVEY.md F8), :52 (scale = 1/sqrt(dim) = 1/16, not 1/sqrt(head_dim); F7).
+// Self- and cross-attention share this kernel; cross-attention reads K/V rows of
+// the other speaker channel's sequence (vap/modules.py:287-289).
+//
+// One CTA = 64 queries of one (sequence, head); K/V stream through shared memory
+// in 64-key tiles up to the diagonal; the T x T score matrix never exists.
+#include "common.cuh"
+
+namespace vapb {
+
+constexpr int AQ = 64, AK = 64, AD = 64, ALD = 68, ATHREADS = 256;
+constexpr int ATT_SMEM = (AQ * ALD + AK * ALD + AK * AD + AQ * ALD) * 4;
+
+__global__ void __launch_bounds__(ATHREADS)
+attention_f32_kernel(const float* __restrict__ q, long long q_row_stride, const float* __restrict__ k,
+                     const float* __restrict__ v, long long kv_row_stride, float* __restrict__ out, int nseq,
+                     int T, const float* __restrict__ slopes, int cross) {
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;               // [AQ][ALD]
+  float* Ks = Qs + AQ * ALD;      // [AK][ALD]
+  float* Vs = Ks + AK * ALD;      // [AK][AD]
+  float* Ps = Vs + AK * AD;       // [AQ][ALD]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int kvseq = cross ? (seq + nseq / 2) % nseq : seq;
+  const float slope = slopes[head];
+  const float* qb = q + ((long long)seq * T) * q_row_stride + head * AD;
+  const float* kb = k + ((long long)kvseq * T) * kv_row_stride + head * AD;
+  const float* vb = v + ((long long)kvseq * T) * kv_row_stride + head * AD;
+  const int q0 = qt * AQ;
+
+  for (int idx = tid; idx < AQ * AD / 4; idx += ATHREADS) {
+    const int r = idx >> 4, d4 = (idx & 15) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) x = *reinterpret_cast<const float4*>(qb + (long long)(q0 + r) * q_row_stride + d4);
+    *reinterpret_cast<float4*>(&Qs[r * ALD + d4]) = x;
+  }
+
+  float o[4][4], mrow[4], lrow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    mrow[i] = -INFINITY;
+    lrow[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[i][c] = 0.f;
+  }
+
+  for (int kt = 0; kt <= qt; ++kt) {
+    const int k0 = kt * AK;
+    __syncthreads();  // previous tile's readers are done (also orders the Q stores)
+    for (int idx = tid; idx < AK * AD / 4; idx += ATHREADS) {
+      const int r = idx >> 4, d4 = (idx & 15) * 4;
+      float4 kx = make_float4(0.f, 0.f, 0.f, 0.f), vx = kx;
+      if (k0 + r < T) {
+        kx = *reinterpret_cast<const float4*>(kb + (long long)(k0 + r) * kv_row_stride + d4);
+        vx = *reinterpret_cast<const float4*>(vb + (long long)(k0 + r) * kv_row_stride + d4);
+      }
+      *reinterpret_cast<float4*>(&Ks[r * ALD + d4]) = kx;
+      *reinterpret_cast<float4*>(&Vs[r * AD + d4]) = vx;
+    }
+    __syncthreads();
+
+    // S[i][j]: query ty*4+i, key tx+16*j
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < AD; d4 += 4) {
+      float4 qf[4], kf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qf[i] = *reinterpret_cast<const float4*>(&Qs[(ty * 4 + i) * ALD + d4]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kf[j] = *reinterpret_cast<const float4*>(&Ks[(tx + 16 * j) * ALD + d4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] = fmaf(qf[i].x, kf[j].x, s[i][j]);
+          s[i][j] = fmaf(qf[i].y, kf[j].y, s[i][j]);
+          s[i][j] = fmaf(qf[i].z, kf[j].z, s[i][j]);
+          s[i][j] = fmaf(qf[i].w, kf[j].w, s[i][j]);
+        }
+    }
+    // scale, ALiBi bias (1.0 + m*j, the reference's form), causal mask, online softmax
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int qi = q0 + ty * 4 + i;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kj = k0 + tx + 16 * j;
+        const float bias = __fadd_rn(__fmul_rn(slope, (float)kj), 1.0f);  // (m*j) + 1, no FMA contraction
+        float x = s[i][j] * 0.0625f + bias;
+        if (kj > qi || kj >= T) x = -INFINITY;
+        s[i][j] = x;
+        mx = fmaxf(mx, x);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float mnew = fmaxf(mrow[i], mx);  // finite: key 0 is visible to every query in tile 0
+      const float alpha = expf(mrow[i] - mnew);
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pij = expf(s[i][j] - mnew);
+        ps += pij;
+        Ps[(ty * 4 + i) * ALD + tx + 16 * j] = pij;
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      lrow[i] = lrow[i] * alpha + ps;
+      mrow[i] = mnew;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[i][c] *= alpha;
+    }
+    __syncthreads();
+    // O[i][c] += sum_key P[q][key] * V[key][tx*4+c]
+#pragma unroll 4
+    for (int k4 = 0; k4 < AK; k4 += 4) {
+      float4 pf[4], vf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pf[i] = *reinterpret_cast<const float4*>(&Ps[(ty * 4 + i) * ALD + k4]);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) vf[kk] = *reinterpret_cast<const float4*>(&Vs[(k4 + kk) * AD + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pv[4] = {pf[i].x, pf[i].y, pf[i].z, pf[i].w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          o[i][0] = fmaf(pv[kk], vf[kk].x, o[i][0]);
+          o[i][1] = fmaf(pv[kk], vf[kk].y, o[i][1]);
+          o[i][2] = fmaf(pv[kk], vf[kk].z, o[i][2]);
+          o[i][3] = fmaf(pv[kk], vf[kk].w, o[i][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + ty * 4 + i;
+    if (qi < T) {
+      const float inv = 1.0f / lrow[i];
+      *reinterpret_cast<float4*>(out + ((long long)seq * T + qi) * kDim + head * AD + tx * 4) =
+          make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+    }
+  }
+}
+
+int launch_attention_f32(cudaStream_t st, const float* q, long long q_row_stride, const float* k, const float* v,
+                         long long kv_row_stride, float* out, int nseq, int T, int n_heads, const float* slopes,
+                         int cross) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    configured = true;
+  }
+  dim3 grid((unsigned)((T + AQ - 1) / AQ), (unsigned)n_heads, (unsigned)nseq);
+  attention_f32_kernel<<<grid, ATHREADS, ATT_SMEM, st>>>(q, q_row_stride, k, v, kv_row_stride, out, nseq, T,
+                                                         slopes, cross);
+  return 1;
+}
+
+}  // namespace vapb

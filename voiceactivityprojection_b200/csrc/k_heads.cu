@@ -1,0 +1,157 @@
+// Output heads of VapGPT.probs: bandwidth-bound, one warp per frame.
+// Reference: vap/model.py:258-260 (va_classifier on x1, x2, concatenated),
+// :189-210 (softmax, sigmoid, H = -sum p log2 p, p_now / p_future),
+// vap/objective.py:184-204 (codebook marginalisation, p / (sum + 1e-5)),
+// :93-110 (class index -> 8 bits, LSB first; bits 0-3 speaker 0 bins 0-3,
+// bits 4-7 speaker 1), :53-72,112-139,209-243 (labels from the model's own
+// sigmoid(vad), per-frame cross entropy).
+#include "common.cuh"
+
+namespace vapb {
+
+// vad_logits[b,t,c] = dot(x[c*B+b, t, :], w) + bias ; vad = sigmoid
+__global__ void __launch_bounds__(256)
+vad_head_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int batch,
+                int T, float* __restrict__ vad_logits, float* __restrict__ vad_sig) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);  // over (2B * T)
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)2 * batch * T) return;
+  const float* xr = x + row * kDim;
+  const float4 a0 = *reinterpret_cast<const float4*>(xr + lane * 4);
+  const float4 a1 = *reinterpret_cast<const float4*>(xr + 128 + lane * 4);
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + lane * 4));
+  const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + 128 + lane * 4));
+  float s = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y + a1.z * w1.z +
+            a1.w * w1.w;
+  s = warp_sum(s) + bias[0];
+  if (lane == 0) {
+    const long long seq = row / T, t = row % T;
+    const long long c = seq / batch, b = seq % batch;
+    const long long o = (b * T + t) * 2 + c;
+    if (vad_logits) vad_logits[o] = s;
+    if (vad_sig) vad_sig[o] = 1.0f / (1.0f + expf(-s));
+  }
+}
+
+int launch_vad_head(cudaStream_t st, const float* x, const float* w, const float* b, int batch, int T,
+                    float* vad_logits, float* vad_sig) {
+  const long long rows = (long long)2 * batch * T;
+  vad_head_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w, b, batch, T, vad_logits, vad_sig);
+  return 1;
+}
+
+// One warp per frame; lane owns classes lane*4..+3 and 128+lane*4..+3.
+__global__ void __launch_bounds__(256)
+probs_kernel(const float* __restrict__ logits, long long rows, int now_lo, int now_hi, int fut_lo, int fut_hi,
+             float* __restrict__ probs, float* __restrict__ p_now, float* __restrict__ p_future,
+             float* __restrict__ H, float* __restrict__ lse, uint8_t* __restrict__ argmax) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* lr = logits + row * kClasses;
+  const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
+  const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
+  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  float mx = v[0];
+  int best = 0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j)
+    if (v[j] > mx) { mx = v[j]; best = j; }
+  int bidx = (best < 4 ? 0 : 128) + lane * 4 + (best & 3);
+  // warp argmax, first index wins ties (torch.argmax semantics on CPU)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+    if (om > mx || (om == mx && oi < bidx)) { mx = om; bidx = oi; }
+  }
+  float e[8], s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    e[j] = expf(v[j] - mx);
+    s += e[j];
+  }
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  float h = 0.f, pn0 = 0.f, pn1 = 0.f, pf0 = 0.f, pf1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float p = e[j] * inv;
+    e[j] = p;
+    h -= p * log2f(p);  // NaN when p underflows to 0, like the reference (model.py:201)
+    const int cls = (j < 4 ? 0 : 128) + lane * 4 + (j & 3);
+    int n0 = 0, n1 = 0, f0 = 0, f1 = 0;
+    for (int b = now_lo; b <= now_hi; ++b) { n0 += (cls >> b) & 1; n1 += (cls >> (4 + b)) & 1; }
+    for (int b = fut_lo; b <= fut_hi; ++b) { f0 += (cls >> b) & 1; f1 += (cls >> (4 + b)) & 1; }
+    pn0 = fmaf(p, (float)n0, pn0); pn1 = fmaf(p, (float)n1, pn1);
+    pf0 = fmaf(p, (float)f0, pf0); pf1 = fmaf(p, (float)f1, pf1);
+  }
+  h = warp_sum(h);
+  pn0 = warp_sum(pn0); pn1 = warp_sum(pn1);
+  pf0 = warp_sum(pf0); pf1 = warp_sum(pf1);
+  if (probs) {
+    float* pr = probs + row * kClasses;
+    *reinterpret_cast<float4*>(pr + lane * 4) = make_float4(e[0], e[1], e[2], e[3]);
+    *reinterpret_cast<float4*>(pr + 128 + lane * 4) = make_float4(e[4], e[5], e[6], e[7]);
+  }
+  if (lane == 0) {
+    if (H) H[row] = h;
+    if (p_now) {
+      const float d = (pn0 + pn1) + 1e-5f;
+      p_now[row * 2] = pn0 / d;
+      p_now[row * 2 + 1] = pn1 / d;
+    }
+    if (p_future) {
+      const float d = (pf0 + pf1) + 1e-5f;
+      p_future[row * 2] = pf0 / d;
+      p_future[row * 2 + 1] = pf1 / d;
+    }
+    if (lse) lse[row] = mx + logf(s);
+    if (argmax) argmax[row] = (uint8_t)bidx;
+  }
+}
+
+int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
+                 int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse, uint8_t* argmax) {
+  probs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs,
+                                                           p_now, p_future, H, lse, argmax);
+  return 1;
+}
+
+// loss[b,t] = logsumexp(logits[b,t]) - logits[b,t,label], t < T-100, where the
+// label packs 8 bits: bit (4*c + bin) = mean(vad[b, t+1+start : t+1+end, c]) >= 0.5
+// over bins of 10/20/30/40 frames.
+__global__ void __launch_bounds__(128)
+loss_kernel(const float* __restrict__ logits, const float* __restrict__ vad, const float* __restrict__ lse,
+            int batch, int T, float* __restrict__ loss) {
+  const int n = T - 100;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)batch * n) return;
+  const long long b = i / n, t = i % n;
+  const float* vb = vad + (b * T + t + 1) * 2;
+  const int bins[4] = {10, 20, 30, 40};
+  int label = 0, start = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int f = start; f < start + bins[k]; ++f) {
+      const float2 x = *reinterpret_cast<const float2*>(vb + 2 * f);
+      s0 += x.x;
+      s1 += x.y;
+    }
+    if (s0 / (float)bins[k] >= 0.5f) label |= 1 << k;
+    if (s1 / (float)bins[k] >= 0.5f) label |= 1 << (4 + k);
+    start += bins[k];
+  }
+  loss[i] = lse[b * T + t] - logits[(b * T + t) * kClasses + label];
+}
+
+int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, const float* lse, int batch, int T,
+                float* loss) {
+  const long long n = (long long)batch * (T - 100);
+  if (n <= 0) return 0;
+  loss_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(logits, vad_sig, lse, batch, T, loss);
+  return 1;
+}
+
+}  // namespace vapb

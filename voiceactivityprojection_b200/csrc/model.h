@@ -1,0 +1,94 @@
+// Internal model / plan structures shared by api.cu and the two forward paths.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vapb {
+
+constexpr int kMaxLayers = 16;
+constexpr int kFfn = 768;
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+// One dtype's packed weights (device pointers into the arena). T = float or bf16.
+struct LayerW {
+  const float *ln_sa_g, *ln_sa_b, *ln_ffn_g, *ln_ffn_b, *ln_src_g, *ln_src_b;
+  const float *slopes, *slopes_cross;
+  const void *wqkv;     // [256][768]  (q | k | v)
+  const void *wproj;    // [256][256]
+  const void *wq_c;     // [256][256]
+  const void *wkv_c;    // [256][512]  (k | v)
+  const void *wproj_c;  // [256][256]
+  const void *w1;       // [256][768]
+  const void *w2;       // [768][256]
+};
+
+struct Weights {
+  // conv0 (always fp32: it runs on CUDA cores)
+  const float *c0_w, *c0_b, *c0_g, *c0_be;
+  const void *conv_w[5];                    // [k*256][256], index 1..4
+  const float *conv_b[5], *conv_g[5], *conv_be[5];
+  const void *rnn_wih[kMaxLayers];          // [256][G*256]
+  const float *rnn_bx[kMaxLayers];          // b_ih + b_hh (GRU: n gate gets b_in only)
+  const float *rnn_whh_t[kMaxLayers];       // fp32 [256][G*256]
+  const float *rnn_bhn[kMaxLayers];         // GRU b_hn
+  const void *ds_w;                         // [5*256][256]
+  const float *ds_b, *ds_g, *ds_be;
+  LayerW chan[kMaxLayers], cross[kMaxLayers];
+  const void *comb_a, *comb_b;              // [256][256]
+  const float *comb_g, *comb_be;
+  const float *va_w, *va_b;
+  const void *head_w;                       // [256][256]
+  const float *head_b;
+};
+
+struct Model {
+  int device = 0;
+  bool finalized = false;
+  int ar_kind = 0, ar_layers = 0, channel_layers = 0, cross_layers = 0, num_heads = 0;
+  std::map<std::string, HostTensor> staged;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  Weights w32{};   // fp32 [K][N] packing (SIMT path)
+  void* bf16_state = nullptr;  // tensor-path weights / tensor maps (forward_bf16.cu)
+  int n_sm = 148;
+  unsigned long long launches = 0;
+  std::string err;
+};
+
+// Geometry of one (batch, n_samples) problem.
+struct Geometry {
+  int batch, nseq;
+  long long S, L[5], T;
+};
+int make_geometry(int batch, long long n_samples, Geometry* g);
+
+// A named intermediate activation of a forward pass (diagnostics).
+struct StageRef {
+  const void* ptr;
+  int is_bf16;
+  RowMap map;
+  int nseq, rows_per_seq;
+};
+
+// ---- FP32 path (forward_fp32.cu) -------------------------------------------
+size_t workspace_bytes_fp32(const Model& m, const Geometry& g);
+int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
+                 float* vad_logits, float* vad_sig, const float** comb_out);
+int stage_fp32(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
+
+// ---- BF16 tensor-core path (forward_bf16.cu) --------------------------------
+int bf16_prepare(Model& m);   // pack bf16 weights after the fp32 arena is built
+void bf16_release(Model& m);
+size_t workspace_bytes_bf16(const Model& m, const Geometry& g);
+int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
+                 float* vad_logits, float* vad_sig, const float** comb_out);
+int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
+
+}  // namespace vapb

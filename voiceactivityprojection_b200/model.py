@@ -1,0 +1,341 @@
+"""Drop-in facade for the reference's `vap.model` on the stereo inference path.
+
+Mirrors `VapConfig` and `VapGPT` of the reference (vap/model.py:42-79, 125-268)
+— same constructor, attributes (`sample_rate`, `frame_hz`, `conf`, `objective`,
+`horizon_time`), `load_state_dict` of the reference's flat state dicts,
+`forward`, `probs`, `vad`, `.to()/.eval()` — but every device op is a hand-written
+sm_100a kernel behind the C-ABI of include/vapb.h (libvapb.so, loaded with
+ctypes). There is no CPU implementation: CPU tensors raise.
+
+Differences a caller can see:
+  * `VapGPT()` needs no CPC checkpoint; the gAR cell (LSTM/GRU) and depth are
+    inferred from the state dict in `load_state_dict`.
+  * `forward(..., attention=True)` raises NotImplementedError (attention maps are
+    never materialised).
+  * `precision="fp32"` (default; CUDA-core FMA, parity with the reference) or
+    `"bf16"` (tcgen05 tensor cores) — constructor keyword, attribute, or env
+    VAPB_PRECISION.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+from .objective import ObjectiveVAP
+from .utils import vad_fill_silences, vad_omit_spikes
+
+BIN_TIMES: list = [0.2, 0.4, 0.6, 0.8]
+
+
+def load_older_state_dict(path="example/VAP_3mmz3t0u_50Hz_ad20s_134-epoch9-val_2.56.ckpt"):
+    """Lightning .ckpt -> flat state dict (reference vap/model.py:28-39)."""
+    sd = torch.load(path, map_location="cpu", weights_only=False)["state_dict"]
+    new_sd = {}
+    for k, v in sd.items():
+        if "VAP.codebook" in k:
+            continue
+        if "vap_head" in k:
+            k = k.replace("vap_head.projection_head", "vap_head")
+        new_sd[k.replace("net.", "")] = v
+    return new_sd
+
+
+@dataclass
+class VapConfig:
+    """Field-for-field the reference's VapConfig (vap/model.py:42-79)."""
+
+    sample_rate: int = 16_000
+    frame_hz: int = 50
+    bin_times: List[float] = field(default_factory=lambda: BIN_TIMES)
+
+    # Encoder (training flags in the reference; accepted and ignored here)
+    freeze_encoder: int = 1
+    load_pretrained: int = 1
+
+    # GPT
+    dim: int = 256
+    channel_layers: int = 1
+    cross_layers: int = 3
+    num_heads: int = 4
+    dropout: float = 0.1
+
+    @staticmethod
+    def add_argparse_args(parser, fields_added=[]):
+        for k, v in VapConfig.__dataclass_fields__.items():
+            if k == "bin_times":
+                parser.add_argument(f"--vap_{k}", nargs="+", type=float, default=v.default_factory())
+            else:
+                parser.add_argument(f"--vap_{k}", type=v.type if callable(v.type) else eval(v.type),
+                                    default=v.default)
+            fields_added.append(k)
+        return parser, fields_added
+
+    @staticmethod
+    def args_to_conf(args):
+        return VapConfig(
+            **{k.replace("vap_", ""): v for k, v in vars(args).items() if k.startswith("vap_")}
+        )
+
+
+class VapGPT(nn.Module):
+    def __init__(self, conf: Optional[VapConfig] = None, precision: Optional[str] = None):
+        super().__init__()
+        if conf is None:
+            conf = VapConfig()
+        self.conf = conf
+        self.sample_rate = conf.sample_rate
+        self.frame_hz = conf.frame_hz
+        if conf.dim != 256 or conf.num_heads != 4 or conf.sample_rate != 16000 or conf.frame_hz != 50:
+            raise NotImplementedError(
+                "the B200 path implements the shipped configuration: dim=256, num_heads=4, 16 kHz, 50 Hz"
+            )
+        if [round(b * conf.frame_hz) for b in conf.bin_times] != [10, 20, 30, 40]:
+            raise NotImplementedError("bin_times must be [.2, .4, .6, .8]")
+        self.precision = precision or os.environ.get("VAPB_PRECISION", "fp32")
+        if self.precision not in _lib.MODES:
+            raise ValueError(f"precision must be one of {list(_lib.MODES)}")
+        self.objective = ObjectiveVAP(bin_times=conf.bin_times, frame_hz=conf.frame_hz)
+        self._sd: Dict[str, Tensor] = {}  # the reference-schema state dict (CPU fp32 master copy)
+        self._device = torch.device("cpu")
+        self._handle = None
+        self._handle_device = None
+        self._ws = None
+        self.objective._owner = self
+
+    # ------------------------------------------------------------------ state
+    @property
+    def horizon_time(self):
+        return self.objective.horizon_time
+
+    def state_dict(self, *args, **kwargs):
+        return {k: v.clone() for k, v in self._sd.items()}
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Strict load of a reference state dict (run.py:200-201). Layout (LSTM vs
+        GRU, depth) is taken from the tensor shapes; errors are raised with the
+        library's message, in nn.Module.load_state_dict's wording."""
+        sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
+        self._release()
+        self._sd = sd
+        if self._device.type == "cuda":
+            self._ensure_handle()
+        else:
+            self._validate_on_host()
+        return torch.nn.modules.module._IncompatibleKeys([], [])
+
+    def _validate_on_host(self):
+        # Shape validation lives in the library (vapb_finalize), which needs a
+        # device. Without one only the cheap structural facts are checked here.
+        p = "encoder.encoder.gAR.baseNet.weight_ih_l0"
+        if p not in self._sd:
+            raise RuntimeError(f"Error(s) in loading state_dict for VapGPT: Missing key(s): {p}.")
+
+    def _apply(self, fn, recurse=True):
+        probe = fn(torch.empty(0))
+        if probe.dtype not in (torch.float32,):
+            raise NotImplementedError("weights stay fp32; choose arithmetic with precision='bf16'")
+        if probe.device != self._device:
+            self._release()
+            self._device = probe.device
+        return self
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("inference-only implementation (VapGPT.forward/probs/vad)")
+        return self
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().vapb_destroy(self._handle)
+        self._handle = None
+        self._ws = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure_handle(self):
+        if self._handle is not None:
+            return self._handle
+        if self._device.type != "cuda":
+            raise RuntimeError(
+                "VapGPT (B200) runs on CUDA only; call model.to('cuda') — there is no CPU fallback"
+            )
+        if not self._sd:
+            raise RuntimeError("no weights loaded: call load_state_dict() first")
+        lib = _lib.load()
+        dev = self._device.index if self._device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _lib.check(lib, None, lib.vapb_create(dev, C.byref(h)))
+        try:
+            for k, v in self._sd.items():
+                shape = (C.c_int64 * max(v.ndim, 1))(*v.shape)
+                _lib.check(lib, h, lib.vapb_load_tensor(h, k.encode(), v.data_ptr(), v.ndim, shape))
+            _lib.check(lib, h, lib.vapb_finalize(h))
+        except Exception:
+            lib.vapb_destroy(h)
+            raise
+        self._handle, self._handle_device = h, dev
+        return h
+
+    def describe(self) -> Dict[str, int]:
+        lib, h = _lib.load(), self._ensure_handle()
+        v = [C.c_int() for _ in range(5)]
+        _lib.check(lib, h, lib.vapb_describe(h, *[C.byref(x) for x in v]))
+        return dict(zip(["ar_kind", "ar_layers", "channel_layers", "cross_layers", "num_heads"],
+                        [x.value for x in v]))
+
+    def launch_count(self) -> int:
+        lib, h = _lib.load(), self._ensure_handle()
+        n = C.c_uint64()
+        _lib.check(lib, h, lib.vapb_launch_count(h, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ helpers
+    def _check_input(self, waveform: Tensor) -> Tensor:
+        assert waveform.ndim == 3 and waveform.shape[1] == 2, (
+            f"audio VAP ENCODER: {tuple(waveform.shape)} != (B, 2, n_samples)"
+        )
+        if waveform.device.type != "cuda":
+            raise RuntimeError("waveform must be a CUDA tensor (no CPU fallback); use probs_host() for host buffers")
+        if self._device.type != "cuda":
+            self._device = waveform.device
+        return waveform.to(torch.float32).contiguous()
+
+    def _workspace(self, batch: int, n_samples: int, mode: int):
+        lib, h = _lib.load(), self._ensure_handle()
+        need = C.c_size_t()
+        _lib.check(lib, h, lib.vapb_workspace_bytes(h, batch, n_samples, mode, C.byref(need)))
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != self._device:
+            self._ws = None
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self._device)
+        return self._ws
+
+    def _mode(self, precision=None) -> int:
+        return _lib.MODES[precision or self.precision]
+
+    # ------------------------------------------------------------------ hot path
+    def encode_audio(self, audio: Tensor):
+        raise NotImplementedError("encode_audio is fused into forward(); use stage('enc', ...) for diagnostics")
+
+    @torch.no_grad()
+    def forward(self, waveform: Tensor, attention: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
+        """vap/model.py:249-268 -> {"logits": (B,T,256), "vad": (B,T,2)} (vad = logits)."""
+        if attention:
+            raise NotImplementedError("attention=True: the fused attention kernels never materialise (B,H,T,T) maps")
+        wav = self._check_input(waveform)
+        B, _, S = wav.shape
+        lib, h = _lib.load(), self._ensure_handle()
+        _, T = _lib.frames(S)
+        mode = self._mode(precision)
+        ws = self._workspace(B, S, mode)
+        logits = torch.empty((B, T, 256), dtype=torch.float32, device=wav.device)
+        vad = torch.empty((B, T, 2), dtype=torch.float32, device=wav.device)
+        st = torch.cuda.current_stream(wav.device).cuda_stream
+        _lib.check(lib, h, lib.vapb_forward(h, st, wav.data_ptr(), B, S, mode, ws.data_ptr(), ws.numel(),
+                                            logits.data_ptr(), vad.data_ptr()))
+        return {"logits": logits, "vad": vad}
+
+    @torch.no_grad()
+    def probs(self, waveform: Tensor, vad: Optional[Tensor] = None, now_lims: List[int] = [0, 1],
+              future_lims: List[int] = [2, 3], precision: Optional[str] = None,
+              out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """vap/model.py:180-225. Keys: probs, vad, p_now, p_future, H, loss — `loss`
+        is always present and needs T > 100, exactly like the reference (its `vad`
+        argument is overwritten by the model's own sigmoid)."""
+        wav = self._check_input(waveform)
+        B, _, S = wav.shape
+        lib, h = _lib.load(), self._ensure_handle()
+        _, T = _lib.frames(S)
+        if T <= 100:
+            raise RuntimeError(
+                f"maximum size for tensor at dimension 1 is {T - 1} but size is 100"
+            )
+        mode = self._mode(precision)
+        ws = self._workspace(B, S, mode)
+        dev = wav.device
+        if out is None:
+            out = self.alloc_outputs(B, T, dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib, h, lib.vapb_probs(
+            h, st, wav.data_ptr(), B, S, mode, ws.data_ptr(), ws.numel(),
+            now_lims[0], now_lims[-1], future_lims[0], future_lims[1],
+            None, None, out["probs"].data_ptr(), out["vad"].data_ptr(), out["p_now"].data_ptr(),
+            out["p_future"].data_ptr(), out["H"].data_ptr(), out["loss"].data_ptr(), None))
+        return out
+
+    @staticmethod
+    def alloc_outputs(B: int, T: int, device) -> Dict[str, Tensor]:
+        f = dict(dtype=torch.float32, device=device)
+        return {
+            "probs": torch.empty((B, T, 256), **f),
+            "vad": torch.empty((B, T, 2), **f),
+            "p_now": torch.empty((B, T, 2), **f),
+            "p_future": torch.empty((B, T, 2), **f),
+            "H": torch.empty((B, T), **f),
+            "loss": torch.empty((B, T - 100), **f),
+        }
+
+    @torch.no_grad()
+    def probs_host(self, waveform: Tensor, keys=("probs", "vad", "p_now", "p_future", "H", "loss"),
+                   precision: Optional[str] = None, **kw) -> Dict[str, Tensor]:
+        """End-to-end call with HOST buffers: what run.py does around model.probs
+        (run.py:239-241): host->device copy of the waveform, the forward, and
+        device->host copies of the outputs, all on the current stream."""
+        if waveform.device.type != "cpu":
+            raise RuntimeError("probs_host takes a CPU tensor")
+        if self._device.type != "cuda":
+            raise RuntimeError("call model.to('cuda') first")
+        dev_wav = waveform.to(self._device, non_blocking=True)
+        o = self.probs(dev_wav, precision=precision, **kw)
+        host = {k: torch.empty(o[k].shape, dtype=o[k].dtype, pin_memory=True) for k in keys}
+        for k in keys:
+            host[k].copy_(o[k], non_blocking=True)
+        torch.cuda.current_stream(self._device).synchronize()
+        return host
+
+    @torch.no_grad()
+    def vad(self, waveform: Tensor, max_fill_silence_time: float = 0.02, max_omit_spike_time: float = 0.02,
+            vad_cutoff: float = 0.5) -> Tensor:
+        """vap/model.py:227-247."""
+        v = (self(waveform)["vad"].sigmoid() >= vad_cutoff).float()
+        for b in range(v.shape[0]):
+            v[b] = vad_fill_silences(v[b], max_fill_time=max_fill_silence_time, frame_hz=self.frame_hz)
+            v[b] = vad_omit_spikes(v[b], max_omit_time=max_omit_spike_time, frame_hz=self.frame_hz)
+        return v
+
+    # ------------------------------------------------------------------ diagnostics
+    @torch.no_grad()
+    def stage(self, name: str, waveform: Tensor, precision: Optional[str] = None) -> Tensor:
+        """Runs forward and returns one intermediate activation as fp32
+        (vapb_get_stage): 'conv', 'ar', 'enc', 'ch', 'ar0'.., 'comb'.
+        Sequence rows are channel-major (c*B + b)."""
+        wav = self._check_input(waveform)
+        B, _, S = wav.shape
+        self.forward(wav, precision=precision)
+        lib, h = _lib.load(), self._ensure_handle()
+        T100, T = _lib.frames(S)
+        rows = T100 if name in ("conv", "ar") else T
+        nseq = B if name == "comb" else 2 * B
+        out = torch.empty((nseq, rows, 256), dtype=torch.float32, device=wav.device)
+        mode = self._mode(precision)
+        ws = self._workspace(B, S, mode)
+        st = torch.cuda.current_stream(wav.device).cuda_stream
+        _lib.check(lib, h, lib.vapb_get_stage(h, st, name.encode(), B, S, mode, ws.data_ptr(), ws.numel(),
+                                              out.data_ptr(), out.numel()))
+        return out
+
+
+VapStereo = VapGPT  # the name BASELINE.json's north_star uses for this class
