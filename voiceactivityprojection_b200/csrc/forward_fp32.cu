@@ -143,6 +143,7 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
   float* rnn_out = nullptr;
   for (int l = 0; l < m.ar_layers; ++l) {
     Epilogue e = epi_plain(F(p.xproj), G * kDim);
+    e.out1_map = RowMap{L4 * G * kDim, (long long)G * kDim};  // rows_per_seq == L4 in this GEMM
     e.bias = w.rnn_bx[l];
     cx.gemm(rnn_in, rnn_in_map, w.rnn_wih[l], (int)(nseq * L4), (int)L4, G * kDim, kDim, e);
     rnn_out = F(p.rnn[l & 1]) + 4 * kDim;
@@ -169,9 +170,9 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     e.b1 = w.ds_be;
     e.act = ACT_GELU;
     e.out1 = F(p.stage[0]);
-    e.out1_map = dense(kDim);
+    e.out1_map = RowMap{T * kDim, kDim};  // rows_per_seq == T in this GEMM
     first_ln(0, &e.g2, &e.b2);
-    if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = F(p.z); e.out2_map = dense(kDim); }
+    if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = F(p.z); e.out2_map = RowMap{T * kDim, kDim}; }
     const float* base = F(p.rnn[(m.ar_layers - 1) & 1]);  // frame 2t-4 == padded row 2t
     cx.gemm(base, RowMap{p.rnn_lpad * kDim, 2 * kDim}, w.ds_w, MT, (int)T, kDim, 5 * kDim, e);
   }
