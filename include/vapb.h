@@ -124,6 +124,18 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
                    int mode, void* workspace, size_t workspace_bytes, float* out,
                    size_t out_elems);
 
+/* Per-kernel-family device timing for roofline reports. vapb_profile_begin turns
+ * on CUDA-event bracketing of every launch group (events recorded on the launch
+ * stream); vapb_profile_end synchronises, returns the summed milliseconds and
+ * kernel launches per family and turns it off again. Families (index):
+ * 0 conv0, 1 conv implicit-GEMMs (conv1-4, downsample), 2 linear GEMMs
+ * (gAR input projection, q/k/v/proj, FFN, combinator, vap_head), 3 attention,
+ * 4 gAR recurrence, 5 heads (vad, probs, loss), 6 other (padding, exports).
+ * Arrays must hold VAPB_PROFILE_FAMILIES entries. */
+#define VAPB_PROFILE_FAMILIES 7
+int vapb_profile_begin(VapbHandle* h);
+int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches);
+
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);
 

@@ -27,6 +27,8 @@ SYMBOLS = {
     "vapb_probs": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _i, _i, _i, _i] + [_fp] * 9),
     "vapb_probs_from_logits": (_i, [_vp, _vp, _fp, _i64, _i, _i, _i, _i] + [_fp] * 5),
     "vapb_get_stage": (_i, [_vp, _vp, C.c_char_p, _i, _i64, _i, _vp, _sz, _fp, _sz]),
+    "vapb_profile_begin": (_i, [_vp]),
+    "vapb_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "vapb_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "vapb_build_info": (C.c_char_p, []),
 }
@@ -48,6 +50,9 @@ def load():
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
+
+
+PROFILE_FAMILIES = ["conv0", "conv_gemm", "linear_gemm", "attention", "rnn", "heads", "other"]
 
 
 class VapbError(RuntimeError):

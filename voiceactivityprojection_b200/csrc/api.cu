@@ -346,6 +346,8 @@ int vapb_finalize(VapbHandle* h) {
 
 int vapb_destroy(VapbHandle* h) {
   if (!h) return VAPB_OK;
+  for (auto& r : h->m.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->m.event_pool) cudaEventDestroy(e);
   bf16_release(h->m);
   if (h->m.arena) cudaFree(h->m.arena);
   delete h;
@@ -471,6 +473,7 @@ int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t
   rc = run_forward(m, st, wav, g, mode, ws, lg, vad_logits, vs);
   if (rc) return rc;
   const long long rows = (long long)batch * g.T;
+  ProfScope ps(m, st, CAT_HEADS);
   m.launches += launch_probs(st, lg, rows, now_lo, now_hi, fut_lo, fut_hi, probs, p_now, p_future, H,
                              loss ? lse : nullptr, argmax);
   if (loss) m.launches += launch_loss(st, lg, vs, lse, batch, (int)g.T, loss);
@@ -513,6 +516,34 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
   CUDA_OK(m, cudaSetDevice(m.device));
   m.launches += launch_to_f32((cudaStream_t)stream, ref.ptr, ref.is_bf16, ref.map, ref.nseq, ref.rows_per_seq, out);
   CUDA_OK(m, cudaPeekAtLastError());
+  return VAPB_OK;
+}
+
+int vapb_profile_begin(VapbHandle* h) {
+  if (!h) return VAPB_E_INVALID;
+  Model& m = h->m;
+  for (auto& r : m.prof) { m.event_pool.push_back(r.a); m.event_pool.push_back(r.b); }
+  m.prof.clear();
+  m.profiling = true;
+  return VAPB_OK;
+}
+
+int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches) {
+  if (!h || !ms || !launches) return VAPB_E_INVALID;
+  Model& m = h->m;
+  m.profiling = false;
+  for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  CUDA_OK(m, cudaSetDevice(m.device));
+  for (auto& r : m.prof) {
+    CUDA_OK(m, cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_OK(m, cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cat] += t;
+    launches[r.cat] += r.launches;
+    m.event_pool.push_back(r.a);
+    m.event_pool.push_back(r.b);
+  }
+  m.prof.clear();
   return VAPB_OK;
 }
 

@@ -75,8 +75,10 @@ RowMap dense(long long n) { return RowMap{0, n}; }
 struct Ctx {
   Model& m;
   cudaStream_t st;
-  void gemm(const void* A, RowMap amap, const void* W, int M, int rps, int N, int K, const Epilogue& e) {
+  void gemm(const void* A, RowMap amap, const void* W, int M, int rps, int N, int K, const Epilogue& e,
+            int cat = CAT_LINEAR_GEMM) {
     GemmProblem p{A, amap, W, M, rps, N, K};
+    ProfScope ps(m, st, cat);
     m.launches += launch_gemm_f32(st, p, e);
   }
 };
@@ -103,6 +105,8 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
 
   // physical zero padding of the conv inputs (interior rows are fully rewritten)
+  {
+  ProfScope ps(m, st, CAT_OTHER);
   for (int i = 0; i < 4; ++i) {
     m.launches += launch_zero_rows(st, F(p.act[i]), 4, p.mb, p.lpad[i] * kDim, 0, p.lo[i]);
     m.launches += launch_zero_rows(st, F(p.act[i]), 4, p.mb, p.lpad[i] * kDim, p.lo[i] + g.L[i],
@@ -110,12 +114,14 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
   }
   for (int i = 0; i < (m.ar_layers > 1 ? 2 : 1); ++i)
     m.launches += launch_zero_rows(st, F(p.rnn[i]), 4, nseq, p.rnn_lpad * kDim, 0, 4);
+  }
 
   // ---- CPC gEncoder: conv0 (CUDA cores) + conv1..4 (implicit GEMM), micro-batched
   for (int s0 = 0; s0 < nseq; s0 += p.mb) {
     const int n = (nseq - s0 < p.mb) ? nseq - s0 : p.mb;
+    { ProfScope ps(m, st, CAT_CONV0);
     m.launches += launch_conv0(st, wav, g.batch, g.S, s0, n, g.L[0], w.c0_w, w.c0_b, w.c0_g, w.c0_be,
-                               F(p.act[0]), 0, p.lpad[0] * kDim, (int)p.lo[0]);
+                               F(p.act[0]), 0, p.lpad[0] * kDim, (int)p.lo[0]); }
     for (int i = 1; i <= 4; ++i) {
       const Conv& c = kConv[i];
       Epilogue e{};
@@ -133,7 +139,7 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       }
       // input frame s*t - p sits at padded row s*t (lo == p)
       cx.gemm(F(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, w.conv_w[i],
-              (int)(n * g.L[i]), (int)g.L[i], kDim, c.k * kDim, e);
+              (int)(n * g.L[i]), (int)g.L[i], kDim, c.k * kDim, e, CAT_CONV_GEMM);
     }
   }
 
@@ -147,6 +153,7 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     e.bias = w.rnn_bx[l];
     cx.gemm(rnn_in, rnn_in_map, w.rnn_wih[l], (int)(nseq * L4), (int)L4, G * kDim, kDim, e);
     rnn_out = F(p.rnn[l & 1]) + 4 * kDim;
+    ProfScope ps(m, st, CAT_RNN);
     m.launches += launch_rnn_f32(st, m.ar_kind, F(p.xproj), w.rnn_whh_t[l], w.rnn_bhn[l], rnn_out,
                                  p.rnn_lpad * kDim, nseq, (int)L4);
     rnn_in = rnn_out;
@@ -174,7 +181,7 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     first_ln(0, &e.g2, &e.b2);
     if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = F(p.z); e.out2_map = RowMap{T * kDim, kDim}; }
     const float* base = F(p.rnn[(m.ar_layers - 1) & 1]);  // frame 2t-4 == padded row 2t
-    cx.gemm(base, RowMap{p.rnn_lpad * kDim, 2 * kDim}, w.ds_w, MT, (int)T, kDim, 5 * kDim, e);
+    cx.gemm(base, RowMap{p.rnn_lpad * kDim, 2 * kDim}, w.ds_w, MT, (int)T, kDim, 5 * kDim, e, CAT_CONV_GEMM);
   }
 
   // ---- transformer layers
@@ -186,8 +193,9 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     // z == LN_self_attn(x_in)
     cx.gemm(F(p.z), dense(kDim), lw.wqkv, MT, MT, 3 * kDim, kDim, epi_plain(F(p.qkv), 3 * kDim));
     if (cross) cx.gemm(x_in, dense(kDim), lw.wkv_c, MT, MT, 2 * kDim, kDim, epi_plain(F(p.kvc), 2 * kDim));
+    { ProfScope ps(m, st, CAT_ATTN);
     m.launches += launch_attention_f32(st, F(p.qkv), 3 * kDim, F(p.qkv) + kDim, F(p.qkv) + 2 * kDim, 3 * kDim,
-                                       F(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0);
+                                       F(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0); }
     const float* x_mid = nullptr;
     {
       Epilogue e{};
@@ -205,8 +213,9 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     }
     if (cross) {
       cx.gemm(F(p.z), dense(kDim), lw.wq_c, MT, MT, kDim, kDim, epi_plain(F(p.qc), kDim));
+      { ProfScope ps(m, st, CAT_ATTN);
       m.launches += launch_attention_f32(st, F(p.qc), kDim, F(p.kvc), F(p.kvc) + kDim, 2 * kDim, F(p.y), nseq,
-                                         (int)T, m.num_heads, lw.slopes_cross, 1);
+                                         (int)T, m.num_heads, lw.slopes_cross, 1); }
       Epilogue e{};
       e.resid = x_mid;
       e.resid_map = dense(kDim);
@@ -250,8 +259,10 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     e.out1_map = dense(kDim);
     cx.gemm(x_last + (long long)c * MB * kDim, dense(kDim), c == 0 ? w.comb_a : w.comb_b, MB, MB, kDim, kDim, e);
   }
-  if (vad_logits || vad_sig)
+  if (vad_logits || vad_sig) {
+    ProfScope ps(m, st, CAT_HEADS);
     m.launches += launch_vad_head(st, x_last, w.va_w, w.va_b, g.batch, (int)T, vad_logits, vad_sig);
+  }
   {
     Epilogue e = epi_plain(logits, kClasses);
     e.bias = w.head_b;

@@ -48,7 +48,15 @@ struct Weights {
   const float *head_b;
 };
 
+// Per-kernel-family device timing (CUDA events on the launch stream), used by
+// bench.py for the roofline of the dominant kernel. Off unless requested.
+enum ProfCat { CAT_CONV0 = 0, CAT_CONV_GEMM, CAT_LINEAR_GEMM, CAT_ATTN, CAT_RNN, CAT_HEADS, CAT_OTHER, CAT_COUNT };
+struct ProfRec { int cat; int launches; cudaEvent_t a, b; };
+
 struct Model {
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
   int device = 0;
   bool finalized = false;
   int ar_kind = 0, ar_layers = 0, channel_layers = 0, cross_layers = 0, num_heads = 0;
@@ -60,6 +68,36 @@ struct Model {
   int n_sm = 148;
   unsigned long long launches = 0;
   std::string err;
+};
+
+// RAII: times everything launched on `st` during its lifetime under `cat`.
+struct ProfScope {
+  Model& m;
+  cudaStream_t st;
+  int cat;
+  unsigned long long l0;
+  cudaEvent_t a = nullptr;
+  ProfScope(Model& m_, cudaStream_t st_, int cat_) : m(m_), st(st_), cat(cat_), l0(m_.launches) {
+    if (!m.profiling) return;
+    a = take();
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEvent_t b = take();
+    cudaEventRecord(b, st);
+    m.prof.push_back(ProfRec{cat, (int)(m.launches - l0), a, b});
+  }
+  cudaEvent_t take() {
+    if (!m.event_pool.empty()) {
+      cudaEvent_t e = m.event_pool.back();
+      m.event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
 };
 
 // Geometry of one (batch, n_samples) problem.
