@@ -136,6 +136,18 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
 int vapb_profile_begin(VapbHandle* h);
 int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches);
 
+/* Unit-test hook for the tcgen05 GEMM kernel (tests/test_gpu_kernels.py): one
+ * launch of csrc/k_gemm_tc.cu on caller-provided device buffers.
+ * A: bf16, row (seq, t) at A + seq*a_seq_stride + t*a_row_stride (elements), K
+ * contiguous elements per row (rows may overlap: implicit conv). W: bf16 [N][K].
+ * Outputs / residual are dense (nseq*rows_per_seq, N). Returns 0 or a negative
+ * code; the message is copied to err (if non-NULL). */
+int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W,
+                       int nseq, int rows_per_seq, int N, int K, const float* bias, int norm1,
+                       const float* g1, const float* b1, int act, const float* resid, int accumulate,
+                       float* out1_f32, void* out1_bf16, int norm2, const float* g2, const float* b2,
+                       void* out2_bf16, char* err, int err_len);
+
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);
 

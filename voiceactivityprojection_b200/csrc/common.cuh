@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 namespace vapb {
 
 constexpr int kDim = 256;       // model dim == CPC hidden (vap/model.py:53)
@@ -52,6 +54,18 @@ struct GemmProblem {
   int K;
 };
 
+// Tensor-core GEMM (k_gemm_tc.cu): A and W are bf16; W is [N][K] (K contiguous).
+// The epilogue's out1 goes to out1_f32 and/or out1_bf16 (Epilogue::out1 ignored).
+struct TcGemmArgs {
+  const void* A;
+  RowMap a_map;
+  const void* W;
+  int nseq, rows_per_seq, N, K;
+  Epilogue e;
+  float* out1_f32;
+  __nv_bfloat16* out1_bf16;
+};
+
 // ---- launchers (each returns the number of kernels it launched) -------------
 int launch_conv0(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq,
                  long long L0, const float* w /*[10][256]*/, const float* bias, const float* g,
@@ -59,6 +73,8 @@ int launch_conv0(cudaStream_t st, const float* wav, int batch, long long n_sampl
                  int out_pad_rows);
 
 int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
+
+int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);  // -1 on error
 
 int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
                      long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence
