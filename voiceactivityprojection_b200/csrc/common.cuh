@@ -87,6 +87,12 @@ int launch_rnn_f32(cudaStream_t st, int kind /*0 LSTM 1 GRU*/, const float* xpro
                    const float* whh_t /*[256][G*256]*/, const float* bhn /*GRU b_hn [256] or null*/,
                    float* out, long long out_seq_stride, int nseq, int T);
 
+int launch_attention_simt_bf16(cudaStream_t st, const __nv_bfloat16* q, long long q_row_stride,
+                               const __nv_bfloat16* k, const __nv_bfloat16* v, long long kv_row_stride,
+                               __nv_bfloat16* out, int nseq, int T, int n_heads, const float* slopes, int cross);
+int launch_rnn_f32_bf16out(cudaStream_t st, int kind, const float* xproj, const float* whh_t, const float* bhn,
+                           __nv_bfloat16* out, long long out_seq_stride, int nseq, int T);
+
 int launch_vad_head(cudaStream_t st, const float* x /*[2B][T][256] channel-major*/, const float* w,
                     const float* b, int batch, int T, float* vad_logits /*(B,T,2) or null*/,
                     float* vad_sig /*(B,T,2) or null*/);

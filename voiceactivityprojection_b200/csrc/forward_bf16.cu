@@ -1,13 +1,418 @@
-// BF16 tensor-core path (placeholder until the tcgen05 kernels land).
+// BF16 tensor-core orchestration of VapGPT.forward (same call stack as
+// forward_fp32.cu; reference vap/model.py:249-268).
+//
+// Every contraction runs on tcgen05 (k_gemm_tc.cu) with bf16 operands and fp32
+// accumulation in TMEM; norms, softmax, residual stream and the recurrence state
+// stay fp32. Activation buffers that feed a GEMM are bf16 channels-last; the
+// residual stream x is fp32 with a bf16 shadow where an un-normalised copy is a
+// GEMM operand (cross-attention K/V source, combinator input).
+#include <cstring>
+#include <vector>
+
 #include "model.h"
 
 namespace vapb {
-int bf16_prepare(Model&) { return 0; }
-void bf16_release(Model&) {}
-size_t workspace_bytes_bf16(const Model&, const Geometry&) { return 0; }
-int forward_bf16(Model& m, cudaStream_t, const float*, const Geometry&, char*, float*, float*, float*, const float**) {
-  m.err = "bf16 mode not built";
-  return -5;
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct Conv { int k, s, p; };
+const Conv kConv[5] = {{10, 5, 3}, {8, 4, 2}, {4, 2, 1}, {4, 2, 1}, {4, 2, 1}};
+
+size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+struct LayerW16 {
+  const bf16 *wqkv, *wproj, *wq_c, *wkv_c, *wproj_c, *w1, *w2;
+};
+struct State16 {
+  void* arena = nullptr;
+  const bf16* conv_w[5];
+  const bf16* rnn_wih[kMaxLayers];
+  const bf16* ds_w;
+  LayerW16 chan[kMaxLayers], cross[kMaxLayers];
+  const bf16 *comb_a, *comb_b, *head_w;
+};
+
+struct Plan16 {
+  int mb;
+  long long lo[4], lpad[4], rnn_lpad;
+  size_t act[4], act4, xproj, rnn[2], stage[2 * kMaxLayers + 1], xs, xa, xb, z, qkv, kvc, qc, y, h, comb, combb,
+      bytes;
+};
+
+Plan16 make_plan(const Model& m, const Geometry& g) {
+  Plan16 p{};
+  const int G = m.ar_kind == 0 ? 4 : 3;
+  const long long per_seq0 = (g.L[0] + 16) * kDim * 2;
+  long long mb = (4LL << 30) / per_seq0;
+  if (mb < 1) mb = 1;
+  if (mb > g.nseq) mb = g.nseq;
+  p.mb = (int)mb;
+  size_t off = 0;
+  for (int i = 0; i < 4; ++i) {
+    const Conv& nx = kConv[i + 1];
+    p.lo[i] = nx.p;
+    const long long need = (long long)nx.s * (g.L[i + 1] - 1) + nx.k;
+    long long lp = need > nx.p + g.L[i] ? need : nx.p + g.L[i];
+    lp = (lp + nx.s - 1) / nx.s * nx.s;
+    p.lpad[i] = lp;
+    p.act[i] = off;
+    off = align_up(off + (size_t)mb * lp * kDim * 2);
+  }
+  p.act4 = off;  off = align_up(off + (size_t)g.nseq * g.L[4] * kDim * 2);
+  p.xproj = off; off = align_up(off + (size_t)g.nseq * g.L[4] * G * kDim * 4);
+  p.rnn_lpad = 4 + g.L[4] + (g.L[4] & 1);  // even, so the stride-2 tensor map strides nest
+  for (int i = 0; i < 2; ++i) {
+    p.rnn[i] = off;
+    if (i == 0 || m.ar_layers > 1) off = align_up(off + (size_t)g.nseq * p.rnn_lpad * kDim * 2);
+  }
+  const size_t rows = (size_t)g.nseq * g.T;
+  const int n_stage = 1 + m.channel_layers + m.cross_layers;
+  for (int i = 0; i < n_stage; ++i) { p.stage[i] = off; off = align_up(off + rows * kDim * 4); }
+  p.xs = off;  off = align_up(off + rows * kDim * 2);   // bf16 shadow of the current layer input
+  p.xa = off;  off = align_up(off + rows * kDim * 4);
+  p.xb = off;  off = align_up(off + rows * kDim * 4);
+  p.z = off;   off = align_up(off + rows * kDim * 2);
+  p.qkv = off; off = align_up(off + rows * 3 * kDim * 2);
+  p.kvc = off; off = align_up(off + rows * 2 * kDim * 2);
+  p.qc = off;  off = align_up(off + rows * kDim * 2);
+  p.y = off;   off = align_up(off + rows * kDim * 2);
+  p.h = off;   off = align_up(off + rows * kFfn * 2);
+  p.comb = off;  off = align_up(off + rows / 2 * kDim * 4);
+  p.combb = off; off = align_up(off + rows / 2 * kDim * 2);
+  p.bytes = off;
+  return p;
 }
-int stage_bf16(const Model&, const Geometry&, char*, const std::string&, StageRef*) { return -1; }
+
+RowMap dense(long long rows, long long n) { return RowMap{rows * n, n}; }
+
+struct Ctx {
+  Model& m;
+  cudaStream_t st;
+  int rc = 0;
+  // A: bf16 rows; W: bf16 [N][K]
+  void gemm(const bf16* A, RowMap amap, const bf16* W, int nseq, int rps, int N, int K, const Epilogue& e,
+            float* out_f32, bf16* out_bf16, int cat = CAT_LINEAR_GEMM) {
+    if (rc) return;
+    TcGemmArgs a{};
+    a.A = A; a.a_map = amap; a.W = W;
+    a.nseq = nseq; a.rows_per_seq = rps; a.N = N; a.K = K;
+    a.e = e;
+    a.out1_f32 = out_f32; a.out1_bf16 = out_bf16;
+    ProfScope ps(m, st, cat);
+    std::string err;
+    const int n = launch_gemm_tc(st, a, m.n_sm, &err);
+    if (n < 0) { m.err = err; rc = -3; return; }
+    m.launches += n;
+  }
+};
+
+std::vector<bf16> to_bf16(const std::vector<float>& v) {
+  std::vector<bf16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+  return o;
+}
+
+}  // namespace
+
+int bf16_prepare(Model& m) {
+  State16* s = new State16();
+  std::vector<char> host;
+  struct Fix { const bf16** slot; size_t off; };
+  std::vector<Fix> fixes;
+  auto put = [&](const bf16** slot, const std::vector<float>& v) {
+    const size_t off = (host.size() + 1023) / 1024 * 1024;
+    std::vector<bf16> b = to_bf16(v);
+    host.resize(off + b.size() * 2);
+    memcpy(host.data() + off, b.data(), b.size() * 2);
+    fixes.push_back({slot, off});
+  };
+  auto T = [&](const std::string& k) -> const HostTensor& { return m.staged[k]; };
+  auto conv_nk = [&](const HostTensor& t) {  // (out,in,k) -> [out][tap*in + cin]
+    const int64_t co = t.shape[0], ci = t.shape[1], k = t.shape[2];
+    std::vector<float> o((size_t)co * ci * k);
+    for (int64_t n = 0; n < co; ++n)
+      for (int64_t c = 0; c < ci; ++c)
+        for (int64_t j = 0; j < k; ++j) o[((size_t)n * k + j) * ci + c] = t.data[((size_t)n * ci + c) * k + j];
+    return o;
+  };
+  auto cat_rows = [&](std::vector<const HostTensor*> ts) {
+    std::vector<float> o;
+    for (auto* t : ts) o.insert(o.end(), t->data.begin(), t->data.end());
+    return o;
+  };
+  const std::string GE = "encoder.encoder.gEncoder.", AR = "encoder.encoder.gAR.baseNet.";
+  for (int i = 1; i < 5; ++i) put(&s->conv_w[i], conv_nk(T(GE + "conv" + std::to_string(i) + ".weight")));
+  for (int l = 0; l < m.ar_layers; ++l) put(&s->rnn_wih[l], T(AR + "weight_ih_l" + std::to_string(l)).data);
+  put(&s->ds_w, conv_nk(T("encoder.downsample.1.weight")));
+  auto layer = [&](const std::string& p, bool cross, LayerW16& lw) {
+    put(&lw.wqkv, cat_rows({&T(p + "mha.query.weight"), &T(p + "mha.key.weight"), &T(p + "mha.value.weight")}));
+    put(&lw.wproj, T(p + "mha.proj.weight").data);
+    if (cross) {
+      put(&lw.wq_c, T(p + "mha_cross.query.weight").data);
+      put(&lw.wkv_c, cat_rows({&T(p + "mha_cross.key.weight"), &T(p + "mha_cross.value.weight")}));
+      put(&lw.wproj_c, T(p + "mha_cross.proj.weight").data);
+    }
+    put(&lw.w1, T(p + "ffnetwork.0.weight").data);
+    put(&lw.w2, T(p + "ffnetwork.3.weight").data);
+  };
+  for (int l = 0; l < m.channel_layers; ++l) layer("ar_channel.layers." + std::to_string(l) + ".", false, s->chan[l]);
+  for (int l = 0; l < m.cross_layers; ++l) layer("ar.layers." + std::to_string(l) + ".", true, s->cross[l]);
+  put(&s->comb_a, T("ar.combinator.h0_a.weight").data);
+  put(&s->comb_b, T("ar.combinator.h0_b.weight").data);
+  put(&s->head_w, T("vap_head.weight").data);
+  if (cudaMalloc(&s->arena, host.size()) != cudaSuccess ||
+      cudaMemcpy(s->arena, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    m.err = "bf16 weight arena: CUDA allocation/copy failed";
+    delete s;
+    return -3;
+  }
+  for (auto& f : fixes) *f.slot = reinterpret_cast<const bf16*>(static_cast<char*>(s->arena) + f.off);
+  m.bf16_state = s;
+  return 0;
+}
+
+void bf16_release(Model& m) {
+  State16* s = static_cast<State16*>(m.bf16_state);
+  if (!s) return;
+  if (s->arena) cudaFree(s->arena);
+  delete s;
+  m.bf16_state = nullptr;
+}
+
+size_t workspace_bytes_bf16(const Model& m, const Geometry& g) { return make_plan(m, g).bytes; }
+
+int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
+                 float* vad_logits, float* vad_sig, const float**) {
+  const State16& s = *static_cast<const State16*>(m.bf16_state);
+  const Plan16 p = make_plan(m, g);
+  const Weights& w = m.w32;  // fp32 vectors (biases, norm affine, slopes, va head) and conv0
+  Ctx cx{m, st};
+  const int G = m.ar_kind == 0 ? 4 : 3;
+  const int nseq = g.nseq;
+  const long long T = g.T, L4 = g.L[4];
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  auto H = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
+
+  {
+    ProfScope ps(m, st, CAT_OTHER);
+    for (int i = 0; i < 4; ++i) {
+      m.launches += launch_zero_rows(st, H(p.act[i]), 2, p.mb, p.lpad[i] * kDim, 0, p.lo[i]);
+      m.launches += launch_zero_rows(st, H(p.act[i]), 2, p.mb, p.lpad[i] * kDim, p.lo[i] + g.L[i],
+                                     p.lpad[i] - p.lo[i] - g.L[i]);
+    }
+    for (int i = 0; i < (m.ar_layers > 1 ? 2 : 1); ++i) {
+      m.launches += launch_zero_rows(st, H(p.rnn[i]), 2, nseq, p.rnn_lpad * kDim, 0, 4);
+      m.launches += launch_zero_rows(st, H(p.rnn[i]), 2, nseq, p.rnn_lpad * kDim, 4 + L4, p.rnn_lpad - 4 - L4);
+    }
+  }
+
+  // ---- CPC gEncoder
+  for (int s0 = 0; s0 < nseq; s0 += p.mb) {
+    const int n = (nseq - s0 < p.mb) ? nseq - s0 : p.mb;
+    {
+      ProfScope ps(m, st, CAT_CONV0);
+      m.launches += launch_conv0(st, wav, g.batch, g.S, s0, n, g.L[0], w.c0_w, w.c0_b, w.c0_g, w.c0_be,
+                                 H(p.act[0]), 1, p.lpad[0] * kDim, (int)p.lo[0]);
+    }
+    for (int i = 1; i <= 4; ++i) {
+      const Conv& c = kConv[i];
+      Epilogue e{};
+      e.bias = w.conv_b[i];
+      e.norm1 = NORM_CHANNEL;
+      e.g1 = w.conv_g[i];
+      e.b1 = w.conv_be[i];
+      e.act = ACT_RELU;
+      bf16* out;
+      if (i < 4) {
+        out = H(p.act[i]) + p.lo[i] * kDim;
+        e.out1_map = RowMap{p.lpad[i] * kDim, kDim};
+      } else {
+        out = H(p.act4) + (long long)s0 * L4 * kDim;
+        e.out1_map = RowMap{L4 * kDim, kDim};
+      }
+      cx.gemm(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
+              kDim, c.k * kDim, e, nullptr, out, CAT_CONV_GEMM);
+    }
+  }
+
+  // ---- gAR
+  const bf16* rnn_in = H(p.act4);
+  RowMap rnn_in_map{L4 * kDim, kDim};
+  for (int l = 0; l < m.ar_layers; ++l) {
+    Epilogue e{};
+    e.bias = w.rnn_bx[l];
+    e.out1_map = RowMap{L4 * G * kDim, (long long)G * kDim};
+    cx.gemm(rnn_in, rnn_in_map, s.rnn_wih[l], nseq, (int)L4, G * kDim, kDim, e, F(p.xproj), nullptr);
+    bf16* rnn_out = H(p.rnn[l & 1]) + 4 * kDim;
+    {
+      ProfScope ps(m, st, CAT_RNN);
+      m.launches += launch_rnn_f32_bf16out(st, m.ar_kind, F(p.xproj), w.rnn_whh_t[l], w.rnn_bhn[l], rnn_out,
+                                           p.rnn_lpad * kDim, nseq, (int)L4);
+    }
+    rnn_in = rnn_out;
+    rnn_in_map = RowMap{p.rnn_lpad * kDim, kDim};
+  }
+
+  // ---- downsample
+  const int n_layers = m.channel_layers + m.cross_layers;
+  auto first_ln = [&](int li, const float** gg, const float** bb) {
+    if (li >= n_layers) { *gg = nullptr; *bb = nullptr; return; }
+    const LayerW& lw = li < m.channel_layers ? w.chan[li] : w.cross[li - m.channel_layers];
+    *gg = lw.ln_sa_g;
+    *bb = lw.ln_sa_b;
+  };
+  const int MT = (int)(nseq * T);
+  {
+    Epilogue e{};
+    e.bias = w.ds_b;
+    e.norm1 = NORM_LAYER;
+    e.g1 = w.ds_g;
+    e.b1 = w.ds_be;
+    e.act = ACT_GELU;
+    e.out1_map = dense(T, kDim);
+    first_ln(0, &e.g2, &e.b2);
+    if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = H(p.z); e.out2_map = dense(T, kDim); }
+    cx.gemm(H(p.rnn[(m.ar_layers - 1) & 1]), RowMap{p.rnn_lpad * kDim, 2 * kDim}, s.ds_w, nseq, (int)T, kDim,
+            5 * kDim, e, F(p.stage[0]), H(p.xs), CAT_CONV_GEMM);
+  }
+
+  // ---- transformer layers (rows are dense (nseq*T, .) from here on)
+  const RowMap d256 = dense(MT, kDim);
+  for (int li = 0; li < n_layers; ++li) {
+    const bool cross = li >= m.channel_layers;
+    const LayerW& lw = cross ? w.cross[li - m.channel_layers] : w.chan[li];
+    const LayerW16& lh = cross ? s.cross[li - m.channel_layers] : s.chan[li];
+    const float* x_in = F(p.stage[li]);
+    {
+      Epilogue e{};
+      e.out1_map = dense(MT, 3 * kDim);
+      cx.gemm(H(p.z), d256, lh.wqkv, 1, MT, 3 * kDim, kDim, e, nullptr, H(p.qkv));
+    }
+    if (cross) {
+      Epilogue e{};
+      e.out1_map = dense(MT, 2 * kDim);
+      cx.gemm(H(p.xs), d256, lh.wkv_c, 1, MT, 2 * kDim, kDim, e, nullptr, H(p.kvc));
+    }
+    if (cx.rc) return cx.rc;
+    {
+      ProfScope ps(m, st, CAT_ATTN);
+      m.launches += launch_attention_simt_bf16(st, H(p.qkv), 3 * kDim, H(p.qkv) + kDim, H(p.qkv) + 2 * kDim,
+                                               3 * kDim, H(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0);
+    }
+    float* x_mid = cross ? F(p.xa) : F(p.xb);
+    {
+      Epilogue e{};
+      e.resid = x_in;
+      e.resid_map = d256;
+      e.out1_map = d256;
+      e.norm2 = NORM_LAYER;
+      e.g2 = cross ? lw.ln_src_g : lw.ln_ffn_g;
+      e.b2 = cross ? lw.ln_src_b : lw.ln_ffn_b;
+      e.out2 = H(p.z);
+      e.out2_map = d256;
+      cx.gemm(H(p.y), d256, lh.wproj, 1, MT, kDim, kDim, e, x_mid, nullptr);
+    }
+    if (cross) {
+      {
+        Epilogue e{};
+        e.out1_map = d256;
+        cx.gemm(H(p.z), d256, lh.wq_c, 1, MT, kDim, kDim, e, nullptr, H(p.qc));
+      }
+      if (cx.rc) return cx.rc;
+      {
+        ProfScope ps(m, st, CAT_ATTN);
+        m.launches += launch_attention_simt_bf16(st, H(p.qc), kDim, H(p.kvc), H(p.kvc) + kDim, 2 * kDim, H(p.y),
+                                                 nseq, (int)T, m.num_heads, lw.slopes_cross, 1);
+      }
+      Epilogue e{};
+      e.resid = x_mid;
+      e.resid_map = d256;
+      e.out1_map = d256;
+      e.norm2 = NORM_LAYER;
+      e.g2 = lw.ln_ffn_g;
+      e.b2 = lw.ln_ffn_b;
+      e.out2 = H(p.z);
+      e.out2_map = d256;
+      cx.gemm(H(p.y), d256, lh.wproj_c, 1, MT, kDim, kDim, e, F(p.xb), nullptr);
+    }
+    {
+      Epilogue e{};
+      e.act = ACT_GELU;
+      e.out1_map = dense(MT, kFfn);
+      cx.gemm(H(p.z), d256, lh.w1, 1, MT, kFfn, kDim, e, nullptr, H(p.h));
+    }
+    {
+      Epilogue e{};
+      e.resid = F(p.xb);
+      e.resid_map = d256;
+      e.out1_map = d256;
+      first_ln(li + 1, &e.g2, &e.b2);
+      if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = H(p.z); e.out2_map = d256; }
+      // bf16 shadow of the new residual stream: next cross layer's K/V source, or the combinator input
+      cx.gemm(H(p.h), dense(MT, kFfn), lh.w2, 1, MT, kDim, kFfn, e, F(p.stage[li + 1]), H(p.xs));
+    }
+  }
+
+  // ---- combinator + heads
+  const float* x_last = F(p.stage[n_layers]);
+  const int MB = (int)(g.batch * T);
+  for (int c = 0; c < 2; ++c) {
+    Epilogue e{};
+    e.norm1 = NORM_LAYER;
+    e.g1 = w.comb_g;
+    e.b1 = w.comb_be;
+    e.act = ACT_GELU;
+    e.accumulate = c;
+    e.out1_map = dense(MB, kDim);
+    cx.gemm(H(p.xs) + (long long)c * MB * kDim, dense(MB, kDim), c == 0 ? s.comb_a : s.comb_b, 1, MB, kDim, kDim, e,
+            F(p.comb), c == 1 ? H(p.combb) : nullptr);
+  }
+  if (vad_logits || vad_sig) {
+    ProfScope ps(m, st, CAT_HEADS);
+    m.launches += launch_vad_head(st, x_last, w.va_w, w.va_b, g.batch, (int)T, vad_logits, vad_sig);
+  }
+  {
+    Epilogue e{};
+    e.bias = w.head_b;
+    e.out1_map = dense(MB, kClasses);
+    cx.gemm(H(p.combb), dense(MB, kDim), s.head_w, 1, MB, kClasses, kDim, e, logits, nullptr);
+  }
+  return cx.rc;
+}
+
+int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref) {
+  const Plan16 p = make_plan(m, g);
+  ref->is_bf16 = 0;
+  ref->nseq = g.nseq;
+  ref->rows_per_seq = (int)g.T;
+  ref->map = RowMap{g.T * kDim, kDim};
+  if (name == "conv") {
+    ref->ptr = ws + p.act4;
+    ref->is_bf16 = 1;
+    ref->rows_per_seq = (int)g.L[4];
+    ref->map = RowMap{g.L[4] * kDim, kDim};
+  } else if (name == "ar") {
+    ref->ptr = reinterpret_cast<const bf16*>(ws + p.rnn[(m.ar_layers - 1) & 1]) + 4 * kDim;
+    ref->is_bf16 = 1;
+    ref->rows_per_seq = (int)g.L[4];
+    ref->map = RowMap{p.rnn_lpad * kDim, kDim};
+  } else if (name == "enc") {
+    ref->ptr = ws + p.stage[0];
+  } else if (name == "ch") {
+    ref->ptr = ws + p.stage[m.channel_layers];
+  } else if (name.size() >= 3 && name.compare(0, 2, "ar") == 0) {
+    const int l = atoi(name.c_str() + 2);
+    if (l < 0 || l >= m.cross_layers) return -1;
+    ref->ptr = ws + p.stage[m.channel_layers + l + 1];
+  } else if (name == "comb") {
+    ref->ptr = ws + p.comb;
+    ref->nseq = g.batch;
+  } else {
+    return -1;
+  }
+  return 0;
+}
+
 }  // namespace vapb

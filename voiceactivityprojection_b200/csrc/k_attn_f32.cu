@@ -14,9 +14,26 @@ namespace vapb {
 constexpr int AQ = 64, AK = 64, AD = 64, ALD = 68, ATHREADS = 256;
 constexpr int ATT_SMEM = (AQ * ALD + AK * ALD + AK * AD + AQ * ALD) * 4;
 
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TIO>
 __global__ void __launch_bounds__(ATHREADS)
-attention_f32_kernel(const float* __restrict__ q, long long q_row_stride, const float* __restrict__ k,
-                     const float* __restrict__ v, long long kv_row_stride, float* __restrict__ out, int nseq,
+attention_f32_kernel(const TIO* __restrict__ q, long long q_row_stride, const TIO* __restrict__ k,
+                     const TIO* __restrict__ v, long long kv_row_stride, TIO* __restrict__ out, int nseq,
                      int T, const float* __restrict__ slopes, int cross) {
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;               // [AQ][ALD]
@@ -27,15 +44,15 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row_stride, const 
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int kvseq = cross ? (seq + nseq / 2) % nseq : seq;
   const float slope = slopes[head];
-  const float* qb = q + ((long long)seq * T) * q_row_stride + head * AD;
-  const float* kb = k + ((long long)kvseq * T) * kv_row_stride + head * AD;
-  const float* vb = v + ((long long)kvseq * T) * kv_row_stride + head * AD;
+  const TIO* qb = q + ((long long)seq * T) * q_row_stride + head * AD;
+  const TIO* kb = k + ((long long)kvseq * T) * kv_row_stride + head * AD;
+  const TIO* vb = v + ((long long)kvseq * T) * kv_row_stride + head * AD;
   const int q0 = qt * AQ;
 
   for (int idx = tid; idx < AQ * AD / 4; idx += ATHREADS) {
     const int r = idx >> 4, d4 = (idx & 15) * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < T) x = *reinterpret_cast<const float4*>(qb + (long long)(q0 + r) * q_row_stride + d4);
+    if (q0 + r < T) x = load4(qb + (long long)(q0 + r) * q_row_stride + d4);
     *reinterpret_cast<float4*>(&Qs[r * ALD + d4]) = x;
   }
 
@@ -55,8 +72,8 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row_stride, const 
       const int r = idx >> 4, d4 = (idx & 15) * 4;
       float4 kx = make_float4(0.f, 0.f, 0.f, 0.f), vx = kx;
       if (k0 + r < T) {
-        kx = *reinterpret_cast<const float4*>(kb + (long long)(k0 + r) * kv_row_stride + d4);
-        vx = *reinterpret_cast<const float4*>(vb + (long long)(k0 + r) * kv_row_stride + d4);
+        kx = load4(kb + (long long)(k0 + r) * kv_row_stride + d4);
+        vx = load4(vb + (long long)(k0 + r) * kv_row_stride + d4);
       }
       *reinterpret_cast<float4*>(&Ks[r * ALD + d4]) = kx;
       *reinterpret_cast<float4*>(&Vs[r * AD + d4]) = vx;
@@ -145,24 +162,38 @@ attention_f32_kernel(const float* __restrict__ q, long long q_row_stride, const 
     const int qi = q0 + ty * 4 + i;
     if (qi < T) {
       const float inv = 1.0f / lrow[i];
-      *reinterpret_cast<float4*>(out + ((long long)seq * T + qi) * kDim + head * AD + tx * 4) =
-          make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+      store4(out + ((long long)seq * T + qi) * kDim + head * AD + tx * 4,
+             make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv));
     }
   }
+}
+
+template <typename TIO>
+static int launch_attn(cudaStream_t st, const TIO* q, long long q_row_stride, const TIO* k, const TIO* v,
+                       long long kv_row_stride, TIO* out, int nseq, int T, int n_heads, const float* slopes,
+                       int cross) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attention_f32_kernel<TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    configured = true;
+  }
+  dim3 grid((unsigned)((T + AQ - 1) / AQ), (unsigned)n_heads, (unsigned)nseq);
+  attention_f32_kernel<TIO><<<grid, ATHREADS, ATT_SMEM, st>>>(q, q_row_stride, k, v, kv_row_stride, out, nseq, T,
+                                                              slopes, cross);
+  return 1;
 }
 
 int launch_attention_f32(cudaStream_t st, const float* q, long long q_row_stride, const float* k, const float* v,
                          long long kv_row_stride, float* out, int nseq, int T, int n_heads, const float* slopes,
                          int cross) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    configured = true;
-  }
-  dim3 grid((unsigned)((T + AQ - 1) / AQ), (unsigned)n_heads, (unsigned)nseq);
-  attention_f32_kernel<<<grid, ATHREADS, ATT_SMEM, st>>>(q, q_row_stride, k, v, kv_row_stride, out, nseq, T,
-                                                         slopes, cross);
-  return 1;
+  return launch_attn<float>(st, q, q_row_stride, k, v, kv_row_stride, out, nseq, T, n_heads, slopes, cross);
+}
+
+// bf16 in / bf16 out, fp32 arithmetic (interim attention of the bf16 path)
+int launch_attention_simt_bf16(cudaStream_t st, const __nv_bfloat16* q, long long q_row_stride,
+                               const __nv_bfloat16* k, const __nv_bfloat16* v, long long kv_row_stride,
+                               __nv_bfloat16* out, int nseq, int T, int n_heads, const float* slopes, int cross) {
+  return launch_attn<__nv_bfloat16>(st, q, q_row_stride, k, v, kv_row_stride, out, nseq, T, n_heads, slopes, cross);
 }
 
 }  // namespace vapb

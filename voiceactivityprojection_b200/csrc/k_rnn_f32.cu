@@ -14,10 +14,13 @@ namespace vapb {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-template <int KIND /*0 LSTM, 1 GRU*/, int NB>
+__device__ __forceinline__ void put(float* p, float v) { *p = v; }
+__device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int KIND /*0 LSTM, 1 GRU*/, int NB, typename TOut>
 __global__ void __launch_bounds__(256)
 rnn_f32_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_t, const float* __restrict__ bhn,
-               float* __restrict__ out, long long out_seq_stride, int nseq, int T) {
+               TOut* __restrict__ out, long long out_seq_stride, int nseq, int T) {
   constexpr int G = KIND == 0 ? 4 : 3;
   constexpr int GH = G * kDim;
   __shared__ __align__(16) float hs[2][kDim][NB];
@@ -79,26 +82,26 @@ rnn_f32_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_t,
       }
       hprev[n] = h;
       hs[cur ^ 1][j][n] = h;
-      if (seq0 + n < nseq) out[(long long)(seq0 + n) * out_seq_stride + (long long)t * kDim + j] = h;
+      if (seq0 + n < nseq) put(out + (long long)(seq0 + n) * out_seq_stride + (long long)t * kDim + j, h);
     }
     __syncthreads();
     cur ^= 1;
   }
 }
 
-template <int KIND>
-static int launch_kind(cudaStream_t st, const float* xproj, const float* whh_t, const float* bhn, float* out,
+template <int KIND, typename TOut>
+static int launch_kind(cudaStream_t st, const float* xproj, const float* whh_t, const float* bhn, TOut* out,
                        long long out_seq_stride, int nseq, int T, int n_sm) {
   // sequences per CTA: as few as keeps every SM busy (W_hh streaming is per CTA)
   int nb = 1;
   while (nb < 4 && (nseq + nb - 1) / nb > n_sm) nb *= 2;
   const unsigned grid = (unsigned)((nseq + nb - 1) / nb);
   if (nb == 1)
-    rnn_f32_kernel<KIND, 1><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
+    rnn_f32_kernel<KIND, 1, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
   else if (nb == 2)
-    rnn_f32_kernel<KIND, 2><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
+    rnn_f32_kernel<KIND, 2, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
   else
-    rnn_f32_kernel<KIND, 4><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
+    rnn_f32_kernel<KIND, 4, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
   return 1;
 }
 
@@ -107,8 +110,18 @@ int launch_rnn_f32(cudaStream_t st, int kind, const float* xproj, const float* w
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  return kind == 0 ? launch_kind<0>(st, xproj, whh_t, bhn, out, out_seq_stride, nseq, T, n_sm)
-                   : launch_kind<1>(st, xproj, whh_t, bhn, out, out_seq_stride, nseq, T, n_sm);
+  return kind == 0 ? launch_kind<0, float>(st, xproj, whh_t, bhn, out, out_seq_stride, nseq, T, n_sm)
+                   : launch_kind<1, float>(st, xproj, whh_t, bhn, out, out_seq_stride, nseq, T, n_sm);
+}
+
+// fp32 recurrence, bf16 output (interim recurrence of the bf16 path)
+int launch_rnn_f32_bf16out(cudaStream_t st, int kind, const float* xproj, const float* whh_t, const float* bhn,
+                           __nv_bfloat16* out, long long out_seq_stride, int nseq, int T) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  return kind == 0 ? launch_kind<0, __nv_bfloat16>(st, xproj, whh_t, bhn, out, out_seq_stride, nseq, T, n_sm)
+                   : launch_kind<1, __nv_bfloat16>(st, xproj, whh_t, bhn, out, out_seq_stride, nseq, T, n_sm);
 }
 
 }  // namespace vapb
