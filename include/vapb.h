@@ -148,6 +148,19 @@ int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_
                        float* out1_f32, void* out1_bf16, int norm2, const float* g2, const float* b2,
                        void* out2_bf16, char* err, int err_len);
 
+/* Unit-test hooks for the tensor-core gAR recurrence (csrc/k_rnn_tc.cu).
+ * vapb_debug_rnn_pack (host only): nn.LSTM / nn.GRU parameters of one layer
+ * (weight_ih (G*256,256), weight_hh, bias_ih, bias_hh; kind 0 = LSTM, 1 = GRU) ->
+ * the kernel's packed fp32 [1024][512] weight and [1024] bias.
+ * vapb_debug_rnn_tc: one launch. x: device bf16, row (seq,t) at
+ * x + seq*x_seq_stride + t*x_row_stride; w_cat: device bf16 [1024][512];
+ * bias: device fp32 [1024]; out: device bf16 rows at out + seq*out_seq_stride + t*256. */
+int vapb_debug_rnn_pack(int kind, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                        float* w_cat, float* bias);
+int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_stride, int64_t x_row_stride,
+                      const void* w_cat, const float* bias, void* out, int64_t out_seq_stride, int nseq, int T,
+                      char* err, int err_len);
+
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);
 

@@ -92,3 +92,45 @@ def test_gemm_tc_residual_layernorm2_gelu_accumulate():
     assert (o1 - ref1).abs().max().item() <= 3e-3
     o2, _, _ = _gemm_tc(A, 0, K, W, 1, M, 256, K, norm1=2, g1=g1, b1=b1, act=2, accumulate=True, out1_init=o1)
     assert (o2 - 2 * ref1).abs().max().item() <= 6e-3
+
+
+def _rnn_tc(kind, x, w_ih, w_hh, b_ih, b_hh):
+    """x: (nseq, T, 256) bf16 cuda. Returns (nseq, T, 256) bf16."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    wcat = torch.empty((1024, 512), dtype=torch.float32)
+    bias = torch.empty(1024, dtype=torch.float32)
+    rc = lib.vapb_debug_rnn_pack(kind, w_ih.contiguous().data_ptr(), w_hh.contiguous().data_ptr(),
+                                 b_ih.contiguous().data_ptr(), b_hh.contiguous().data_ptr(), wcat.data_ptr(),
+                                 bias.data_ptr())
+    assert rc == 0
+    wcat_d, bias_d = wcat.cuda().bfloat16().contiguous(), bias.cuda()
+    nseq, T, _ = x.shape
+    out = torch.zeros((nseq, T, 256), device="cuda", dtype=torch.bfloat16)
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_rnn_tc(st, kind, x.data_ptr(), T * 256, 256, wcat_d.data_ptr(), bias_d.data_ptr(),
+                               out.data_ptr(), T * 256, nseq, T, err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("kind,nseq,T", [(0, 2, 5), (0, 37, 233), (1, 16, 64), (1, 70, 200), (0, 64, 2000)])
+def test_rnn_tc_matches_torch(kind, nseq, T):
+    """tcgen05 cluster recurrence vs nn.LSTM / nn.GRU (fp32, on the bf16-rounded weights and inputs)."""
+    torch.manual_seed(100 * kind + nseq + T)
+    cell = (torch.nn.LSTM if kind == 0 else torch.nn.GRU)(256, 256, batch_first=True)
+    with torch.no_grad():
+        for p in cell.parameters():
+            p.copy_(p.bfloat16().float() if p.ndim == 2 else p)
+    x = (torch.randn(nseq, T, 256) * 0.7).bfloat16()
+    with torch.no_grad():
+        ref, _ = cell(x.float())
+    out = _rnn_tc(kind, x.cuda().contiguous(), cell.weight_ih_l0.detach(), cell.weight_hh_l0.detach(),
+                  cell.bias_ih_l0.detach(), cell.bias_hh_l0.detach()).float().cpu()
+    err = (out - ref).abs().max().item()
+    # h is rounded to bf16 every step (|h| < 1 -> 2^-9 abs) and fed back; tanh/sigmoid are MUFU approximations
+    assert err <= 2e-2, f"max-abs {err}"
+    assert (out - ref).abs().mean().item() <= 2e-3

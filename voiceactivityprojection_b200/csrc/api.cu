@@ -586,6 +586,31 @@ int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_
   return VAPB_OK;
 }
 
+int vapb_debug_rnn_pack(int kind, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                        float* w_cat, float* bias) {
+  if (!w_ih || !w_hh || !b_ih || !b_hh || !w_cat || !bias || (kind != 0 && kind != 1)) return VAPB_E_INVALID;
+  rnn_tc_pack(kind, w_ih, w_hh, b_ih, b_hh, w_cat, bias);
+  return VAPB_OK;
+}
+
+int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_stride, int64_t x_row_stride,
+                      const void* w_cat, const float* bias, void* out, int64_t out_seq_stride, int nseq, int T,
+                      char* err, int err_len) {
+  std::string msg;
+  int rc = launch_rnn_tc((cudaStream_t)stream, kind, reinterpret_cast<const __nv_bfloat16*>(x), x_seq_stride,
+                         x_row_stride, reinterpret_cast<const __nv_bfloat16*>(w_cat), bias,
+                         reinterpret_cast<__nv_bfloat16*>(out), out_seq_stride, nseq, T, &msg);
+  if (rc >= 0) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+  }
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches) {
   if (!h || !launches) return VAPB_E_INVALID;
   *launches = h->m.launches;

@@ -93,6 +93,14 @@ int launch_attention_simt_bf16(cudaStream_t st, const __nv_bfloat16* q, long lon
 int launch_rnn_f32_bf16out(cudaStream_t st, int kind, const float* xproj, const float* whh_t, const float* bhn,
                            __nv_bfloat16* out, long long out_seq_stride, int nseq, int T);
 
+// Tensor-core recurrence (k_rnn_tc.cu). x rows at x + seq*x_seq_stride + t*x_row_stride (elements, bf16);
+// out rows at out + seq*out_seq_stride + t*256. Returns launches or -1.
+int launch_rnn_tc(cudaStream_t st, int kind, const __nv_bfloat16* x, long long x_seq_stride, long long x_row_stride,
+                  const __nv_bfloat16* w_cat, const float* bias, __nv_bfloat16* out, long long out_seq_stride,
+                  int nseq, int T, std::string* err);
+void rnn_tc_pack(int kind, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                 float* w_cat /*[1024][512]*/, float* bias /*[1024]*/);
+
 int launch_vad_head(cudaStream_t st, const float* x /*[2B][T][256] channel-major*/, const float* w,
                     const float* b, int batch, int T, float* vad_logits /*(B,T,2) or null*/,
                     float* vad_sig /*(B,T,2) or null*/);

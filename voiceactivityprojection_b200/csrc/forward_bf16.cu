@@ -28,7 +28,8 @@ struct LayerW16 {
 struct State16 {
   void* arena = nullptr;
   const bf16* conv_w[5];
-  const bf16* rnn_wih[kMaxLayers];
+  const bf16* rnn_wcat[kMaxLayers];   // [1024][512] packed [W_ih | W_hh] (k_rnn_tc.cu)
+  const float* rnn_bias[kMaxLayers];  // [1024]
   const bf16* ds_w;
   LayerW16 chan[kMaxLayers], cross[kMaxLayers];
   const bf16 *comb_a, *comb_b, *head_w;
@@ -37,13 +38,12 @@ struct State16 {
 struct Plan16 {
   int mb;
   long long lo[4], lpad[4], rnn_lpad;
-  size_t act[4], act4, xproj, rnn[2], stage[2 * kMaxLayers + 1], xs, xa, xb, z, qkv, kvc, qc, y, h, comb, combb,
+  size_t act[4], act4, rnn[2], stage[2 * kMaxLayers + 1], xs, xa, xb, z, qkv, kvc, qc, y, h, comb, combb,
       bytes;
 };
 
 Plan16 make_plan(const Model& m, const Geometry& g) {
   Plan16 p{};
-  const int G = m.ar_kind == 0 ? 4 : 3;
   const long long per_seq0 = (g.L[0] + 16) * kDim * 2;
   long long mb = (4LL << 30) / per_seq0;
   if (mb < 1) mb = 1;
@@ -61,7 +61,6 @@ Plan16 make_plan(const Model& m, const Geometry& g) {
     off = align_up(off + (size_t)mb * lp * kDim * 2);
   }
   p.act4 = off;  off = align_up(off + (size_t)g.nseq * g.L[4] * kDim * 2);
-  p.xproj = off; off = align_up(off + (size_t)g.nseq * g.L[4] * G * kDim * 4);
   p.rnn_lpad = 4 + g.L[4] + (g.L[4] & 1);  // even, so the stride-2 tensor map strides nest
   for (int i = 0; i < 2; ++i) {
     p.rnn[i] = off;
@@ -128,6 +127,12 @@ int bf16_prepare(Model& m) {
     memcpy(host.data() + off, b.data(), b.size() * 2);
     fixes.push_back({slot, off});
   };
+  auto put_f32 = [&](const float** slot, const std::vector<float>& v) {
+    const size_t off = (host.size() + 1023) / 1024 * 1024;
+    host.resize(off + v.size() * 4);
+    memcpy(host.data() + off, v.data(), v.size() * 4);
+    fixes.push_back({reinterpret_cast<const bf16**>(slot), off});
+  };
   auto T = [&](const std::string& k) -> const HostTensor& { return m.staged[k]; };
   auto conv_nk = [&](const HostTensor& t) {  // (out,in,k) -> [out][tap*in + cin]
     const int64_t co = t.shape[0], ci = t.shape[1], k = t.shape[2];
@@ -144,7 +149,14 @@ int bf16_prepare(Model& m) {
   };
   const std::string GE = "encoder.encoder.gEncoder.", AR = "encoder.encoder.gAR.baseNet.";
   for (int i = 1; i < 5; ++i) put(&s->conv_w[i], conv_nk(T(GE + "conv" + std::to_string(i) + ".weight")));
-  for (int l = 0; l < m.ar_layers; ++l) put(&s->rnn_wih[l], T(AR + "weight_ih_l" + std::to_string(l)).data);
+  for (int l = 0; l < m.ar_layers; ++l) {
+    const std::string n = std::to_string(l);
+    std::vector<float> wcat((size_t)1024 * 512), bias(1024);
+    rnn_tc_pack(m.ar_kind, T(AR + "weight_ih_l" + n).data.data(), T(AR + "weight_hh_l" + n).data.data(),
+                T(AR + "bias_ih_l" + n).data.data(), T(AR + "bias_hh_l" + n).data.data(), wcat.data(), bias.data());
+    put(&s->rnn_wcat[l], wcat);
+    put_f32(&s->rnn_bias[l], bias);
+  }
   put(&s->ds_w, conv_nk(T("encoder.downsample.1.weight")));
   auto layer = [&](const std::string& p, bool cross, LayerW16& lw) {
     put(&lw.wqkv, cat_rows({&T(p + "mha.query.weight"), &T(p + "mha.key.weight"), &T(p + "mha.value.weight")}));
@@ -189,7 +201,6 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
   const Plan16 p = make_plan(m, g);
   const Weights& w = m.w32;  // fp32 vectors (biases, norm affine, slopes, va head) and conv0
   Ctx cx{m, st};
-  const int G = m.ar_kind == 0 ? 4 : 3;
   const int nseq = g.nseq;
   const long long T = g.T, L4 = g.L[4];
   auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
@@ -241,15 +252,14 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
   const bf16* rnn_in = H(p.act4);
   RowMap rnn_in_map{L4 * kDim, kDim};
   for (int l = 0; l < m.ar_layers; ++l) {
-    Epilogue e{};
-    e.bias = w.rnn_bx[l];
-    e.out1_map = RowMap{L4 * G * kDim, (long long)G * kDim};
-    cx.gemm(rnn_in, rnn_in_map, s.rnn_wih[l], nseq, (int)L4, G * kDim, kDim, e, F(p.xproj), nullptr);
     bf16* rnn_out = H(p.rnn[l & 1]) + 4 * kDim;
     {
       ProfScope ps(m, st, CAT_RNN);
-      m.launches += launch_rnn_f32_bf16out(st, m.ar_kind, F(p.xproj), w.rnn_whh_t[l], w.rnn_bhn[l], rnn_out,
-                                           p.rnn_lpad * kDim, nseq, (int)L4);
+      std::string err;
+      const int n = launch_rnn_tc(st, m.ar_kind, rnn_in, rnn_in_map.seq_stride, rnn_in_map.row_stride, s.rnn_wcat[l],
+                                  s.rnn_bias[l], rnn_out, p.rnn_lpad * kDim, nseq, (int)L4, &err);
+      if (n < 0) { m.err = err; return -3; }
+      m.launches += n;
     }
     rnn_in = rnn_out;
     rnn_in_map = RowMap{p.rnn_lpad * kDim, kDim};

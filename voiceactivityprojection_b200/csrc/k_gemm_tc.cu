@@ -316,8 +316,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                    const uint32_t* box, std::string* err) {
+bool make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+               const uint64_t* strides_elems, const uint32_t* box, int swizzle, std::string* err) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     if (err) *err = "cuTensorMapEncodeTiled not available";
@@ -329,23 +329,34 @@ bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t
     gdim[i] = dims[i];
     bdim[i] = box[i];
     estride[i] = 1;
-    if (i > 0) gstride[i - 1] = strides_elems[i - 1] * 2;  // bytes
+    if (i > 0) gstride[i - 1] = strides_elems[i - 1] * elem_bytes;  // bytes
   }
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride,
-                        bdim, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) {
-      char buf[256];
-      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu] strides [%llu,%llu] box [%u,%u,%u]",
-               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
-               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_elems[0] : 0),
-               (unsigned long long)(rank > 2 ? strides_elems[1] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+      char buf[320];
+      snprintf(buf, sizeof buf,
+               "cuTensorMapEncodeTiled failed (%d): rank %d elem %d dims [%llu,%llu,%llu,%llu] strides [%llu,%llu,%llu] box "
+               "[%u,%u,%u,%u]",
+               (int)r, rank, elem_bytes, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+               (unsigned long long)(rank > 1 ? strides_elems[0] : 0), (unsigned long long)(rank > 2 ? strides_elems[1] : 0),
+               (unsigned long long)(rank > 3 ? strides_elems[2] : 0), box[0], rank > 1 ? box[1] : 0,
+               rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
       *err = buf;
     }
     return false;
   }
   return true;
+}
+
+bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box, std::string* err) {
+  return make_tmap(map, base, 2, rank, dims, strides_elems, box, 128, err);
 }
 
 int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err) {
