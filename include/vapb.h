@@ -159,7 +159,8 @@ int vapb_debug_rnn_pack(int kind, const float* w_ih, const float* w_hh, const fl
                         float* w_cat, float* bias);
 int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_stride, int64_t x_row_stride,
                       const void* w_cat, const float* bias, void* out, int64_t out_seq_stride, int nseq, int T,
-                      char* err, int err_len);
+                      char* err, int err_len, long long* dbg_clocks /* device [32][8] SM-clock samples or NULL */,
+                      int groups /* 16-sequence groups per cluster: 2..4, 0 = auto */);
 
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);

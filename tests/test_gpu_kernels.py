@@ -94,7 +94,7 @@ def test_gemm_tc_residual_layernorm2_gelu_accumulate():
     assert (o2 - 2 * ref1).abs().max().item() <= 6e-3
 
 
-def _rnn_tc(kind, x, w_ih, w_hh, b_ih, b_hh):
+def _rnn_tc(kind, x, w_ih, w_hh, b_ih, b_hh, groups=0):
     """x: (nseq, T, 256) bf16 cuda. Returns (nseq, T, 256) bf16."""
     from voiceactivityprojection_b200 import _lib
 
@@ -111,14 +111,16 @@ def _rnn_tc(kind, x, w_ih, w_hh, b_ih, b_hh):
     err = C.create_string_buffer(512)
     st = torch.cuda.current_stream().cuda_stream
     rc = lib.vapb_debug_rnn_tc(st, kind, x.data_ptr(), T * 256, 256, wcat_d.data_ptr(), bias_d.data_ptr(),
-                               out.data_ptr(), T * 256, nseq, T, err, 512)
+                               out.data_ptr(), T * 256, nseq, T, err, 512, None, groups)
     assert rc == 0, err.value.decode()
     torch.cuda.synchronize()
     return out
 
 
-@pytest.mark.parametrize("kind,nseq,T", [(0, 2, 5), (0, 37, 233), (1, 16, 64), (1, 70, 200), (0, 64, 2000)])
-def test_rnn_tc_matches_torch(kind, nseq, T):
+@pytest.mark.parametrize("kind,nseq,T,groups", [(0, 2, 5, 0), (0, 37, 233, 1602), (1, 16, 64, 3202), (1, 70, 200, 1604),
+                                                (0, 64, 2000, 0), (0, 300, 50, 3202), (0, 512, 40, 0),
+                                                (1, 512, 33, 0)])
+def test_rnn_tc_matches_torch(kind, nseq, T, groups):
     """tcgen05 cluster recurrence vs nn.LSTM / nn.GRU (fp32, on the bf16-rounded weights and inputs)."""
     torch.manual_seed(100 * kind + nseq + T)
     cell = (torch.nn.LSTM if kind == 0 else torch.nn.GRU)(256, 256, batch_first=True)
@@ -129,7 +131,7 @@ def test_rnn_tc_matches_torch(kind, nseq, T):
     with torch.no_grad():
         ref, _ = cell(x.float())
     out = _rnn_tc(kind, x.cuda().contiguous(), cell.weight_ih_l0.detach(), cell.weight_hh_l0.detach(),
-                  cell.bias_ih_l0.detach(), cell.bias_hh_l0.detach()).float().cpu()
+                  cell.bias_ih_l0.detach(), cell.bias_hh_l0.detach(), groups).float().cpu()
     err = (out - ref).abs().max().item()
     # h is rounded to bf16 every step (|h| < 1 -> 2^-9 abs) and fed back; tanh/sigmoid are MUFU approximations
     assert err <= 2e-2, f"max-abs {err}"

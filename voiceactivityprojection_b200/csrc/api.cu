@@ -595,11 +595,11 @@ int vapb_debug_rnn_pack(int kind, const float* w_ih, const float* w_hh, const fl
 
 int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_stride, int64_t x_row_stride,
                       const void* w_cat, const float* bias, void* out, int64_t out_seq_stride, int nseq, int T,
-                      char* err, int err_len) {
+                      char* err, int err_len, long long* dbg_clocks, int groups) {
   std::string msg;
   int rc = launch_rnn_tc((cudaStream_t)stream, kind, reinterpret_cast<const __nv_bfloat16*>(x), x_seq_stride,
                          x_row_stride, reinterpret_cast<const __nv_bfloat16*>(w_cat), bias,
-                         reinterpret_cast<__nv_bfloat16*>(out), out_seq_stride, nseq, T, &msg);
+                         reinterpret_cast<__nv_bfloat16*>(out), out_seq_stride, nseq, T, &msg, dbg_clocks, groups);
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }

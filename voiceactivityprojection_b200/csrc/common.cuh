@@ -97,7 +97,7 @@ int launch_rnn_f32_bf16out(cudaStream_t st, int kind, const float* xproj, const 
 // out rows at out + seq*out_seq_stride + t*256. Returns launches or -1.
 int launch_rnn_tc(cudaStream_t st, int kind, const __nv_bfloat16* x, long long x_seq_stride, long long x_row_stride,
                   const __nv_bfloat16* w_cat, const float* bias, __nv_bfloat16* out, long long out_seq_stride,
-                  int nseq, int T, std::string* err);
+                  int nseq, int T, std::string* err, long long* dbg = nullptr, int groups = 0);
 void rnn_tc_pack(int kind, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                  float* w_cat /*[1024][512]*/, float* bias /*[1024]*/);
 
