@@ -162,6 +162,14 @@ int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_strid
                       char* err, int err_len, long long* dbg_clocks /* device [32][8] SM-clock samples or NULL */,
                       int groups /* 16-sequence groups per cluster: 2..4, 0 = auto */);
 
+/* Unit-test hook for the tcgen05 fused attention (csrc/k_attn_tc.cu): one launch.
+ * q/k/v: device bf16, row (seq,t) at ptr + (seq*T + t)*row_stride, 256 = n_heads*64
+ * columns used; out: dense bf16 (nseq*T, 256); slopes: device fp32 [n_heads].
+ * cross != 0: K/V of sequence (seq + nseq/2) % nseq (the other speaker channel). */
+int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const void* k, const void* v,
+                       int64_t kv_row_stride, void* out, int nseq, int T, int n_heads, const float* slopes,
+                       int cross, char* err, int err_len);
+
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);
 

@@ -136,3 +136,53 @@ def test_rnn_tc_matches_torch(kind, nseq, T, groups):
     # h is rounded to bf16 every step (|h| < 1 -> 2^-9 abs) and fed back; tanh/sigmoid are MUFU approximations
     assert err <= 2e-2, f"max-abs {err}"
     assert (out - ref).abs().mean().item() <= 2e-3
+
+
+def _attn_ref(q, k, v, slopes, cross):
+    """fp32 torch statement of vap/modules.py:82-110,169-202 on (nseq, T, 256) inputs."""
+    nseq, T, _ = q.shape
+    H = slopes.numel()
+    if cross:
+        idx = (torch.arange(nseq, device=q.device) + nseq // 2) % nseq
+        k, v = k[idx], v[idx]
+    qh, kh, vh = (t.float().reshape(nseq, T, H, 64).transpose(1, 2) for t in (q, k, v))
+    att = qh @ kh.transpose(-1, -2) * (1.0 / 16.0)
+    j = torch.arange(T, device=q.device, dtype=torch.float32)
+    bias = 1.0 + slopes.view(1, H, 1, 1) * j.view(1, 1, 1, T)
+    mask = torch.ones(T, T, device=q.device, dtype=torch.bool).tril()
+    att = (att + bias).masked_fill(~mask, float("-inf")).softmax(-1)
+    return (att @ vh).transpose(1, 2).reshape(nseq, T, 256)
+
+
+@pytest.mark.parametrize("nseq,T,cross,packed,scale", [(2, 117, 0, True, 1.0), (4, 128, 1, False, 1.0),
+                                                       (2, 1000, 0, True, 1.0), (6, 500, 1, False, 4.0),
+                                                       (80, 300, 0, True, 8.0), (2, 1250, 1, False, 1.0)])
+def test_attention_tc_matches_torch(nseq, T, cross, packed, scale):
+    """tcgen05 fused causal ALiBi attention vs a plain fp32 softmax(QK^T/16 + 1 + m*j) V."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(nseq * 1000 + T)
+    slopes = torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda")
+    if packed:  # self-attention layout: q | k | v in one (nseq*T, 768) buffer
+        buf = (torch.randn((nseq, T, 768), device="cuda", generator=g) * scale).bfloat16()
+        q, k, v = buf[..., :256], buf[..., 256:512], buf[..., 512:]
+        qs = ks = 768
+    else:  # cross-attention layout: q alone, k | v in one (nseq*T, 512) buffer
+        q = (torch.randn((nseq, T, 256), device="cuda", generator=g) * scale).bfloat16()
+        kv = (torch.randn((nseq, T, 512), device="cuda", generator=g) * scale).bfloat16()
+        k, v = kv[..., :256], kv[..., 256:]
+        qs, ks = 256, 512
+    out = torch.full((nseq, T, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_attn_tc(st, q.data_ptr(), qs, k.data_ptr(), v.data_ptr(), ks, out.data_ptr(), nseq, T, 4,
+                                slopes.data_ptr(), cross, err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, slopes, cross)
+    d = (out.float() - ref).abs()
+    assert torch.isfinite(out.float()).all()
+    # P and the output are rounded to bf16 (2^-9 relative); V is O(scale)
+    assert d.max().item() <= 2e-2 * scale, d.max().item()
+    assert d.mean().item() <= 2e-3 * scale

@@ -611,6 +611,27 @@ int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_strid
   return VAPB_OK;
 }
 
+int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const void* k, const void* v,
+                       int64_t kv_row_stride, void* out, int nseq, int T, int n_heads, const float* slopes,
+                       int cross, char* err, int err_len) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  std::string msg;
+  typedef const __nv_bfloat16* bp;
+  int rc = launch_attention_tc((cudaStream_t)stream, (bp)q, q_row_stride, (bp)k, (bp)v, kv_row_stride,
+                               reinterpret_cast<__nv_bfloat16*>(out), nseq, T, n_heads, slopes, cross, n_sm, &msg);
+  if (rc >= 0) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+  }
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches) {
   if (!h || !launches) return VAPB_E_INVALID;
   *launches = h->m.launches;

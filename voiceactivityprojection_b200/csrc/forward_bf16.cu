@@ -308,8 +308,11 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     if (cx.rc) return cx.rc;
     {
       ProfScope ps(m, st, CAT_ATTN);
-      m.launches += launch_attention_simt_bf16(st, H(p.qkv), 3 * kDim, H(p.qkv) + kDim, H(p.qkv) + 2 * kDim,
-                                               3 * kDim, H(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0);
+      std::string err;
+      const int n = launch_attention_tc(st, H(p.qkv), 3 * kDim, H(p.qkv) + kDim, H(p.qkv) + 2 * kDim, 3 * kDim, H(p.y),
+                                        nseq, (int)T, m.num_heads, lw.slopes, 0, m.n_sm, &err);
+      if (n < 0) { m.err = err; return -3; }
+      m.launches += n;
     }
     float* x_mid = cross ? F(p.xa) : F(p.xb);
     {
@@ -333,8 +336,11 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       if (cx.rc) return cx.rc;
       {
         ProfScope ps(m, st, CAT_ATTN);
-        m.launches += launch_attention_simt_bf16(st, H(p.qc), kDim, H(p.kvc), H(p.kvc) + kDim, 2 * kDim, H(p.y),
-                                                 nseq, (int)T, m.num_heads, lw.slopes_cross, 1);
+        std::string err;
+        const int n = launch_attention_tc(st, H(p.qc), kDim, H(p.kvc), H(p.kvc) + kDim, 2 * kDim, H(p.y), nseq, (int)T,
+                                          m.num_heads, lw.slopes_cross, 1, m.n_sm, &err);
+        if (n < 0) { m.err = err; return -3; }
+        m.launches += n;
       }
       Epilogue e{};
       e.resid = x_mid;

@@ -1,0 +1,357 @@
+// BF16 fused causal ALiBi attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+// Reference: vap/modules.py:82-110 (scores, softmax, PV), :169-202 (bias 1 + m_h*j on
+// allowed positions, -inf above the diagonal), :52 (scale 1/sqrt(dim) = 1/16).
+// Self- and cross-attention share the kernel; cross-attention reads K/V rows of the
+// other speaker channel's sequence (vap/modules.py:287-289).
+//
+// Work item = (sequence, head pair, 128-query tile). One persistent CTA per SM walks the
+// items from the longest (last query tile) to the shortest. The two heads of a pair are two
+// independent "slots" that ping-pong: while the softmax warps of one slot are on the CUDA
+// cores / MUFU, the other slot's QK^T and PV run on the tensor pipe.
+//
+// Per slot and 128-key tile (keys are visited from the diagonal tile DOWN to key 0: the
+// ALiBi bias grows with the key index, so the running row maximum is almost always set by
+// the first tile and the accumulator rescale below is rare):
+//   S[128 q][128 k]  = Q K^T      tcgen05.mma, Q and K tiles K-major SW128 in smem (TMA)
+//   softmax          : one thread per query row (TMEM lane); two passes over S with
+//                      tcgen05.ld (row max, then exp2 / row sum); P is written back to
+//                      TMEM as packed bf16 pairs
+//   O[128 q][64 d]  += P V        tcgen05.mma, A = P from TMEM, B = V tile MN-major SW128
+// The T x T score matrix never exists; O stays in TMEM for the whole row of tiles.
+#include <string>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace vapb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int AT_TILE = 128 * 64 * 2;  // one 128-row x 64-column bf16 tile (Q, K or V of one head)
+constexpr int AT_THREADS = 384;        // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 softmax slot 0, 8-11 softmax slot 1
+constexpr int AT_OFF_Q = 0;                        // [slot]
+constexpr int AT_OFF_K = 2 * AT_TILE;              // [slot][stage]
+constexpr int AT_OFF_V = AT_OFF_K + 4 * AT_TILE;   // [slot][stage]
+constexpr int AT_OFF_BAR = AT_OFF_V + 4 * AT_TILE;
+constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024 /*alignment slack*/;
+// TMEM columns of a slot: S fp32 [0,128), P bf16x2 [128,192), O fp32 [192,256)
+constexpr int AT_COL_P = 128, AT_COL_O = 192, AT_SLOT_COLS = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct alignas(64) AttnParams {
+  CUtensorMap tq, tk, tv;  // (256 head*d, T, nseq) bf16, SW128, box (64, 128, 1)
+  __nv_bfloat16* out;      // (nseq*T, 256)
+  const float* slopes;     // [n_heads]
+  int nseq, T, nqt, head_pairs, n_items, cross;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Item {
+  int qi, seq, hp;
+};
+__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+  const int per_q = p.nseq * p.head_pairs;
+  Item it;
+  it.qi = p.nqt - 1 - item / per_q;
+  const int rem = item % per_q;
+  it.seq = rem / p.head_pairs;
+  it.hp = rem % p.head_pairs;
+  return it;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + AT_OFF_BAR;
+  auto q_full = [&](int s) { return bar_base + 8u * s; };
+  auto q_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto kv_full = [&](int s, int st) { return bar_base + 8u * (4 + s * 2 + st); };
+  auto kv_empty = [&](int s, int st) { return bar_base + 8u * (8 + s * 2 + st); };
+  auto s_full = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto p_full = [&](int s) { return bar_base + 8u * (14 + s); };
+  auto o_final = [&](int s) { return bar_base + 8u * (16 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 18;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tq);
+    prefetch_tmap(&p.tk);
+    prefetch_tmap(&p.tv);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+      for (int st = 0; st < 2; ++st) {
+        mbar_init(kv_full(s, st), 1);
+        mbar_init(kv_empty(s, st), 1);
+      }
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 128);
+      mbar_init(o_final(s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      uint32_t n_item = 0, kvc[2] = {0, 0};
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_item) {
+        const Item it = decode_item(p, item);
+        const int kvseq = p.cross ? (it.seq + p.nseq / 2) % p.nseq : it.seq;
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(q_empty(s), (n_item & 1u) ^ 1u);
+          mbar_arrive_expect_tx(q_full(s), AT_TILE);
+          tma_load_3d(smem_base + AT_OFF_Q + s * AT_TILE, &p.tq, q_full(s), (it.hp * 2 + s) * 64, it.qi * 128, it.seq);
+        }
+        for (int kt = it.qi; kt >= 0; --kt) {
+          for (int s = 0; s < 2; ++s) {
+            const int st = kvc[s] & 1;
+            mbar_wait(kv_empty(s, st), ((kvc[s] >> 1) & 1u) ^ 1u);
+            ++kvc[s];
+            mbar_arrive_expect_tx(kv_full(s, st), 2 * AT_TILE);
+            const int col = (it.hp * 2 + s) * 64;
+            tma_load_3d(smem_base + AT_OFF_K + (s * 2 + st) * AT_TILE, &p.tk, kv_full(s, st), col, kt * 128, kvseq);
+            tma_load_3d(smem_base + AT_OFF_V + (s * 2 + st) * AT_TILE, &p.tv, kv_full(s, st), col, kt * 128, kvseq);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+      uint32_t n_item = 0, kvc[2] = {0, 0}, pc[2] = {0, 0};
+      auto issue_qk = [&](int s) {
+        const int st = kvc[s] & 1;
+        mbar_wait(kv_full(s, st), (kvc[s] >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t qa = smem_base + AT_OFF_Q + s * AT_TILE;
+        const uint32_t ka = smem_base + AT_OFF_K + (s * 2 + st) * AT_TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + s * AT_SLOT_COLS, make_smem_desc_sw128(qa + k * 32, 0, 1024),
+                    make_smem_desc_sw128(ka + k * 32, 0, 1024), idesc_qk, k != 0);
+        umma_commit(s_full(s));
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_item) {
+        const Item it = decode_item(p, item);
+        const int ntiles = it.qi + 1;
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(q_full(s), n_item & 1u);
+          issue_qk(s);
+        }
+        for (int n = 0; n < ntiles; ++n) {
+          for (int s = 0; s < 2; ++s) {
+            mbar_wait(p_full(s), pc[s] & 1u);
+            ++pc[s];
+            tc_fence_after();
+            const int st = kvc[s] & 1;
+            const uint32_t va = smem_base + AT_OFF_V + (s * 2 + st) * AT_TILE;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(tmem_base + s * AT_SLOT_COLS + AT_COL_O, tmem_base + s * AT_SLOT_COLS + AT_COL_P + kk * 8,
+                           make_smem_desc_sw128(va + kk * 2048, 1024, 1024), idesc_pv, (n | kk) != 0);
+            umma_commit(kv_empty(s, st));
+            ++kvc[s];
+            if (n + 1 < ntiles) {
+              issue_qk(s);
+            } else {
+              umma_commit(q_empty(s));
+              umma_commit(o_final(s));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== softmax: slot = head of the pair, thread = one query row (TMEM lane)
+    const int s = (warp - 4) >> 2, quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + s * AT_SLOT_COLS;
+    const uint32_t t_p = t_s + AT_COL_P, t_o = t_s + AT_COL_O;
+    constexpr float SC = 0.0625f * kLog2e;
+    uint32_t sc_cnt = 0, oc_cnt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      const int head = it.hp * 2 + s;
+      const float slope2 = p.slopes[head] * kLog2e;
+      float m = -INFINITY, l = 0.f;
+      for (int n = 0; n <= it.qi; ++n) {
+        const int k0 = (it.qi - n) * 128;
+        const bool diag = n == 0;
+        const int nchunks = diag ? quad + 1 : 4;  // 32-key chunks with a visible key for this warp's rows
+        const float base = fmaf(slope2, (float)k0, kLog2e);
+        mbar_wait(s_full(s), sc_cnt & 1u);
+        ++sc_cnt;
+        tc_fence_after();
+        // pass A: row maximum of the biased scores (log2 domain)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_s + c * 32, r);
+          tmem_ld_wait();
+          const float cb = fmaf(slope2, (float)(c * 32), base);
+          const bool edge = diag && c == quad;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb));
+            if (edge && i > lane) t = -INFINITY;
+            mx = fmaxf(mx, t);
+          }
+        }
+        const float m_new = fmaxf(m, mx);
+        if (n > 0 && __any_sync(0xffffffffu, m_new > m)) {
+          // rare: rescale the accumulator (PV of the previous tile has completed: s_full was committed after it)
+          const float alpha = ex2_fast(m - m_new);
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_o + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(t_o + c * 32, r);
+          }
+        }
+        m = m_new;
+        // pass B: p = 2^(t - m), row sum, P -> TMEM as bf16 pairs (column c holds keys 2c, 2c+1)
+        const float base_m = base - m;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          if (c < nchunks) {
+            uint32_t r[32];
+            tmem_ld32(t_s + c * 32, r);
+            tmem_ld_wait();
+            const float cb = fmaf(slope2, (float)(c * 32), base_m);
+            const bool edge = diag && c == quad;
+            float ps = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb)));
+              float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
+              if (edge && i > lane) p0 = 0.f;
+              if (edge && i + 1 > lane) p1 = 0.f;
+              ps += p0 + p1;
+              pk[i >> 1] = pack_bf16(p0, p1);
+            }
+            l += ps;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
+          tmem_st16(t_p + c * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full(s));
+      }
+      // epilogue: O / l -> bf16 -> out[(seq*T + q), head*64 .. +64)
+      mbar_wait(o_final(s), oc_cnt & 1u);
+      ++oc_cnt;
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const int q = it.qi * 128 + row;
+      __nv_bfloat16* dst = p.out + ((long long)it.seq * p.T + q) * kDim + head * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_o + c * 32, r);
+        tmem_ld_wait();
+        if (q < p.T) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = u;
+          }
+        }
+      }
+      tc_fence_before();  // the O reads are ordered before the next item's p_full arrivals
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// q/k/v: bf16 rows of 256 (= n_heads*64) at ptr + (seq*T + t)*row_stride; out: dense (nseq*T, 256) bf16.
+int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row_stride, const __nv_bfloat16* k,
+                        const __nv_bfloat16* v, long long kv_row_stride, __nv_bfloat16* out, int nseq, int T,
+                        int n_heads, const float* slopes, int cross, int n_sm, std::string* err) {
+  if (n_heads % 2 || n_heads * 64 != kDim) {
+    if (err) *err = "attention_tc: needs an even number of heads of 64";
+    return -1;
+  }
+  if (cross && (nseq % 2)) {
+    if (err) *err = "attention_tc: cross attention needs both channels";
+    return -1;
+  }
+  AttnParams p{};
+  const uint32_t box[3] = {64, 128, 1};
+  auto mk = [&](CUtensorMap* m, const void* base, long long rs) {
+    const uint64_t dims[3] = {(uint64_t)kDim, (uint64_t)T, (uint64_t)nseq};
+    const uint64_t strides[2] = {(uint64_t)rs, (uint64_t)rs * (uint64_t)T};
+    return make_tmap(m, base, 2, 3, dims, strides, box, 128, err);
+  };
+  if (!mk(&p.tq, q, q_row_stride) || !mk(&p.tk, k, kv_row_stride) || !mk(&p.tv, v, kv_row_stride)) return -1;
+  p.out = out;
+  p.slopes = slopes;
+  p.nseq = nseq;
+  p.T = T;
+  p.nqt = (T + 127) / 128;
+  p.head_pairs = n_heads / 2;
+  p.n_items = p.nqt * nseq * p.head_pairs;
+  p.cross = cross;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {
+      if (err) *err = "attention_tc: cannot reserve shared memory";
+      return -1;
+    }
+    configured = true;
+  }
+  const int grid = p.n_items < n_sm ? p.n_items : n_sm;
+  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p);
+  return 1;
+}
+
+}  // namespace vapb
