@@ -1,0 +1,165 @@
+"""CPU tests of the host side: C-ABI surface, session stitching, wav loading,
+config/argparse mirror, JSON contract. No kernel is launched here."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_header():
+    from voiceactivityprojection_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "vapb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vapb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/vapb.h but not exported by libvapb.so"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert b"sm_100a" in lib.vapb_build_info()
+
+
+def test_frames_chain_matches_oracle():
+    from oracle import vap_oracle as O
+    from voiceactivityprojection_b200 import _lib
+
+    for n in [32159, 37392, 160000, 320000, 400000, 9600000, 33333]:
+        assert _lib.frames(n) == tuple(O.n_frames(n))[-2:]
+    with pytest.raises(_lib.VapbError):
+        _lib.frames(3)
+
+
+def test_no_cpu_fallback():
+    from oracle import synth
+    from voiceactivityprojection_b200 import VapConfig, VapGPT
+
+    m = VapGPT(VapConfig())
+    m.load_state_dict(synth.make_state_dict(0))
+    with pytest.raises(RuntimeError):
+        m.probs(torch.zeros(1, 2, 40000))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 40000))
+    with pytest.raises(NotImplementedError):
+        m.train()
+
+
+class _FakeModel:
+    """Cheap stand-in with the facade's probs() contract: frame features are
+    deterministic functions of the window's samples, so stitching is checkable."""
+    sample_rate, frame_hz = 16000, 50
+
+    def probs(self, w, **kw):
+        B, _, S = w.shape
+        T = S // 320
+        f = w[..., : T * 320].reshape(B, 2, T, 320)
+        a = f.mean(-1).transpose(1, 2)                      # (B, T, 2)
+        pos = torch.arange(T, dtype=w.dtype, device=w.device)[None, :, None]  # position inside the window matters
+        return {"probs": (a.sum(-1, keepdim=True) + pos).repeat(1, 1, 4), "vad": a + pos, "p_now": a - pos,
+                "p_future": a * 2 + pos, "H": a.sum(-1) + pos[..., 0], "loss": a[:, : T - 100, 0]}
+
+
+def _reference_loop(wav, model, context_time=20, step_time=5):
+    """Restatement of run.py:23-131 (one forward per window, concatenation)."""
+    n = wav.shape[-1]
+    duration = round(n / model.sample_rate, 2)
+    cs, ss = int((context_time + step_time) * model.sample_rate), int(step_time * model.sample_rate)
+    sf = int(step_time * model.frame_hz)
+    folds = wav.unfold(dimension=-1, size=cs, step=ss).permute(2, 0, 1, 3)
+    out = model.probs(folds[0])
+    keys = ["vad", "p_now", "p_future", "probs", "H"]
+    for w in folds[1:]:
+        o = model.probs(w)
+        for k in keys:
+            out[k] = torch.cat([out[k], o[k][:, -sf:]], dim=1)
+    if round(duration * model.frame_hz) != out["p_now"].shape[1]:
+        om = round(duration * model.frame_hz) - out["p_now"].shape[1]
+        o = model.probs(wav[..., -cs:])
+        for k in keys:
+            out[k] = torch.cat([out[k], o[k][:, -om:]], dim=1)
+    return out
+
+
+@pytest.mark.parametrize("B,seconds,max_batch", [(1, 45.0, 64), (2, 61.3, 3), (1, 25.0, 8), (3, 40.0, 4), (1, 172.7, 16)])
+def test_batched_session_stitching_equals_reference_loop(B, seconds, max_batch):
+    from voiceactivityprojection_b200.session import step_extraction
+
+    g = torch.Generator().manual_seed(int(seconds * 10) + B)
+    wav = torch.randn(B, 2, int(seconds * 16000), generator=g)
+    m = _FakeModel()
+    got = step_extraction(wav, m, device="cpu", max_batch=max_batch)
+    ref = _reference_loop(wav, m)
+    assert list(got.keys()) == list(ref.keys())
+    for k in ref:
+        assert got[k].shape == ref[k].shape, k
+        assert torch.equal(got[k], ref[k]), k
+
+
+def test_session_shorter_than_one_window_raises():
+    from voiceactivityprojection_b200.session import step_extraction
+
+    with pytest.raises(RuntimeError, match="maximum size for tensor"):
+        step_extraction(torch.zeros(1, 2, 16000 * 20), _FakeModel(), device="cpu")
+
+
+def test_load_waveform_int16_scaling_and_resample(tmp_path):
+    from scipy.io import wavfile
+    import torchaudio.functional as AF
+
+    from voiceactivityprojection_b200.audio import load_waveform
+
+    rng = np.random.default_rng(0)
+    pcm = (rng.standard_normal(24000) * 3000).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    wavfile.write(p, 24000, pcm)
+    x, sr = load_waveform(p)
+    assert sr == 24000 and x.shape == (1, 24000)
+    assert torch.equal(x[0], torch.from_numpy(pcm.astype(np.float32)) / 32768.0)
+    y, sr = load_waveform(p, sample_rate=16000)
+    assert sr == 16000 and y.shape == (1, 16000)
+    assert torch.equal(y, AF.resample(x, 24000, 16000))
+    st = np.stack([pcm, -pcm], axis=1)
+    wavfile.write(p, 16000, st)
+    z, _ = load_waveform(p, sample_rate=16000)
+    assert z.shape == (2, 24000) and torch.equal(z[0], -z[1])
+    zm, _ = load_waveform(p, mono=True)
+    assert zm.shape == (1, 24000) and zm.abs().max() == 0
+
+
+def test_config_argparse_mirror_and_cli_flags():
+    from voiceactivityprojection_b200 import VapConfig
+    from voiceactivityprojection_b200.run import get_args
+
+    args, conf = get_args(["-a", "x.wav", "-sd", "s.pt", "--vap_channel_layers", "2", "--chunk"])
+    assert conf == VapConfig(channel_layers=2) and args.chunk and args.filename is None
+    assert conf.bin_times == [0.2, 0.4, 0.6, 0.8] and conf.dim == 256 and conf.cross_layers == 3
+
+
+def test_json_contract(tmp_path):
+    from voiceactivityprojection_b200.utils import read_json, tensor_dict_to_json, write_json
+
+    out = {k: torch.arange(6, dtype=torch.float32).reshape(1, 3, 2) for k in ["probs", "vad", "p_now", "p_future"]}
+    out["H"] = torch.zeros(1, 3)
+    out["loss"] = torch.ones(1, 1)
+    p = str(tmp_path / "o.json")
+    write_json(tensor_dict_to_json(out), p)
+    d = read_json(p)
+    assert list(d.keys()) == ["probs", "vad", "p_now", "p_future", "H", "loss"]
+    assert d["p_now"] == [[[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]]]
+    assert json.load(open(p)) == d
+
+
+def test_vad_postprocessing_run_length_filters():
+    from voiceactivityprojection_b200.utils import vad_fill_silences, vad_omit_spikes
+
+    v = torch.tensor([[1, 0], [0, 0], [1, 1], [1, 0], [0, 0], [0, 1], [1, 0]], dtype=torch.float32)
+    f = vad_fill_silences(v.clone(), max_fill_time=0.02, frame_hz=50)  # 1-frame silences become active
+    assert f[:, 0].tolist() == [1, 1, 1, 1, 0, 0, 1]
+    o = vad_omit_spikes(v.clone(), max_omit_time=0.02, frame_hz=50)    # 1-frame activity removed
+    assert o[:, 1].tolist() == [0, 0, 0, 0, 0, 0, 0]
+    assert o[:, 0].tolist() == [0, 0, 1, 1, 0, 0, 0]
