@@ -72,6 +72,17 @@ int launch_conv0(cudaStream_t st, const float* wav, int batch, long long n_sampl
                  const float* b, void* out, int out_bf16, long long out_seq_stride /*elements*/,
                  int out_pad_rows);
 
+// conv0 for the tensor path (k_conv0_v2.cu): closed-form ChannelNorm statistics, packed fp32 FMAs, bf16 out.
+struct Conv0Stats {
+  float G[10][10];  // sum_c (w_c - wbar)(w_c - wbar)'
+  float h2[10];     // 2 sum_c (b_c - bbar)(w_c - wbar)
+  float s;          // sum_c (b_c - bbar)^2
+};
+void conv0_v2_fold(const float* w, const float* bias, const float* g, float* u, float* d, Conv0Stats* cs);
+int launch_conv0_v2(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq,
+                    long long L0, const float* u, const float* d, const float* beta, const Conv0Stats& cs,
+                    __nv_bfloat16* out, long long out_seq_stride, int out_pad_rows);
+
 int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
 
 int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);  // -1 on error

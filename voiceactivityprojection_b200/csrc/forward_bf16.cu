@@ -33,6 +33,8 @@ struct State16 {
   const bf16* ds_w;
   LayerW16 chan[kMaxLayers], cross[kMaxLayers];
   const bf16 *comb_a, *comb_b, *head_w;
+  const float *c0_u, *c0_d;  // folded conv0 + ChannelNorm parameters (k_conv0_v2.cu)
+  Conv0Stats c0_stats;
 };
 
 struct Plan16 {
@@ -174,6 +176,13 @@ int bf16_prepare(Model& m) {
   put(&s->comb_a, T("ar.combinator.h0_a.weight").data);
   put(&s->comb_b, T("ar.combinator.h0_b.weight").data);
   put(&s->head_w, T("vap_head.weight").data);
+  {
+    std::vector<float> u(10 * kDim), d(kDim);
+    conv0_v2_fold(T(GE + "conv0.weight").data.data(), T(GE + "conv0.bias").data.data(),
+                  T(GE + "batchNorm0.weight").data.data(), u.data(), d.data(), &s->c0_stats);
+    put_f32(&s->c0_u, u);
+    put_f32(&s->c0_d, d);
+  }
   if (cudaMalloc(&s->arena, host.size()) != cudaSuccess ||
       cudaMemcpy(s->arena, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     m.err = "bf16 weight arena: CUDA allocation/copy failed";
@@ -224,8 +233,8 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     const int n = (nseq - s0 < p.mb) ? nseq - s0 : p.mb;
     {
       ProfScope ps(m, st, CAT_CONV0);
-      m.launches += launch_conv0(st, wav, g.batch, g.S, s0, n, g.L[0], w.c0_w, w.c0_b, w.c0_g, w.c0_be,
-                                 H(p.act[0]), 1, p.lpad[0] * kDim, (int)p.lo[0]);
+      m.launches += launch_conv0_v2(st, wav, g.batch, g.S, s0, n, g.L[0], s.c0_u, s.c0_d, w.c0_be, s.c0_stats,
+                                    H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0]);
     }
     for (int i = 1; i <= 4; ++i) {
       const Conv& c = kConv[i];
