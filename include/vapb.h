@@ -148,6 +148,16 @@ int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_
                        float* out1_f32, void* out1_bf16, int norm2, const float* g2, const float* b2,
                        void* out2_bf16, char* err, int err_len);
 
+/* Unit-test hook for the linear-layer GEMM (csrc/k_gemm_lin.cu): same operands as
+ * vapb_debug_gemm_tc; outputs are dense (nseq*rows_per_seq, N). f32_mode 1: out1_f32
+ * and resid_blocked use the row-blocked fp32 layout [row/128][col/4][row%128][4]
+ * (buffers padded to a multiple of 128 rows); f32_mode 2: out1_f32 is row-major. */
+int vapb_debug_gemm_lin(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W,
+                        int nseq, int rows_per_seq, int N, int K, const float* bias, int norm1, const float* g1,
+                        const float* b1, int act, const float* resid_blocked, int accumulate, float* out1_f32,
+                        int f32_mode, void* out1_bf16, int norm2, const float* g2, const float* b2, void* out2_bf16,
+                        char* err, int err_len);
+
 /* Unit-test hooks for the tensor-core gAR recurrence (csrc/k_rnn_tc.cu).
  * vapb_debug_rnn_pack (host only): nn.LSTM / nn.GRU parameters of one layer
  * (weight_ih (G*256,256), weight_hh, bias_ih, bias_hh; kind 0 = LSTM, 1 = GRU) ->

@@ -186,3 +186,125 @@ def test_attention_tc_matches_torch(nseq, T, cross, packed, scale):
     # P and the output are rounded to bf16 (2^-9 relative); V is O(scale)
     assert d.max().item() <= 2e-2 * scale, d.max().item()
     assert d.mean().item() <= 2e-3 * scale
+
+
+def _to_blocked(x):
+    """(M, 256) fp32 -> row-blocked [ceil(M/128)][64][128][4] flat buffer (k_gemm_lin.cu layout)."""
+    M = x.shape[0]
+    Mp = (M + 127) // 128 * 128
+    xp = torch.zeros((Mp, 256), device=x.device, dtype=torch.float32)
+    xp[:M] = x
+    return xp.view(Mp // 128, 128, 64, 4).permute(0, 2, 1, 3).contiguous()
+
+
+def _from_blocked(b, M):
+    return b.permute(0, 2, 1, 3).reshape(-1, 256)[:M]
+
+
+def _gemm_lin(A, W, M, N, K, bias=None, norm1=0, g1=None, b1=None, act=0, resid=None, accumulate=False, out1_init=None,
+              f32_mode=1, want_f32=True, want_bf16=False, norm2=0, g2=None, b2=None, nseq=1, a_seq_stride=0,
+              a_row_stride=None):
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    dev = A.device
+    rps = M // nseq
+    out1 = None
+    if want_f32:
+        if f32_mode == 1:
+            out1 = _to_blocked(out1_init if out1_init is not None else torch.full((M, N), float("nan"), device=dev))
+        else:
+            out1 = torch.full((M, N), float("nan"), device=dev)
+    out1b = torch.zeros((M, N), device=dev, dtype=torch.bfloat16) if want_bf16 else None
+    out2 = torch.zeros((M, N), device=dev, dtype=torch.bfloat16) if norm2 else None
+    rb = _to_blocked(resid) if resid is not None else None
+    err = C.create_string_buffer(512)
+    p = lambda t: None if t is None else t.data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_gemm_lin(st, A.data_ptr(), a_seq_stride, a_row_stride or K, W.data_ptr(), nseq, rps, N, K, p(bias),
+                                 norm1, p(g1), p(b1), act, p(rb), int(accumulate), p(out1), f32_mode, p(out1b), norm2,
+                                 p(g2), p(b2), p(out2), err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    if want_f32 and f32_mode == 1:
+        out1 = _from_blocked(out1, M)
+    return out1, out1b, out2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 256), (4096 + 77, 512, 256), (300, 256, 768)])
+def test_gemm_lin_plain_bf16_out(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    _, outb, _ = _gemm_lin(A, W, M, N, K, want_f32=False, want_bf16=True)
+    ref = A.float() @ W.float().T
+    assert (outb.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_lin_rowmajor_f32_with_bias():
+    M, N, K = 1000 + 37, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out, _, _ = _gemm_lin(A, W, M, N, K, bias=bias, f32_mode=2)
+    ref = A.float() @ W.float().T + bias
+    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_lin_residual_layernorm2_blocked():
+    M, K = 2000 + 5, 768
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((256, K), device="cuda", generator=g) * 0.05).bfloat16()
+    resid = torch.randn((M, 256), device="cuda", generator=g)
+    g2 = torch.randn(256, device="cuda", generator=g)
+    b2 = torch.randn(256, device="cuda", generator=g)
+    out1, out1b, out2 = _gemm_lin(A, W, M, 256, K, resid=resid, want_bf16=True, norm2=2, g2=g2, b2=b2)
+    v = A.float() @ W.float().T + resid
+    assert (out1 - v).abs().max().item() <= 2e-3 * v.abs().max().item()
+    assert (out1b.float() - v).abs().max().item() <= 1e-2 * v.abs().max().item()
+    assert (out2.float() - _norm(v, 2, g2, b2)).abs().max().item() <= 5e-2
+
+
+def test_gemm_lin_norm1_gelu_accumulate():
+    """Combinator branch: GELU(LN(x W^T)) accumulated onto the first branch (vap/modules.py:446-449)."""
+    M, K = 900, 256
+    g = torch.Generator(device="cuda").manual_seed(13)
+    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
+    W = (torch.randn((256, K), device="cuda", generator=g) * 0.08).bfloat16()
+    g1 = torch.randn(256, device="cuda", generator=g)
+    b1 = torch.randn(256, device="cuda", generator=g)
+    prev = torch.randn((M, 256), device="cuda", generator=g)
+    out1, out1b, _ = _gemm_lin(A, W, M, 256, K, norm1=2, g1=g1, b1=b1, act=2, accumulate=True, out1_init=prev,
+                               want_bf16=True)
+    v = F.gelu(_norm(A.float() @ W.float().T, 2, g1, b1)) + prev
+    assert (out1 - v).abs().max().item() <= 3e-3   # tanh-form GELU on tanh.approx: <= ~1e-3 abs
+    assert (out1b.float() - v).abs().max().item() <= 3e-2
+
+
+def test_gemm_lin_implicit_conv_multi_seq():
+    """Downsample conv: k=5, s=2 over left-padded sequences, LayerNorm + GELU, blocked fp32 + bf16 + LN2 outputs."""
+    g = torch.Generator(device="cuda").manual_seed(14)
+    nseq, L, k, s = 3, 233, 5, 2
+    T = (L - 1) // 2 + 1
+    Lpad = 4 + L + (L & 1)
+    x = torch.randn((nseq, L, 256), device="cuda", generator=g).bfloat16()
+    buf = torch.zeros((nseq, Lpad, 256), device="cuda", dtype=torch.bfloat16)
+    buf[:, 4:4 + L] = x
+    w = torch.randn((256, 256, k), device="cuda", generator=g) * 0.03
+    Wp = w.permute(0, 2, 1).reshape(256, k * 256).contiguous().bfloat16()
+    bias = torch.randn(256, device="cuda", generator=g)
+    g1 = torch.randn(256, device="cuda", generator=g)
+    b1 = torch.randn(256, device="cuda", generator=g)
+    g2 = torch.randn(256, device="cuda", generator=g)
+    b2 = torch.randn(256, device="cuda", generator=g)
+    out1, out1b, out2 = _gemm_lin(buf, Wp, nseq * T, 256, k * 256, bias=bias, norm1=2, g1=g1, b1=b1, act=2,
+                                  want_bf16=True, norm2=2, g2=g2, b2=b2, nseq=nseq, a_seq_stride=Lpad * 256,
+                                  a_row_stride=s * 256)
+    wr = Wp.float().reshape(256, k, 256).permute(0, 2, 1)
+    y = F.conv1d(F.pad(x.float().transpose(1, 2), (4, 0)), wr, bias, stride=s).transpose(1, 2).reshape(nseq * T, 256)
+    v = F.gelu(_norm(y, 2, g1, b1))
+    assert (out1 - v).abs().max().item() <= 2e-2
+    assert (out1b.float() - v).abs().max().item() <= 4e-2
+    assert (out2.float() - _norm(v, 2, g2, b2)).abs().max().item() <= 8e-2

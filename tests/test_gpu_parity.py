@@ -144,3 +144,71 @@ def test_get_probs_from_logits_matches_oracle():
     assert _maxerr(got["p_now"], O.probs_next_speaker_aggregate(p, 0, 1)) <= 1e-6
     assert _maxerr(got["p_future"], O.probs_next_speaker_aggregate(p, 2, 3)) <= 1e-6
     assert _maxerr(got["p_tot"], O.probs_next_speaker_aggregate(p, 0, 3)) <= 1e-6
+
+
+def test_session_stitching_matches_reference_golden():
+    """run.py:23-131 semantics with batched windows vs the reference's own step_extraction output."""
+    from oracle import synth
+    from voiceactivityprojection_b200.session import step_extraction
+
+    recipe, g = load_golden("session_45s")
+    sd = synth.make_state_dict(recipe["seed"], recipe["ar_mode"], recipe["ar_layers"], recipe["gain"])
+    m = _model(sd)
+    for tag in ("a", "b"):
+        n = int(g[f"{tag}_n_samples"])
+        wav = synth.make_waveform(1, n, recipe["wav_seed"], recipe["kind"])
+        out = step_extraction(wav, m, "cuda", max_batch=3)
+        assert list(out.keys()) == ["probs", "vad", "p_now", "p_future", "H", "loss"]
+        for k in ["vad", "p_now", "p_future"]:
+            assert out[k].shape == g[f"{tag}_{k}"].shape
+            assert _maxerr(out[k], g[f"{tag}_{k}"]) <= 1e-5, (tag, k)
+        assert _maxerr(out["H"], g[f"{tag}_H"]) <= 1e-4
+        assert torch.equal(out["probs"].argmax(-1).to(torch.uint8), g[f"{tag}_probs_argmax"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bulk_runner_equals_direct_calls(precision):
+    """Pipelined H2D / forward / D2H over pinned host batches returns exactly what direct probs() calls return."""
+    from oracle import synth
+    from voiceactivityprojection_b200.bulk import ALL_KEYS, BulkRunner
+
+    sd = synth.make_state_dict(3, "LSTM", 1, 2.0)
+    m = _model(sd, precision)
+    n = 40000
+    sizes = [4, 4, 4, 2]  # ragged last batch
+    host = [synth.make_waveform(b, n, 20 + i, "turns").pin_memory() for i, b in enumerate(sizes)]
+    direct = [{k: v.cpu().clone() for k, v in m.probs(h.cuda()).items()} for h in host]
+    got = []
+    runner = BulkRunner(m, 4, n, keys=ALL_KEYS + ("argmax",))
+    stats = runner.run(host, sink=lambda i, b, o: got.append((i, b, {k: v.clone() for k, v in o.items()})))
+    assert [g_[0] for g_ in got] == [0, 1, 2, 3] and [g_[1] for g_ in got] == sizes
+    hist = torch.zeros(256, dtype=torch.int64)
+    for (i, b, o), d in zip(got, direct):
+        for k in ALL_KEYS:
+            assert torch.equal(o[k], d[k]), (i, k)
+        assert torch.equal(o["argmax"].long(), d["probs"].argmax(-1))
+        hist += torch.bincount(o["argmax"].reshape(-1).long(), minlength=256)
+    assert stats.chunks == sum(sizes) and stats.frames == sum(sizes) * 125
+    assert torch.equal(stats.class_hist, hist)
+    assert stats.vad_active.tolist() == sum((d["vad"] >= 0.5).sum(dim=(0, 1)) for d in direct).tolist()
+    assert runner.h2d_bytes == sum(sizes) * 2 * n * 4
+
+
+BF16_TOL = dict(probs=5e-3, vad=2e-2, p_now=2e-3, p_future=2e-3, logits=0.1)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_bf16_within_stated_tolerance_of_reference_golden(name):
+    """bf16 tensor-core mode vs the reference's fp32 outputs."""
+    recipe, g = load_golden(name)
+    sd, wav = golden_inputs(recipe, g)
+    m = _model(sd, "bf16")
+    x = wav.cuda()
+    fwd = m(x)
+    out = m.probs(x)
+    assert _maxerr(fwd["logits"], g["logits"]) <= BF16_TOL["logits"]
+    for k in ["probs", "vad", "p_now", "p_future"]:
+        if k in g:
+            assert _maxerr(out[k], g[k]) <= BF16_TOL[k], k
+    agree = (fwd["logits"].argmax(-1).cpu() == g["logits"].argmax(-1)).float().mean().item()
+    assert agree >= 0.95, agree

@@ -87,6 +87,10 @@ int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
 
 int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);  // -1 on error
 
+// Linear-layer GEMM with staged / blocked epilogue I/O (k_gemm_lin.cu). f32_mode: 1 = out1_f32, resid and
+// accumulate use the row-blocked fp32 layout [row/128][col/4][row%128][4]; 2 = out1_f32 row-major via TMA.
+int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm, std::string* err);
+
 int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
                      long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence
 
@@ -128,7 +132,10 @@ int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, cons
                 int T, float* loss);
 
 int launch_to_f32(cudaStream_t st, const void* src, int src_bf16, RowMap src_map, int nseq,
-                  int rows_per_seq, float* dst);
+                  int rows_per_seq, float* dst, int src_blocked = 0);
+// vad head on the row-blocked fp32 residual stream (k_heads.cu)
+int launch_vad_head_blocked(cudaStream_t st, const float* x, const float* w, const float* b, int batch, int T,
+                            float* vad_logits, float* vad_sig);
 
 // ---- small device helpers ----------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -69,18 +69,19 @@ Plan16 make_plan(const Model& m, const Geometry& g) {
     if (i == 0 || m.ar_layers > 1) off = align_up(off + (size_t)g.nseq * p.rnn_lpad * kDim * 2);
   }
   const size_t rows = (size_t)g.nseq * g.T;
+  const size_t rows_blk = (rows + 127) / 128 * 128;  // fp32 residual-stream buffers use the row-blocked layout
   const int n_stage = 1 + m.channel_layers + m.cross_layers;
-  for (int i = 0; i < n_stage; ++i) { p.stage[i] = off; off = align_up(off + rows * kDim * 4); }
+  for (int i = 0; i < n_stage; ++i) { p.stage[i] = off; off = align_up(off + rows_blk * kDim * 4); }
   p.xs = off;  off = align_up(off + rows * kDim * 2);   // bf16 shadow of the current layer input
-  p.xa = off;  off = align_up(off + rows * kDim * 4);
-  p.xb = off;  off = align_up(off + rows * kDim * 4);
+  p.xa = off;  off = align_up(off + rows_blk * kDim * 4);
+  p.xb = off;  off = align_up(off + rows_blk * kDim * 4);
   p.z = off;   off = align_up(off + rows * kDim * 2);
   p.qkv = off; off = align_up(off + rows * 3 * kDim * 2);
   p.kvc = off; off = align_up(off + rows * 2 * kDim * 2);
   p.qc = off;  off = align_up(off + rows * kDim * 2);
   p.y = off;   off = align_up(off + rows * kDim * 2);
   p.h = off;   off = align_up(off + rows * kFfn * 2);
-  p.comb = off;  off = align_up(off + rows / 2 * kDim * 4);
+  p.comb = off;  off = align_up(off + (rows / 2 + 127) / 128 * 128 * kDim * 4);
   p.combb = off; off = align_up(off + rows / 2 * kDim * 2);
   p.bytes = off;
   return p;
@@ -104,6 +105,21 @@ struct Ctx {
     ProfScope ps(m, st, cat);
     std::string err;
     const int n = launch_gemm_tc(st, a, m.n_sm, &err);
+    if (n < 0) { m.err = err; rc = -3; return; }
+    m.launches += n;
+  }
+  // row-local layers: staged / blocked epilogue I/O (k_gemm_lin.cu); fp32 rows are blocked unless f32_mode == 2
+  void lin(const bf16* A, RowMap amap, const bf16* W, int nseq, int rps, int N, int K, const Epilogue& e,
+           float* out_f32, bf16* out_bf16, int f32_mode = 1, int cat = CAT_LINEAR_GEMM) {
+    if (rc) return;
+    TcGemmArgs a{};
+    a.A = A; a.a_map = amap; a.W = W;
+    a.nseq = nseq; a.rows_per_seq = rps; a.N = N; a.K = K;
+    a.e = e;
+    a.out1_f32 = out_f32; a.out1_bf16 = out_bf16;
+    ProfScope ps(m, st, cat);
+    std::string err;
+    const int n = launch_gemm_lin(st, a, f32_mode, m.n_sm, &err);
     if (n < 0) { m.err = err; rc = -3; return; }
     m.launches += n;
   }
@@ -293,8 +309,8 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     e.out1_map = dense(T, kDim);
     first_ln(0, &e.g2, &e.b2);
     if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = H(p.z); e.out2_map = dense(T, kDim); }
-    cx.gemm(H(p.rnn[(m.ar_layers - 1) & 1]), RowMap{p.rnn_lpad * kDim, 2 * kDim}, s.ds_w, nseq, (int)T, kDim,
-            5 * kDim, e, F(p.stage[0]), H(p.xs), CAT_CONV_GEMM);
+    cx.lin(H(p.rnn[(m.ar_layers - 1) & 1]), RowMap{p.rnn_lpad * kDim, 2 * kDim}, s.ds_w, nseq, (int)T, kDim,
+            5 * kDim, e, F(p.stage[0]), H(p.xs), 1, CAT_CONV_GEMM);
   }
 
   // ---- transformer layers (rows are dense (nseq*T, .) from here on)
@@ -307,12 +323,12 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     {
       Epilogue e{};
       e.out1_map = dense(MT, 3 * kDim);
-      cx.gemm(H(p.z), d256, lh.wqkv, 1, MT, 3 * kDim, kDim, e, nullptr, H(p.qkv));
+      cx.lin(H(p.z), d256, lh.wqkv, 1, MT, 3 * kDim, kDim, e, nullptr, H(p.qkv));
     }
     if (cross) {
       Epilogue e{};
       e.out1_map = dense(MT, 2 * kDim);
-      cx.gemm(H(p.xs), d256, lh.wkv_c, 1, MT, 2 * kDim, kDim, e, nullptr, H(p.kvc));
+      cx.lin(H(p.xs), d256, lh.wkv_c, 1, MT, 2 * kDim, kDim, e, nullptr, H(p.kvc));
     }
     if (cx.rc) return cx.rc;
     {
@@ -334,13 +350,13 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       e.b2 = cross ? lw.ln_src_b : lw.ln_ffn_b;
       e.out2 = H(p.z);
       e.out2_map = d256;
-      cx.gemm(H(p.y), d256, lh.wproj, 1, MT, kDim, kDim, e, x_mid, nullptr);
+      cx.lin(H(p.y), d256, lh.wproj, 1, MT, kDim, kDim, e, x_mid, nullptr);
     }
     if (cross) {
       {
         Epilogue e{};
         e.out1_map = d256;
-        cx.gemm(H(p.z), d256, lh.wq_c, 1, MT, kDim, kDim, e, nullptr, H(p.qc));
+        cx.lin(H(p.z), d256, lh.wq_c, 1, MT, kDim, kDim, e, nullptr, H(p.qc));
       }
       if (cx.rc) return cx.rc;
       {
@@ -360,13 +376,13 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       e.b2 = lw.ln_ffn_b;
       e.out2 = H(p.z);
       e.out2_map = d256;
-      cx.gemm(H(p.y), d256, lh.wproj_c, 1, MT, kDim, kDim, e, F(p.xb), nullptr);
+      cx.lin(H(p.y), d256, lh.wproj_c, 1, MT, kDim, kDim, e, F(p.xb), nullptr);
     }
     {
       Epilogue e{};
       e.act = ACT_GELU;
       e.out1_map = dense(MT, kFfn);
-      cx.gemm(H(p.z), d256, lh.w1, 1, MT, kFfn, kDim, e, nullptr, H(p.h));
+      cx.lin(H(p.z), d256, lh.w1, 1, MT, kFfn, kDim, e, nullptr, H(p.h));
     }
     {
       Epilogue e{};
@@ -376,7 +392,7 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       first_ln(li + 1, &e.g2, &e.b2);
       if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = H(p.z); e.out2_map = d256; }
       // bf16 shadow of the new residual stream: next cross layer's K/V source, or the combinator input
-      cx.gemm(H(p.h), dense(MT, kFfn), lh.w2, 1, MT, kDim, kFfn, e, F(p.stage[li + 1]), H(p.xs));
+      cx.lin(H(p.h), dense(MT, kFfn), lh.w2, 1, MT, kDim, kFfn, e, F(p.stage[li + 1]), H(p.xs));
     }
   }
 
@@ -391,18 +407,18 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     e.act = ACT_GELU;
     e.accumulate = c;
     e.out1_map = dense(MB, kDim);
-    cx.gemm(H(p.xs) + (long long)c * MB * kDim, dense(MB, kDim), c == 0 ? s.comb_a : s.comb_b, 1, MB, kDim, kDim, e,
+    cx.lin(H(p.xs) + (long long)c * MB * kDim, dense(MB, kDim), c == 0 ? s.comb_a : s.comb_b, 1, MB, kDim, kDim, e,
             F(p.comb), c == 1 ? H(p.combb) : nullptr);
   }
   if (vad_logits || vad_sig) {
     ProfScope ps(m, st, CAT_HEADS);
-    m.launches += launch_vad_head(st, x_last, w.va_w, w.va_b, g.batch, (int)T, vad_logits, vad_sig);
+    m.launches += launch_vad_head_blocked(st, x_last, w.va_w, w.va_b, g.batch, (int)T, vad_logits, vad_sig);
   }
   {
     Epilogue e{};
     e.bias = w.head_b;
     e.out1_map = dense(MB, kClasses);
-    cx.gemm(H(p.combb), dense(MB, kDim), s.head_w, 1, MB, kClasses, kDim, e, logits, nullptr);
+    cx.lin(H(p.combb), dense(MB, kDim), s.head_w, 1, MB, kClasses, kDim, e, logits, nullptr, 2);
   }
   return cx.rc;
 }
@@ -425,15 +441,19 @@ int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& n
     ref->map = RowMap{p.rnn_lpad * kDim, kDim};
   } else if (name == "enc") {
     ref->ptr = ws + p.stage[0];
+    ref->blocked = 1;
   } else if (name == "ch") {
     ref->ptr = ws + p.stage[m.channel_layers];
+    ref->blocked = 1;
   } else if (name.size() >= 3 && name.compare(0, 2, "ar") == 0) {
     const int l = atoi(name.c_str() + 2);
     if (l < 0 || l >= m.cross_layers) return -1;
     ref->ptr = ws + p.stage[m.channel_layers + l + 1];
+    ref->blocked = 1;
   } else if (name == "comb") {
     ref->ptr = ws + p.comb;
     ref->nseq = g.batch;
+    ref->blocked = 1;
   } else {
     return -1;
   }

@@ -127,11 +127,12 @@ int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long 
 // Stage export for diagnostics: any activation -> dense fp32 (nseq, rows, 256).
 template <bool SRC_BF16>
 __global__ void to_f32_kernel(const void* __restrict__ src, RowMap map, int rows_per_seq, float* __restrict__ dst,
-                              long long total_rows) {
+                              long long total_rows, int blocked) {
   const long long r = (long long)blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
   if (r >= total_rows) return;
   const int c4 = (threadIdx.x & 63) * 4;
-  const long long off = (r / rows_per_seq) * map.seq_stride + (r % rows_per_seq) * map.row_stride + c4;
+  const long long off = blocked ? (((r >> 7) * 64 + (c4 >> 2)) * 128 + (r & 127)) * 4
+                                : (r / rows_per_seq) * map.seq_stride + (r % rows_per_seq) * map.row_stride + c4;
   float4 v;
   if (SRC_BF16) {
     const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src) + off;
@@ -143,13 +144,13 @@ __global__ void to_f32_kernel(const void* __restrict__ src, RowMap map, int rows
 }
 
 int launch_to_f32(cudaStream_t st, const void* src, int src_bf16, RowMap src_map, int nseq, int rows_per_seq,
-                  float* dst) {
+                  float* dst, int src_blocked) {
   const long long total = (long long)nseq * rows_per_seq;
   const unsigned grid = (unsigned)((total + 3) / 4);
   if (src_bf16)
-    to_f32_kernel<true><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total);
+    to_f32_kernel<true><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, 0);
   else
-    to_f32_kernel<false><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total);
+    to_f32_kernel<false><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, src_blocked);
   return 1;
 }
 

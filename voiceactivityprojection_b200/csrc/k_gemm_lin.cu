@@ -1,0 +1,448 @@
+// BF16 tcgen05 GEMM for the row-local layers of the transformer (q/k/v/proj, FFN,
+// combinator, vap_head; vap/modules.py:9-21,93-95,109,246-275,434-449,
+// vap/model.py:261) and the downsample conv (vap/encoder.py:24-30).
+//
+// Same mainloop as k_gemm_tc.cu (TMA -> smem ring -> tcgen05.mma M128 N256 K16, two
+// TMEM accumulators) but these GEMMs have K = 256..1280, so a 128 x 256 tile spends
+// ~1 us on the tensor pipe and the kernel lives or dies by its epilogue and its HBM
+// traffic. The epilogue therefore moves data only in full lines:
+//   * bf16 outputs (the next GEMM's / attention's TMA-loaded operands) are packed into
+//     a 128-byte-swizzled staging tile in shared memory (conflict-free: lane r writes
+//     16-byte chunk j at r*128 + ((j ^ (r&7)) << 4)) and leave with ONE TMA store per
+//     128 x 64 tile; rows beyond the sequence are clipped by the tensor map;
+//   * the fp32 residual stream is private to the library, so it is kept in a
+//     row-blocked layout [row/128][col/4][row%128][4]: the thread that owns
+//     accumulator row r reads/writes float4s that are contiguous across the warp;
+//   * fp32 row-major outputs (logits) go through the same staging tiles (128 x 32).
+// TMEM loads are double-buffered against the math; GELU uses the tanh form on
+// tanh.approx (3e-4 abs, below the bf16 rounding of its output).
+#include <string>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace vapb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int LBM = 128, LBN = 256, LBK = 64, LSTAGES = 3;
+constexpr int LA_BYTES = LBM * LBK * 2, LB_BYTES = LBN * LBK * 2;
+constexpr int LSTAGE_BYTES = LA_BYTES + LB_BYTES;   // 48 KB
+constexpr int LSTG_TILE = 128 * 128;                // staging tile: 128 rows x 128 B
+constexpr int L_OFF_STG = LSTAGES * LSTAGE_BYTES;   // [half][2] staging tiles
+constexpr int L_OFF_BAR = L_OFF_STG + 4 * LSTG_TILE;
+constexpr int L_OFF_VEC = L_OFF_BAR + 256;
+constexpr int L_THREADS = 384, L_EPI_THREADS = 256;
+
+struct LinVecs {
+  float bias[256], g1[256], b1[256], g2[256], b2[256];
+  float part[2][128][2];
+};
+constexpr int L_SMEM = L_OFF_VEC + (int)sizeof(LinVecs) + 1024 /*alignment slack*/;
+
+struct alignas(64) LinParams {
+  CUtensorMap tma_a, tma_b;
+  CUtensorMap tma_o1;   // out1 bf16  (N, rows, nseq) box (64,128,1) SW128
+  CUtensorMap tma_o2;   // out2 bf16
+  CUtensorMap tma_of;   // out1 fp32 row-major (N, rows, nseq) box (32,128,1) SW128
+  int nseq, rows_per_seq, tiles_per_seq, n_tiles_n, num_k_blocks, N;
+  const float* bias;
+  int norm1;
+  const float *g1, *b1;
+  int act;
+  const float* resid;     // fp32, blocked layout
+  int accumulate;         // v += previous out1_f32 (blocked)
+  float* out1_f32;        // blocked layout (f32_mode 1) or row-major through tma_of (f32_mode 2)
+  int f32_mode;
+  int has_o1_bf16;
+  int norm2;
+  const float *g2, *b2;
+};
+
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);  // sqrt(2/pi) (x + 0.044715 x^3)
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_fast(u), h);
+}
+__device__ __forceinline__ float act_fast(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_GELU) return gelu_tanh_fast(v);
+  return v;
+}
+
+// offset (floats) of (row m, column c) in the blocked fp32 layout; c % 4 == 0 for float4 access
+__device__ __forceinline__ long long blocked_off(long long m, int c) {
+  return (((m >> 7) * 64 + (c >> 2)) * 128 + (m & 127)) * 4 + (c & 3);
+}
+
+__device__ __forceinline__ void bar_half(int half) {
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+}
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_constant__ LinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L_OFF_BAR;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (8 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (10 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 12;
+  LinVecs& ev = *reinterpret_cast<LinVecs*>(smem_gen + L_OFF_VEC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma_a);
+    prefetch_tmap(&p.tma_b);
+    for (int s = 0; s < LSTAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), L_EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp >= 4) {
+    const int e = threadIdx.x - 128;
+    ev.bias[e] = p.bias ? p.bias[e] : 0.f;
+    ev.g1[e] = p.norm1 != NORM_NONE ? p.g1[e] : 1.f;
+    ev.b1[e] = p.norm1 != NORM_NONE ? p.b1[e] : 0.f;
+    ev.g2[e] = p.norm2 != NORM_NONE ? p.g2[e] : 1.f;
+    ev.b2[e] = p.norm2 != NORM_NONE ? p.b2[e] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_tiles = p.nseq * p.tiles_per_seq * p.n_tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+        const int seq = mt / p.tiles_per_seq, t0 = (mt % p.tiles_per_seq) * LBM;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), LSTAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * LSTAGE_BYTES;
+          tma_load_3d(a_dst, &p.tma_a, full_bar(stage), kb * LBK, t0, seq);
+          tma_load_2d(a_dst + LA_BYTES, &p.tma_b, full_bar(stage), kb * LBK, nt * LBN);
+          if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(LBM, LBN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * LBN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * LSTAGE_BYTES;
+          const uint32_t b_addr = a_addr + LA_BYTES;
+#pragma unroll
+          for (int k = 0; k < LBK / 16; ++k)
+            umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
+                      idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // thread = (column half, TMEM lane quadrant, lane): accumulator row quad*32+lane, columns [128*half, +128)
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    const bool leader = (threadIdx.x - 128 - half * 128) == 0;  // issues this half's TMA stores
+    const int cbase = half * 128;
+    const uint32_t stg_addr = smem_base + L_OFF_STG + half * 2 * LSTG_TILE;
+    uint8_t* stg_gen = smem_gen + L_OFF_STG + half * 2 * LSTG_TILE;
+    const uint32_t sw = (uint32_t)(row_in_tile & 7);
+    const uint32_t stg_row = (uint32_t)row_in_tile * 128u;
+    uint32_t stg_cnt = 0;
+    // staging-tile protocol: acquire (previous TMA store that read this buffer has drained) -> all 128 threads
+    // write their row -> publish (fence to the async proxy, barrier, leader issues the store)
+    auto stg_acquire = [&]() -> uint8_t* {
+      if (leader) bulk_wait_read<1>();
+      bar_half(half);
+      return stg_gen + (stg_cnt & 1u) * LSTG_TILE + stg_row;
+    };
+    auto stg_publish = [&](const CUtensorMap* map, int c0, int c1, int c2) {
+      fence_proxy_async();
+      bar_half(half);
+      if (leader) {
+        tma_store_3d(map, stg_addr + (stg_cnt & 1u) * LSTG_TILE, c0, c1, c2);
+        bulk_commit();
+      }
+      ++stg_cnt;
+    };
+    // 32 fp32 -> 32 bf16 = 4 x 16 B chunks at chunk index j0..j0+3 of this thread's staging row
+    auto stg_put_bf16 = [&](uint8_t* rowp, int j0, const float (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(j0 + j)) ^ sw) << 4)) = u;
+      }
+    };
+    auto stg_put_f32 = [&](uint8_t* rowp, const float (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ sw) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    };
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+      const int seq = mt / p.tiles_per_seq, t0 = (mt % p.tiles_per_seq) * LBM;
+      const int t = t0 + row_in_tile;
+      const bool valid = t < p.rows_per_seq;
+      const long long m = (long long)seq * p.rows_per_seq + t;  // dense row (blocked fp32 buffers)
+      const int n0 = nt * LBN + cbase;                            // first global column of this thread
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * LBN + cbase;
+
+      float mean1 = 0.f, rstd1 = 1.f;
+      if (p.norm1 != NORM_NONE) {
+        float s = 0.f, ss = 0.f;
+        uint32_t r[2][32];
+        tmem_ld32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(r[c & 1][i]) + ev.bias[cbase + c * 32 + i];
+            s += v;
+            ss = fmaf(v, v, ss);
+          }
+        }
+        ev.part[half][row_in_tile][0] = s;
+        ev.part[half][row_in_tile][1] = ss;
+        bar_epi();
+        s += ev.part[half ^ 1][row_in_tile][0];
+        ss += ev.part[half ^ 1][row_in_tile][1];
+        mean1 = s * (1.0f / kDim);
+        const float var = fmaxf(ss - s * mean1, 0.f) * (p.norm1 == NORM_CHANNEL ? 1.0f / (kDim - 1) : 1.0f / kDim);
+        rstd1 = rsqrtf(var + kEps);
+        bar_epi();
+      }
+
+      float s2 = 0.f, ss2 = 0.f;
+      {
+        uint32_t r[2][32];
+        uint8_t* rowp = nullptr;
+        tmem_ld32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+          float v[32];
+          if (p.bias || p.norm1 != NORM_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bi = *reinterpret_cast<const float4*>(&ev.bias[cbase + c * 32 + i]);
+              const float4 g = *reinterpret_cast<const float4*>(&ev.g1[cbase + c * 32 + i]);
+              const float4 b = *reinterpret_cast<const float4*>(&ev.b1[cbase + c * 32 + i]);
+              const float bb[4] = {bi.x, bi.y, bi.z, bi.w}, gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x = __uint_as_float(r[c & 1][i + j]) + bb[j];
+                if (p.norm1 != NORM_NONE) x = fmaf((x - mean1) * rstd1, gg[j], be[j]);
+                v[i + j] = act_fast(x, p.act);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = act_fast(__uint_as_float(r[c & 1][i]), p.act);
+          }
+          if (p.resid && valid) {
+            const float* rp = p.resid + blocked_off(m, n0 + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = *reinterpret_cast<const float4*>(rp + i * 512);
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+          }
+          if (p.accumulate && valid) {
+            const float* ap = p.out1_f32 + blocked_off(m, n0 + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = *reinterpret_cast<const float4*>(ap + i * 512);
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+          }
+          if (p.f32_mode == 1) {
+            if (valid) {
+              float* op = p.out1_f32 + blocked_off(m, n0 + c * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(op + i * 512) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          } else if (p.f32_mode == 2) {
+            uint8_t* rp2 = stg_acquire();
+            stg_put_f32(rp2, v);
+            stg_publish(&p.tma_of, n0 + c * 32, t0, seq);
+          }
+          if (p.has_o1_bf16) {
+            if ((c & 1) == 0) rowp = stg_acquire();
+            stg_put_bf16(rowp, (c & 1) * 4, v);
+            if (c & 1) stg_publish(&p.tma_o1, n0 + (c - 1) * 32, t0, seq);
+          }
+          if (p.norm2 != NORM_NONE) {
+            uint32_t w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              s2 += v[i];
+              ss2 = fmaf(v[i], v[i], ss2);
+              w[i] = __float_as_uint(v[i]);
+            }
+            tmem_st32(taddr + c * 32, w);  // keep v for the LayerNorm2 pass
+          }
+        }
+      }
+      if (p.norm2 != NORM_NONE) {
+        tmem_st_wait();
+        ev.part[half][row_in_tile][0] = s2;
+        ev.part[half][row_in_tile][1] = ss2;
+        bar_epi();
+        s2 += ev.part[half ^ 1][row_in_tile][0];
+        ss2 += ev.part[half ^ 1][row_in_tile][1];
+        const float mean2 = s2 * (1.0f / kDim);
+        const float var2 = fmaxf(ss2 - s2 * mean2, 0.f) * (1.0f / kDim);
+        const float rstd2 = rsqrtf(var2 + kEps);
+        bar_epi();
+        uint32_t r[2][32];
+        uint8_t* rowp = nullptr;
+        tmem_ld32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(&ev.g2[cbase + c * 32 + i]);
+            const float4 b = *reinterpret_cast<const float4*>(&ev.b2[cbase + c * 32 + i]);
+            v[i] = fmaf((__uint_as_float(r[c & 1][i]) - mean2) * rstd2, g.x, b.x);
+            v[i + 1] = fmaf((__uint_as_float(r[c & 1][i + 1]) - mean2) * rstd2, g.y, b.y);
+            v[i + 2] = fmaf((__uint_as_float(r[c & 1][i + 2]) - mean2) * rstd2, g.z, b.z);
+            v[i + 3] = fmaf((__uint_as_float(r[c & 1][i + 3]) - mean2) * rstd2, g.w, b.w);
+          }
+          if ((c & 1) == 0) rowp = stg_acquire();
+          stg_put_bf16(rowp, (c & 1) * 4, v);
+          if (c & 1) stg_publish(&p.tma_o2, n0 + (c - 1) * 32, t0, seq);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (leader) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Same arguments as launch_gemm_tc, plus the fp32 layout choices:
+//   f32_mode 1: out1_f32 / resid / accumulate use the blocked layout (dense row index seq*rows_per_seq + t)
+//   f32_mode 2: out1_f32 is row-major (e.out1_map) and written through TMA staging; resid stays blocked.
+int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm, std::string* err) {
+  if (a.N % LBN || a.K % LBK) {
+    if (err) *err = "gemm_lin: N must be a multiple of 256 and K of 64";
+    return -1;
+  }
+  const Epilogue& e = a.e;
+  if ((e.norm1 != NORM_NONE || e.norm2 != NORM_NONE || e.bias) && a.N != LBN) {
+    if (err) *err = "gemm_lin: bias / row norms need N == 256";
+    return -1;
+  }
+  if ((e.resid || e.accumulate || (a.out1_f32 && f32_mode == 1)) && a.N != LBN) {
+    if (err) *err = "gemm_lin: blocked fp32 rows need N == 256";
+    return -1;
+  }
+  LinParams p{};
+  {
+    const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.rows_per_seq, (uint64_t)a.nseq};
+    const uint64_t strides[2] = {(uint64_t)a.a_map.row_stride,
+                                 (uint64_t)(a.nseq > 1 ? a.a_map.seq_stride : a.a_map.row_stride * a.rows_per_seq)};
+    const uint32_t box[3] = {LBK, LBM, 1};
+    if (!make_tmap_bf16(&p.tma_a, a.A, 3, dims, strides, box, err)) return -1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    const uint64_t strides[1] = {(uint64_t)a.K};
+    const uint32_t box[2] = {LBK, LBN};
+    if (!make_tmap_bf16(&p.tma_b, a.W, 2, dims, strides, box, err)) return -1;
+  }
+  auto out_map = [&](CUtensorMap* m, void* base, const RowMap& rm, int elem_bytes) {
+    const uint64_t dims[3] = {(uint64_t)a.N, (uint64_t)a.rows_per_seq, (uint64_t)a.nseq};
+    const uint64_t strides[2] = {(uint64_t)rm.row_stride,
+                                 (uint64_t)(a.nseq > 1 ? rm.seq_stride : rm.row_stride * a.rows_per_seq)};
+    const uint32_t box[3] = {elem_bytes == 2 ? 64u : 32u, 128, 1};
+    return make_tmap(m, base, elem_bytes, 3, dims, strides, box, 128, err);
+  };
+  if (a.out1_bf16 && !out_map(&p.tma_o1, a.out1_bf16, e.out1_map, 2)) return -1;
+  if (e.norm2 != NORM_NONE && !out_map(&p.tma_o2, e.out2, e.out2_map, 2)) return -1;
+  if (a.out1_f32 && f32_mode == 2 && !out_map(&p.tma_of, a.out1_f32, e.out1_map, 4)) return -1;
+  p.nseq = a.nseq;
+  p.rows_per_seq = a.rows_per_seq;
+  p.tiles_per_seq = (a.rows_per_seq + LBM - 1) / LBM;
+  p.n_tiles_n = a.N / LBN;
+  p.num_k_blocks = a.K / LBK;
+  p.N = a.N;
+  p.bias = e.bias;
+  p.norm1 = e.norm1; p.g1 = e.g1; p.b1 = e.b1;
+  p.act = e.act;
+  p.resid = e.resid;
+  p.accumulate = e.accumulate;
+  p.out1_f32 = a.out1_f32;
+  p.f32_mode = a.out1_f32 ? f32_mode : 0;
+  p.has_o1_bf16 = a.out1_bf16 != nullptr;
+  p.norm2 = e.norm2; p.g2 = e.g2; p.b2 = e.b2;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM) != cudaSuccess) {
+      if (err) *err = "gemm_lin: cannot reserve shared memory";
+      return -1;
+    }
+    configured = true;
+  }
+  const int tiles = p.nseq * p.tiles_per_seq * p.n_tiles_n;
+  const int grid = tiles < n_sm ? tiles : n_sm;
+  gemm_lin_kernel<<<grid, L_THREADS, L_SMEM, st>>>(p);
+  return 1;
+}
+
+}  // namespace vapb

@@ -33,6 +33,39 @@ vad_head_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
   }
 }
 
+// Same head on the row-blocked residual stream [row/128][col/4][row%128][4]: one thread per row, so every
+// float4 load is contiguous across the warp.
+__global__ void __launch_bounds__(128)
+vad_head_blocked_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                        int batch, int T, float* __restrict__ vad_logits, float* __restrict__ vad_sig) {
+  __shared__ float4 ws[64];
+  if (threadIdx.x < 64) ws[threadIdx.x] = reinterpret_cast<const float4*>(w)[threadIdx.x];
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (row >= (long long)2 * batch * T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x) + (long long)blockIdx.x * 64 * 128 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 16
+  for (int c = 0; c < 64; ++c) {
+    const float4 a = xr[c * 128];
+    const float4 b = ws[c];
+    s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
+  }
+  const float s = (s0 + s1) + (s2 + s3) + bias[0];
+  const long long seq = row / T, t = row % T;
+  const long long c = seq / batch, b = seq % batch;
+  const long long o = (b * T + t) * 2 + c;
+  if (vad_logits) vad_logits[o] = s;
+  if (vad_sig) vad_sig[o] = 1.0f / (1.0f + expf(-s));
+}
+
+int launch_vad_head_blocked(cudaStream_t st, const float* x, const float* w, const float* b, int batch, int T,
+                            float* vad_logits, float* vad_sig) {
+  const long long rows = (long long)2 * batch * T;
+  vad_head_blocked_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(x, w, b, batch, T, vad_logits, vad_sig);
+  return 1;
+}
+
 int launch_vad_head(cudaStream_t st, const float* x, const float* w, const float* b, int batch, int T,
                     float* vad_logits, float* vad_sig) {
   const long long rows = (long long)2 * batch * T;

@@ -113,6 +113,7 @@ struct StageRef {
   int is_bf16;
   RowMap map;
   int nseq, rows_per_seq;
+  int blocked = 0;  // fp32 row-blocked layout (k_gemm_lin.cu)
 };
 
 // ---- FP32 path (forward_fp32.cu) -------------------------------------------

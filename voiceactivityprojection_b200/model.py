@@ -273,20 +273,24 @@ class VapGPT(nn.Module):
             h, st, wav.data_ptr(), B, S, mode, ws.data_ptr(), ws.numel(),
             now_lims[0], now_lims[-1], future_lims[0], future_lims[1],
             None, None, out["probs"].data_ptr(), out["vad"].data_ptr(), out["p_now"].data_ptr(),
-            out["p_future"].data_ptr(), out["H"].data_ptr(), out["loss"].data_ptr(), None))
+            out["p_future"].data_ptr(), out["H"].data_ptr(), out["loss"].data_ptr(),
+            out["argmax"].data_ptr() if "argmax" in out else None))
         return out
 
     @staticmethod
-    def alloc_outputs(B: int, T: int, device) -> Dict[str, Tensor]:
-        f = dict(dtype=torch.float32, device=device)
-        return {
+    def alloc_outputs(B: int, T: int, device, argmax: bool = False, pin_memory: bool = False) -> Dict[str, Tensor]:
+        """The six `probs()` outputs (vap/model.py:212-224); with argmax=True also the
+        uint8 arg-max projection-window class per frame (an extra the bulk driver uses)."""
+        f = dict(dtype=torch.float32, device=device, pin_memory=pin_memory)
+        extra = {"argmax": torch.empty((B, T), dtype=torch.uint8, device=device, pin_memory=pin_memory)} if argmax else {}
+        return {**{
             "probs": torch.empty((B, T, 256), **f),
             "vad": torch.empty((B, T, 2), **f),
             "p_now": torch.empty((B, T, 2), **f),
             "p_future": torch.empty((B, T, 2), **f),
             "H": torch.empty((B, T), **f),
             "loss": torch.empty((B, T - 100), **f),
-        }
+        }, **extra}
 
     @torch.no_grad()
     def probs_host(self, waveform: Tensor, keys=("probs", "vad", "p_now", "p_future", "H", "loss"),
