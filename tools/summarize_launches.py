@@ -1,45 +1,59 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list:
-per-kernel launch count, total device time and share.
+"""Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv`
+launch list: per-kernel launch count, total device time, share and (when captured) DRAM traffic.
 
-    python tools/summarize_launches.py gpurun_out/launches.csv [--skip N] > profiles/<name>.md
+    python tools/summarize_launches.py gpurun_out/launches.csv [--skip N] [--each] > profiles/<name>.md
 """
 import csv
 import re
 import sys
 from collections import OrderedDict
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0,
+        "ms": 1e3, "msecond": 1e3}
+
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
     name = re.sub(r"<.*", "", name)
-    return name.replace("void ", "").replace("vapb::", "").strip()[:60]
+    return name.replace("void ", "").replace("vapb::", "").replace("(anonymous namespace)::", "").strip()[:60]
 
 
 def main():
     path = sys.argv[1]
     skip = int(sys.argv[sys.argv.index("--skip") + 1]) if "--skip" in sys.argv else 0
-    rows = []
+    launches = OrderedDict()
     with open(path, newline="") as f:
         lines = [l for l in f if not l.startswith("==")]
     for r in csv.DictReader(lines):
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
-        rows.append((int(r["ID"]), short(r["Kernel Name"]), r["Grid Size"], r["Block Size"],
-                     float(r["Metric Value"].replace(",", "")) / 1e3))
-    rows = [r for r in rows if r[0] >= skip]
+        i = int(r["ID"])
+        d = launches.setdefault(i, {"name": short(r["Kernel Name"]), "grid": r["Grid Size"], "block": r["Block Size"]})
+        v = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
+        d[r["Metric Name"]] = v
+    rows = [d for i, d in launches.items() if i >= skip]
+    have_dram = any("dram__bytes_read.sum" in d for d in rows)
+    if "--each" in sys.argv:
+        print("| # | kernel | grid | us | dram rd MB | dram wr MB | GB/s |")
+        print("|---|---|---|---:|---:|---:|---:|")
+        for i, d in enumerate(rows):
+            us = d.get("gpu__time_duration.sum", 0.0)
+            rd, wr = d.get("dram__bytes_read.sum", 0.0) / 1e6, d.get("dram__bytes_write.sum", 0.0) / 1e6
+            print(f"| {i} | {d['name']} | {d['grid']} | {us:.1f} | {rd:.1f} | {wr:.1f} | {(rd + wr) / us * 1e3 if us else 0:.0f} |")
+        return
     agg = OrderedDict()
-    for _, k, grid, blk, us in rows:
-        a = agg.setdefault(k, [0, 0.0, grid, blk])
+    for d in rows:
+        a = agg.setdefault(d["name"], [0, 0.0, d["grid"], d["block"], 0.0])
         a[0] += 1
-        a[1] += us
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[4] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     tot = sum(a[1] for a in agg.values())
     print(f"source: {path}  launches: {len(rows)} (skipped first {skip})  total {tot / 1e3:.2f} ms "
           "(ncu-serialised, cold-cache: compare shares)\n")
-    print("| kernel | launches | total ms | share | avg us | grid (last) | block |")
-    print("|---|---:|---:|---:|---:|---|---|")
-    for k, (n, us, grid, blk) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| {k} | {n} | {us / 1e3:.3f} | {us / tot * 100:.1f}% | {us / n:.1f} | {grid} | {blk} |")
+    print("| kernel | launches | total ms | share | avg us | grid (last) | block |" + (" DRAM GB | GB/s |" if have_dram else ""))
+    print("|---|---:|---:|---:|---:|---|---|" + ("---:|---:|" if have_dram else ""))
+    for k, (n, us, grid, blk, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        extra = f" {by / 1e9:.2f} | {by / us / 1e3:.0f} |" if have_dram else ""
+        print(f"| {k} | {n} | {us / 1e3:.3f} | {us / tot * 100:.1f}% | {us / n:.1f} | {grid} | {blk} |" + extra)
 
 
 if __name__ == "__main__":

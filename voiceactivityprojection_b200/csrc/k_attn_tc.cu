@@ -45,6 +45,8 @@ struct alignas(64) AttnParams {
   __nv_bfloat16* out;      // (nseq*T, 256)
   const float* slopes;     // [n_heads]
   int nseq, T, nqt, head_pairs, n_items, cross;
+  int pair_major;  // large batches: a CTA walks all query tiles of one (sequence, head pair) back to back, so the
+                   // pair's K/V (re-read once per query tile) stay in L2; small batches: spread single tiles
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -70,14 +72,24 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 struct Item {
   int qi, seq, hp;
 };
-__device__ __forceinline__ Item decode_item(const AttnParams& p, int item) {
+// k-th work item of this CTA; false when the CTA is done
+__device__ __forceinline__ bool next_item(const AttnParams& p, int k, Item* it) {
   const int per_q = p.nseq * p.head_pairs;
-  Item it;
-  it.qi = p.nqt - 1 - item / per_q;
+  if (p.pair_major) {
+    const int pi = blockIdx.x + (k / p.nqt) * gridDim.x;
+    if (pi >= per_q) return false;
+    it->qi = p.nqt - 1 - k % p.nqt;
+    it->seq = pi / p.head_pairs;
+    it->hp = pi % p.head_pairs;
+    return true;
+  }
+  const int item = blockIdx.x + k * gridDim.x;
+  if (item >= p.n_items) return false;
+  it->qi = p.nqt - 1 - item / per_q;
   const int rem = item % per_q;
-  it.seq = rem / p.head_pairs;
-  it.hp = rem % p.head_pairs;
-  return it;
+  it->seq = rem / p.head_pairs;
+  it->hp = rem % p.head_pairs;
+  return true;
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
@@ -122,8 +134,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     // ===== TMA producer
     if (lane == 0) {
       uint32_t n_item = 0, kvc[2] = {0, 0};
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_item) {
-        const Item it = decode_item(p, item);
+      Item it;
+      for (int k = 0; next_item(p, k, &it); ++k, ++n_item) {
         const int kvseq = p.cross ? (it.seq + p.nseq / 2) % p.nseq : it.seq;
         for (int s = 0; s < 2; ++s) {
           mbar_wait(q_empty(s), (n_item & 1u) ^ 1u);
@@ -161,8 +173,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                     make_smem_desc_sw128(ka + k * 32, 0, 1024), idesc_qk, k != 0);
         umma_commit(s_full(s));
       };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_item) {
-        const Item it = decode_item(p, item);
+      Item it;
+      for (int k = 0; next_item(p, k, &it); ++k, ++n_item) {
         const int ntiles = it.qi + 1;
         for (int s = 0; s < 2; ++s) {
           mbar_wait(q_full(s), n_item & 1u);
@@ -199,8 +211,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const uint32_t t_p = t_s + AT_COL_P, t_o = t_s + AT_COL_O;
     constexpr float SC = 0.0625f * kLog2e;
     uint32_t sc_cnt = 0, oc_cnt = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
+    Item it;
+    for (int k = 0; next_item(p, k, &it); ++k) {
       const int head = it.hp * 2 + s;
       const float slope2 = p.slopes[head] * kLog2e;
       float m = -INFINITY, l = 0.f;
@@ -341,6 +353,7 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
   p.head_pairs = n_heads / 2;
   p.n_items = p.nqt * nseq * p.head_pairs;
   p.cross = cross;
+  p.pair_major = nseq * p.head_pairs >= 2 * n_sm;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {

@@ -14,6 +14,11 @@
 //     row-blocked layout [row/128][col/4][row%128][4]: the thread that owns
 //     accumulator row r reads/writes float4s that are contiguous across the warp;
 //   * fp32 row-major outputs (logits) go through the same staging tiles (128 x 32).
+// With K = 256 (every q/k/v/proj/FFN-in GEMM) the kernel runs "weight-resident": a CTA owns one 256-column
+// slice of W for its whole life (128 KB of shared memory, loaded once) and streams only A tiles, because at
+// 1 us of tensor time per tile re-fetching 128 KB of W per tile made these GEMMs L2->SM-bandwidth bound
+// (measured: 2.36 GB through L2 for a 1 GB qkv GEMM). CTAs that share an M tile but own different W slices
+// walk the M tiles in lockstep, so A is fetched from HBM once.
 // TMEM loads are double-buffered against the math; GELU uses the tanh form on
 // tanh.approx (3e-4 abs, below the bf16 rounding of its output).
 #include <string>
@@ -30,21 +35,30 @@ namespace {
 constexpr int LBM = 128, LBN = 256, LBK = 64, LSTAGES = 3;
 constexpr int LA_BYTES = LBM * LBK * 2, LB_BYTES = LBN * LBK * 2;
 constexpr int LSTAGE_BYTES = LA_BYTES + LB_BYTES;   // 48 KB
-constexpr int LSTG_TILE = 128 * 128;                // staging tile: 128 rows x 128 B
-constexpr int L_OFF_STG = LSTAGES * LSTAGE_BYTES;   // [half][2] staging tiles
-constexpr int L_OFF_BAR = L_OFF_STG + 4 * LSTG_TILE;
-constexpr int L_OFF_VEC = L_OFF_BAR + 256;
+constexpr int LSTG_HALF = 128 * 128;                // staging per column half: 2 x (128 rows x 64 B) bf16 tiles (SW64),
+                                                    // or 1 x (128 rows x 128 B) fp32 tile (SW128)
 constexpr int L_THREADS = 384, L_EPI_THREADS = 256;
+// shared-memory plan: [operand region][staging 2 x 16 KB][barriers 256 B][LinVecs]
+//   streaming:        3 stages x (A 16 KB + W 32 KB)
+//   weight-resident:  W 4 x 32 KB, then 3 stages x A 16 KB
+template <bool WRES>
+struct LinSmem {
+  static constexpr int OPERANDS = WRES ? 4 * LB_BYTES + LSTAGES * LA_BYTES : LSTAGES * LSTAGE_BYTES;
+  static constexpr int OFF_STG = OPERANDS;
+  static constexpr int OFF_BAR = OFF_STG + 2 * LSTG_HALF;
+  static constexpr int OFF_VEC = OFF_BAR + 256;
+};
 
 struct LinVecs {
   float bias[256], g1[256], b1[256], g2[256], b2[256];
   float part[2][128][2];
 };
-constexpr int L_SMEM = L_OFF_VEC + (int)sizeof(LinVecs) + 1024 /*alignment slack*/;
+template <bool WRES>
+constexpr int lin_smem_bytes() { return LinSmem<WRES>::OFF_VEC + (int)sizeof(LinVecs) + 1024 /*alignment slack*/; }
 
 struct alignas(64) LinParams {
   CUtensorMap tma_a, tma_b;
-  CUtensorMap tma_o1;   // out1 bf16  (N, rows, nseq) box (64,128,1) SW128
+  CUtensorMap tma_o1;   // out1 bf16  (N, rows, nseq) box (32,128,1) SW64
   CUtensorMap tma_o2;   // out2 bf16
   CUtensorMap tma_of;   // out1 fp32 row-major (N, rows, nseq) box (32,128,1) SW128
   int nseq, rows_per_seq, tiles_per_seq, n_tiles_n, num_k_blocks, N;
@@ -84,7 +98,26 @@ __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: 
 
 }  // namespace
 
+// Epilogue features compiled into an instantiation. The do-everything epilogue is ~140 KB of SASS and its warps
+// stalled on instruction fetch (ncu: stall_no_instruction was the top stall reason), so each launch picks the
+// smallest instantiation that covers what it needs.
+enum : int {
+  F_PRE = 1,     // bias and/or norm1 on the accumulator
+  F_ACT = 2,     // ReLU / GELU
+  F_RESID = 4,   // + residual (blocked fp32)
+  F_ACC = 8,     // += previous out1_f32 (blocked fp32)
+  F_F32B = 16,   // out1_f32, blocked
+  F_F32R = 32,   // out1_f32, row-major through TMA
+  F_O1B = 64,    // out1 bf16
+  F_N2 = 128,    // out2 = LayerNorm2(v) bf16
+  F_ALL = 255
+};
+
+template <bool WRES, int F>
 __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_constant__ LinParams p) {
+  constexpr bool C_PRE = F & F_PRE, C_ACT = F & F_ACT, C_RESID = F & F_RESID, C_ACC = F & F_ACC, C_F32B = F & F_F32B,
+                 C_F32R = F & F_F32R, C_O1B = F & F_O1B, C_N2 = F & F_N2;
+  constexpr int L_OFF_STG = LinSmem<WRES>::OFF_STG, L_OFF_BAR = LinSmem<WRES>::OFF_BAR, L_OFF_VEC = LinSmem<WRES>::OFF_VEC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -94,6 +127,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (8 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (10 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 12;
+  const uint32_t w_full = bar_base + 8u * 14;
   LinVecs& ev = *reinterpret_cast<LinVecs*>(smem_gen + L_OFF_VEC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -108,6 +142,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), L_EPI_THREADS);
     }
+    mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -125,21 +160,37 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int num_tiles = p.nseq * p.tiles_per_seq * p.n_tiles_n;
+  // Tile walk. Streaming: (mt, nt) pairs strided over the grid. Weight-resident: the CTA's nt is fixed
+  // (blockIdx % n_tiles_n) and it strides over M tiles with the CTAs of its group.
+  const int num_m_tiles = p.nseq * p.tiles_per_seq;
+  const int groups = WRES ? (int)gridDim.x / p.n_tiles_n : 1;
+  const int my_nt = WRES ? (int)blockIdx.x % p.n_tiles_n : 0;
+  const int tile_first = WRES ? ((int)blockIdx.x / p.n_tiles_n < groups ? (int)blockIdx.x / p.n_tiles_n : num_m_tiles)
+                              : (int)blockIdx.x;
+  const int tile_stride = WRES ? groups : (int)gridDim.x;
+  const int num_tiles = WRES ? num_m_tiles : num_m_tiles * p.n_tiles_n;
+  auto tile_mt = [&](int tile) { return WRES ? tile : tile / p.n_tiles_n; };
+  auto tile_nt = [&](int tile) { return WRES ? my_nt : tile % p.n_tiles_n; };
+  constexpr uint32_t A_RING = WRES ? 4 * LB_BYTES : 0;            // first byte of the A ring
+  constexpr uint32_t A_STRIDE = WRES ? LA_BYTES : LSTAGE_BYTES;   // bytes between ring stages
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+      if (WRES && tile_first < num_tiles) {
+        mbar_arrive_expect_tx(w_full, 4 * LB_BYTES);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem_base + kb * LB_BYTES, &p.tma_b, w_full, kb * LBK, my_nt * LBN);
+      }
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+        const int mt = tile_mt(tile), nt = tile_nt(tile);
         const int seq = mt / p.tiles_per_seq, t0 = (mt % p.tiles_per_seq) * LBM;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), LSTAGE_BYTES);
-          const uint32_t a_dst = smem_base + stage * LSTAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), WRES ? LA_BYTES : LSTAGE_BYTES);
+          const uint32_t a_dst = smem_base + A_RING + stage * A_STRIDE;
           tma_load_3d(a_dst, &p.tma_a, full_bar(stage), kb * LBK, t0, seq);
-          tma_load_2d(a_dst + LA_BYTES, &p.tma_b, full_bar(stage), kb * LBK, nt * LBN);
+          if (!WRES) tma_load_2d(a_dst + LA_BYTES, &p.tma_b, full_bar(stage), kb * LBK, nt * LBN);
           if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -149,15 +200,19 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(LBM, LBN, 0, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (WRES && tile_first < num_tiles) {
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+      }
+      for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * LBN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * LSTAGE_BYTES;
-          const uint32_t b_addr = a_addr + LA_BYTES;
+          const uint32_t a_addr = smem_base + A_RING + stage * A_STRIDE;
+          const uint32_t b_addr = WRES ? smem_base + kb * LB_BYTES : a_addr + LA_BYTES;
 #pragma unroll
           for (int k = 0; k < LBK / 16; ++k)
             umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
@@ -175,29 +230,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
     const int row_in_tile = quad * 32 + lane;
     const bool leader = (threadIdx.x - 128 - half * 128) == 0;  // issues this half's TMA stores
     const int cbase = half * 128;
-    const uint32_t stg_addr = smem_base + L_OFF_STG + half * 2 * LSTG_TILE;
-    uint8_t* stg_gen = smem_gen + L_OFF_STG + half * 2 * LSTG_TILE;
-    const uint32_t sw = (uint32_t)(row_in_tile & 7);
-    const uint32_t stg_row = (uint32_t)row_in_tile * 128u;
+    const uint32_t stg_addr = smem_base + L_OFF_STG + half * LSTG_HALF;
+    uint8_t* stg_gen = smem_gen + L_OFF_STG + half * LSTG_HALF;
+    const uint32_t sw128 = (uint32_t)(row_in_tile & 7), sw64 = (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t stg_cnt = 0;
-    // staging-tile protocol: acquire (previous TMA store that read this buffer has drained) -> all 128 threads
-    // write their row -> publish (fence to the async proxy, barrier, leader issues the store)
-    auto stg_acquire = [&]() -> uint8_t* {
+    // bf16 staging: 32 columns of the tile = 128 rows x 64 B (SWIZZLE_64B: chunk j of row r at r*64 + ((j ^ (r/2 & 3)) << 4),
+    // conflict-free for 8 consecutive rows), two buffers. All 128 threads of the half write their row, then the
+    // leader hands the tile to TMA; a buffer is reused once the store that read it two tiles ago has drained.
+    auto stage_bf16 = [&](const CUtensorMap* map, const float (&v)[32], int c0, int c1, int c2) {
       if (leader) bulk_wait_read<1>();
       bar_half(half);
-      return stg_gen + (stg_cnt & 1u) * LSTG_TILE + stg_row;
-    };
-    auto stg_publish = [&](const CUtensorMap* map, int c0, int c1, int c2) {
-      fence_proxy_async();
-      bar_half(half);
-      if (leader) {
-        tma_store_3d(map, stg_addr + (stg_cnt & 1u) * LSTG_TILE, c0, c1, c2);
-        bulk_commit();
-      }
-      ++stg_cnt;
-    };
-    // 32 fp32 -> 32 bf16 = 4 x 16 B chunks at chunk index j0..j0+3 of this thread's staging row
-    auto stg_put_bf16 = [&](uint8_t* rowp, int j0, const float (&v)[32]) {
+      const uint32_t boff = (stg_cnt & 1u) * 8192u;
+      uint8_t* rowp = stg_gen + boff + (uint32_t)row_in_tile * 64u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 u;
@@ -205,20 +249,37 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
         u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
         u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
         u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(j0 + j)) ^ sw) << 4)) = u;
+        *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
       }
+      fence_proxy_async();
+      bar_half(half);
+      if (leader) {
+        tma_store_3d(map, stg_addr + boff, c0, c1, c2);
+        bulk_commit();
+      }
+      ++stg_cnt;
     };
-    auto stg_put_f32 = [&](uint8_t* rowp, const float (&v)[32]) {
+    // fp32 row-major staging (logits): 32 columns = 128 rows x 128 B (SWIZZLE_128B), single buffer
+    auto stage_f32 = [&](const CUtensorMap* map, const float (&v)[32], int c0, int c1, int c2) {
+      if (leader) bulk_wait_read<0>();
+      bar_half(half);
+      uint8_t* rowp = stg_gen + (uint32_t)row_in_tile * 128u;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ sw) << 4)) =
+        *reinterpret_cast<float4*>(rowp + (((uint32_t)j ^ sw128) << 4)) =
             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      fence_proxy_async();
+      bar_half(half);
+      if (leader) {
+        tma_store_3d(map, stg_addr, c0, c1, c2);
+        bulk_commit();
+      }
     };
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+    for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+      const int mt = tile_mt(tile), nt = tile_nt(tile);
       const int seq = mt / p.tiles_per_seq, t0 = (mt % p.tiles_per_seq) * LBM;
       const int t = t0 + row_in_tile;
       const bool valid = t < p.rows_per_seq;
@@ -229,7 +290,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * LBN + cbase;
 
       float mean1 = 0.f, rstd1 = 1.f;
-      if (p.norm1 != NORM_NONE) {
+      if (C_PRE && p.norm1 != NORM_NONE) {
         float s = 0.f, ss = 0.f;
         uint32_t r[2][32];
         tmem_ld32(taddr, r[0]);
@@ -258,14 +319,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
       float s2 = 0.f, ss2 = 0.f;
       {
         uint32_t r[2][32];
-        uint8_t* rowp = nullptr;
         tmem_ld32(taddr, r[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tmem_ld_wait();
           if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
           float v[32];
-          if (p.bias || p.norm1 != NORM_NONE) {
+          if (C_PRE && (p.bias || p.norm1 != NORM_NONE)) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 bi = *reinterpret_cast<const float4*>(&ev.bias[cbase + c * 32 + i]);
@@ -276,14 +336,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
               for (int j = 0; j < 4; ++j) {
                 float x = __uint_as_float(r[c & 1][i + j]) + bb[j];
                 if (p.norm1 != NORM_NONE) x = fmaf((x - mean1) * rstd1, gg[j], be[j]);
-                v[i + j] = act_fast(x, p.act);
+                v[i + j] = C_ACT ? act_fast(x, p.act) : x;
               }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = act_fast(__uint_as_float(r[c & 1][i]), p.act);
+            for (int i = 0; i < 32; ++i)
+              v[i] = C_ACT ? act_fast(__uint_as_float(r[c & 1][i]), p.act) : __uint_as_float(r[c & 1][i]);
           }
-          if (p.resid && valid) {
+          if (C_RESID && p.resid && valid) {
             const float* rp = p.resid + blocked_off(m, n0 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -291,7 +352,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
               v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
             }
           }
-          if (p.accumulate && valid) {
+          if (C_ACC && p.accumulate && valid) {
             const float* ap = p.out1_f32 + blocked_off(m, n0 + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -299,24 +360,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
               v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
             }
           }
-          if (p.f32_mode == 1) {
+          if (C_F32B && p.f32_mode == 1) {
             if (valid) {
               float* op = p.out1_f32 + blocked_off(m, n0 + c * 32);
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(op + i * 512) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-          } else if (p.f32_mode == 2) {
-            uint8_t* rp2 = stg_acquire();
-            stg_put_f32(rp2, v);
-            stg_publish(&p.tma_of, n0 + c * 32, t0, seq);
+          } else if (C_F32R && p.f32_mode == 2) {
+            stage_f32(&p.tma_of, v, n0 + c * 32, t0, seq);
           }
-          if (p.has_o1_bf16) {
-            if ((c & 1) == 0) rowp = stg_acquire();
-            stg_put_bf16(rowp, (c & 1) * 4, v);
-            if (c & 1) stg_publish(&p.tma_o1, n0 + (c - 1) * 32, t0, seq);
-          }
-          if (p.norm2 != NORM_NONE) {
+          if (C_O1B && p.has_o1_bf16) stage_bf16(&p.tma_o1, v, n0 + c * 32, t0, seq);
+          if (C_N2 && p.norm2 != NORM_NONE) {
             uint32_t w[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -328,7 +383,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
           }
         }
       }
-      if (p.norm2 != NORM_NONE) {
+      if (C_N2 && p.norm2 != NORM_NONE) {
         tmem_st_wait();
         ev.part[half][row_in_tile][0] = s2;
         ev.part[half][row_in_tile][1] = ss2;
@@ -340,7 +395,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
         const float rstd2 = rsqrtf(var2 + kEps);
         bar_epi();
         uint32_t r[2][32];
-        uint8_t* rowp = nullptr;
         tmem_ld32(taddr, r[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -356,9 +410,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
             v[i + 2] = fmaf((__uint_as_float(r[c & 1][i + 2]) - mean2) * rstd2, g.z, b.z);
             v[i + 3] = fmaf((__uint_as_float(r[c & 1][i + 3]) - mean2) * rstd2, g.w, b.w);
           }
-          if ((c & 1) == 0) rowp = stg_acquire();
-          stg_put_bf16(rowp, (c & 1) * 4, v);
-          if (c & 1) stg_publish(&p.tma_o2, n0 + (c - 1) * 32, t0, seq);
+          stage_bf16(&p.tma_o2, v, n0 + c * 32, t0, seq);
         }
       }
       tc_fence_before();
@@ -410,9 +462,13 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
     const uint64_t dims[3] = {(uint64_t)a.N, (uint64_t)a.rows_per_seq, (uint64_t)a.nseq};
     const uint64_t strides[2] = {(uint64_t)rm.row_stride,
                                  (uint64_t)(a.nseq > 1 ? rm.seq_stride : rm.row_stride * a.rows_per_seq)};
-    const uint32_t box[3] = {elem_bytes == 2 ? 64u : 32u, 128, 1};
-    return make_tmap(m, base, elem_bytes, 3, dims, strides, box, 128, err);
+    const uint32_t box[3] = {32, 128, 1};
+    return make_tmap(m, base, elem_bytes, 3, dims, strides, box, elem_bytes == 2 ? 64 : 128, err);
   };
+  if (a.out1_f32 && f32_mode == 2 && (a.out1_bf16 || e.norm2 != NORM_NONE)) {
+    if (err) *err = "gemm_lin: a row-major fp32 output cannot be combined with bf16 outputs";
+    return -1;
+  }
   if (a.out1_bf16 && !out_map(&p.tma_o1, a.out1_bf16, e.out1_map, 2)) return -1;
   if (e.norm2 != NORM_NONE && !out_map(&p.tma_o2, e.out2, e.out2_map, 2)) return -1;
   if (a.out1_f32 && f32_mode == 2 && !out_map(&p.tma_of, a.out1_f32, e.out1_map, 4)) return -1;
@@ -431,17 +487,38 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
   p.f32_mode = a.out1_f32 ? f32_mode : 0;
   p.has_o1_bf16 = a.out1_bf16 != nullptr;
   p.norm2 = e.norm2; p.g2 = e.g2; p.b2 = e.b2;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM) != cudaSuccess) {
+  const int need = ((e.bias || e.norm1 != NORM_NONE) ? F_PRE : 0) | (e.act != ACT_NONE ? F_ACT : 0) |
+                   (e.resid ? F_RESID : 0) | (e.accumulate ? F_ACC : 0) | (p.f32_mode == 1 ? F_F32B : 0) |
+                   (p.f32_mode == 2 ? F_F32R : 0) | (p.has_o1_bf16 ? F_O1B : 0) | (e.norm2 != NORM_NONE ? F_N2 : 0);
+  typedef void (*KFn)(const LinParams);
+  struct Variant { int mask; KFn fn[2]; bool configured[2]; };
+#define VAPB_LIN_VARIANT(M) {M, {gemm_lin_kernel<false, M>, gemm_lin_kernel<true, M>}, {false, false}}
+  static Variant variants[] = {
+      VAPB_LIN_VARIANT(F_O1B),                                        // q/k/v, cross k/v, cross q
+      VAPB_LIN_VARIANT(F_O1B | F_ACT),                                // FFN in + GELU
+      VAPB_LIN_VARIANT(F_RESID | F_F32B | F_N2),                      // attention out-projection
+      VAPB_LIN_VARIANT(F_RESID | F_F32B | F_O1B | F_N2),              // FFN out
+      VAPB_LIN_VARIANT(F_PRE | F_F32R),                               // vap_head
+      VAPB_LIN_VARIANT(F_PRE | F_ACT | F_ACC | F_F32B | F_O1B),       // combinator
+      VAPB_LIN_VARIANT(F_PRE | F_ACT | F_F32B | F_O1B | F_N2),        // downsample conv
+      VAPB_LIN_VARIANT(F_ALL),
+  };
+#undef VAPB_LIN_VARIANT
+  Variant* v = nullptr;
+  for (auto& cand : variants)
+    if ((need & ~cand.mask) == 0) { v = &cand; break; }
+  const int tiles = p.nseq * p.tiles_per_seq * p.n_tiles_n;
+  const int grid = tiles < n_sm ? tiles : n_sm;
+  const int wres = (a.K == 4 * LBK && grid >= p.n_tiles_n) ? 1 : 0;
+  const int smem = wres ? lin_smem_bytes<true>() : lin_smem_bytes<false>();
+  if (!v->configured[wres]) {
+    if (cudaFuncSetAttribute(v->fn[wres], cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       if (err) *err = "gemm_lin: cannot reserve shared memory";
       return -1;
     }
-    configured = true;
+    v->configured[wres] = true;
   }
-  const int tiles = p.nseq * p.tiles_per_seq * p.n_tiles_n;
-  const int grid = tiles < n_sm ? tiles : n_sm;
-  gemm_lin_kernel<<<grid, L_THREADS, L_SMEM, st>>>(p);
+  v->fn[wres]<<<grid, L_THREADS, smem, st>>>(p);
   return 1;
 }
 

@@ -334,7 +334,8 @@ bool make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, con
   const CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim, estride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) {

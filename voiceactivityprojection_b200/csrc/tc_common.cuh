@@ -261,7 +261,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint
 // elements (innermost first; strides for dims 1..rank-1), box in elements.
 bool make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                     const uint32_t* box, std::string* err);
-// General form: element size 2 or 4 bytes, swizzle 0 (none) or 128, rank <= 5.
+// General form: element size 2 or 4 bytes, swizzle 0 (none), 64 or 128, rank <= 5.
 bool make_tmap(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                const uint64_t* strides_elems, const uint32_t* box, int swizzle, std::string* err);
 
