@@ -184,7 +184,8 @@ def test_attention_tc_matches_torch(nseq, T, cross, packed, scale):
     d = (out.float() - ref).abs()
     assert torch.isfinite(out.float()).all()
     # P and the output are rounded to bf16 (2^-9 relative); V is O(scale)
-    assert d.max().item() <= 2e-2 * scale, d.max().item()
+    # P and the output are bf16: allow 2.5 ulp (2^-8 relative) of the largest output; the mean bound is the tight one
+    assert d.max().item() <= 2.5 * 2.0 ** -8 * ref.abs().max().item() + 1e-2, d.max().item()
     assert d.mean().item() <= 2e-3 * scale
 
 

@@ -30,11 +30,15 @@ using namespace tc;
 namespace {
 
 constexpr int AT_TILE = 128 * 64 * 2;  // one 128-row x 64-column bf16 tile (Q, K or V of one head)
-constexpr int AT_THREADS = 384;        // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 softmax slot 0, 8-11 softmax slot 1
-constexpr int AT_OFF_Q = 0;                        // [slot]
-constexpr int AT_OFF_K = 2 * AT_TILE;              // [slot][stage]
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle; warps 4-11 softmax of slot 0, 12-19 softmax of slot 1. A softmax thread
+// owns HALF a query row (64 of the 128 keys of a tile; warps 4 apart share a TMEM lane quadrant), so the
+// dependent chain MMA -> softmax -> MMA of a slot is half as long and 16 warps hide each other's TMEM latency.
+constexpr int AT_THREADS = 640;
+constexpr int AT_OFF_Q = 0;                        // [slot][2 buffers]
+constexpr int AT_OFF_K = 4 * AT_TILE;              // [slot][stage]
 constexpr int AT_OFF_V = AT_OFF_K + 4 * AT_TILE;   // [slot][stage]
-constexpr int AT_OFF_BAR = AT_OFF_V + 4 * AT_TILE;
+constexpr int AT_OFF_X = AT_OFF_V + 4 * AT_TILE;   // row max / row sum exchange: float [slot][parity][half][128]
+constexpr int AT_OFF_BAR = AT_OFF_X + 2 * 2 * 2 * 128 * 4;
 constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024 /*alignment slack*/;
 // TMEM columns of a slot: S fp32 [0,128), P bf16x2 [128,192), O fp32 [192,256)
 constexpr int AT_COL_P = 128, AT_COL_O = 192, AT_SLOT_COLS = 256;
@@ -96,14 +100,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + AT_OFF_BAR;
-  auto q_full = [&](int s) { return bar_base + 8u * s; };
-  auto q_empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto kv_full = [&](int s, int st) { return bar_base + 8u * (4 + s * 2 + st); };
-  auto kv_empty = [&](int s, int st) { return bar_base + 8u * (8 + s * 2 + st); };
-  auto s_full = [&](int s) { return bar_base + 8u * (12 + s); };
-  auto p_full = [&](int s) { return bar_base + 8u * (14 + s); };
-  auto o_final = [&](int s) { return bar_base + 8u * (16 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * 18;
+  auto q_full = [&](int s, int b) { return bar_base + 8u * (s * 2 + b); };
+  auto q_empty = [&](int s, int b) { return bar_base + 8u * (4 + s * 2 + b); };
+  auto kv_full = [&](int s, int st) { return bar_base + 8u * (8 + s * 2 + st); };
+  auto kv_empty = [&](int s, int st) { return bar_base + 8u * (12 + s * 2 + st); };
+  auto s_full = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto p_full = [&](int s) { return bar_base + 8u * (18 + s); };
+  auto o_final = [&](int s) { return bar_base + 8u * (20 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 22;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -111,14 +116,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     prefetch_tmap(&p.tk);
     prefetch_tmap(&p.tv);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(q_full(s), 1);
-      mbar_init(q_empty(s), 1);
       for (int st = 0; st < 2; ++st) {
+        mbar_init(q_full(s, st), 1);
+        mbar_init(q_empty(s, st), 1);
         mbar_init(kv_full(s, st), 1);
         mbar_init(kv_empty(s, st), 1);
       }
       mbar_init(s_full(s), 1);
-      mbar_init(p_full(s), 128);
+      mbar_init(p_full(s), 256);
       mbar_init(o_final(s), 1);
     }
     fence_barrier_init();
@@ -131,17 +136,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===== TMA producer
+    // ===== TMA producer. The Q tile of the NEXT item is requested before the K/V tiles of the current one
+    // (two Q buffers per slot), so an item boundary costs no load latency.
     if (lane == 0) {
-      uint32_t n_item = 0, kvc[2] = {0, 0};
-      Item it;
-      for (int k = 0; next_item(p, k, &it); ++k, ++n_item) {
-        const int kvseq = p.cross ? (it.seq + p.nseq / 2) % p.nseq : it.seq;
+      uint32_t kvc[2] = {0, 0};
+      auto load_q = [&](const Item& it, uint32_t n) {
+        const int b = n & 1;
         for (int s = 0; s < 2; ++s) {
-          mbar_wait(q_empty(s), (n_item & 1u) ^ 1u);
-          mbar_arrive_expect_tx(q_full(s), AT_TILE);
-          tma_load_3d(smem_base + AT_OFF_Q + s * AT_TILE, &p.tq, q_full(s), (it.hp * 2 + s) * 64, it.qi * 128, it.seq);
+          mbar_wait(q_empty(s, b), ((n >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(q_full(s, b), AT_TILE);
+          tma_load_3d(smem_base + AT_OFF_Q + (s * 2 + b) * AT_TILE, &p.tq, q_full(s, b), (it.hp * 2 + s) * 64,
+                      it.qi * 128, it.seq);
         }
+      };
+      Item it, nx;
+      bool have = next_item(p, 0, &it);
+      if (have) load_q(it, 0);
+      for (uint32_t k = 0; have; ++k) {
+        const bool have_next = next_item(p, (int)k + 1, &nx);
+        if (have_next) load_q(nx, k + 1);
+        const int kvseq = p.cross ? (it.seq + p.nseq / 2) % p.nseq : it.seq;
         for (int kt = it.qi; kt >= 0; --kt) {
           for (int s = 0; s < 2; ++s) {
             const int st = kvc[s] & 1;
@@ -153,6 +167,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             tma_load_3d(smem_base + AT_OFF_V + (s * 2 + st) * AT_TILE, &p.tv, kv_full(s, st), col, kt * 128, kvseq);
           }
         }
+        it = nx;
+        have = have_next;
       }
     }
   } else if (warp == 1) {
@@ -165,7 +181,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         const int st = kvc[s] & 1;
         mbar_wait(kv_full(s, st), (kvc[s] >> 1) & 1u);
         tc_fence_after();
-        const uint32_t qa = smem_base + AT_OFF_Q + s * AT_TILE;
+        const uint32_t qa = smem_base + AT_OFF_Q + (s * 2 + (n_item & 1)) * AT_TILE;
         const uint32_t ka = smem_base + AT_OFF_K + (s * 2 + st) * AT_TILE;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       for (int k = 0; next_item(p, k, &it); ++k, ++n_item) {
         const int ntiles = it.qi + 1;
         for (int s = 0; s < 2; ++s) {
-          mbar_wait(q_full(s), n_item & 1u);
+          mbar_wait(q_full(s, n_item & 1), (n_item >> 1) & 1u);
           issue_qk(s);
         }
         for (int n = 0; n < ntiles; ++n) {
@@ -196,7 +212,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             if (n + 1 < ntiles) {
               issue_qk(s);
             } else {
-              umma_commit(q_empty(s));
+              umma_commit(q_empty(s, n_item & 1));
               umma_commit(o_final(s));
             }
           }
@@ -204,101 +220,122 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
       }
     }
   } else if (warp >= 4) {
-    // ===== softmax: slot = head of the pair, thread = one query row (TMEM lane)
-    const int s = (warp - 4) >> 2, quad = warp & 3;
+    // ===== softmax: slot = head of the pair; thread = (query row, half of the tile's keys)
+    const int s = (warp - 4) >> 3, quad = warp & 3, ch = ((warp - 4) >> 2) & 1;
     const int row = quad * 32 + lane;
-    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + s * AT_SLOT_COLS;
-    const uint32_t t_p = t_s + AT_COL_P, t_o = t_s + AT_COL_O;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + s * AT_SLOT_COLS;
+    const uint32_t t_s = t_row + ch * 64, t_p = t_row + AT_COL_P + ch * 32, t_o = t_row + AT_COL_O + ch * 32;
+    float* xch = reinterpret_cast<float*>(smem_gen + AT_OFF_X) + s * 512;  // [parity][half][128]
+    auto slot_bar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); };
     constexpr float SC = 0.0625f * kLog2e;
-    uint32_t sc_cnt = 0, oc_cnt = 0;
+    uint32_t sc_cnt = 0, oc_cnt = 0, xpar = 0;
     Item it;
     for (int k = 0; next_item(p, k, &it); ++k) {
       const int head = it.hp * 2 + s;
       const float slope2 = p.slopes[head] * kLog2e;
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY, l = 0.f;  // l: this thread's partial row sum
       for (int n = 0; n <= it.qi; ++n) {
         const int k0 = (it.qi - n) * 128;
         const bool diag = n == 0;
-        const int nchunks = diag ? quad + 1 : 4;  // 32-key chunks with a visible key for this warp's rows
-        const float base = fmaf(slope2, (float)k0, kLog2e);
+        // this thread's two 32-key chunks are global chunks 2*ch and 2*ch+1; on the diagonal tile chunk g is
+        // visible to this warp's rows iff g <= quad, and chunk g == quad holds the diagonal itself
+        const int g0 = 2 * ch;
+        const int nvis = diag ? min(max(quad + 1 - g0, 0), 2) : 2;
+        const float base = fmaf(slope2, (float)(k0 + 64 * ch), kLog2e);
         mbar_wait(s_full(s), sc_cnt & 1u);
         ++sc_cnt;
         tc_fence_after();
-        // pass A: row maximum of the biased scores (log2 domain)
+        // pass A: upper bound of the row maximum (log2 domain): SC * max_j s_j + bias of the last visible key
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
+        for (int ci = 0; ci < nvis; ++ci) {
           uint32_t r[32];
-          tmem_ld32(t_s + c * 32, r);
+          tmem_ld32(t_s + ci * 32, r);
           tmem_ld_wait();
-          const float cb = fmaf(slope2, (float)(c * 32), base);
-          const bool edge = diag && c == quad;
+          if (diag && g0 + ci == quad) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb));
-            if (edge && i > lane) t = -INFINITY;
-            mx = fmaxf(mx, t);
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i <= lane ? __uint_as_float(r[i]) : -INFINITY);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
           }
         }
-        const float m_new = fmaxf(m, mx);
+        xch[xpar * 256 + ch * 128 + row] = mx;
+        slot_bar();
+        mx = fmaxf(mx, xch[xpar * 256 + (ch ^ 1) * 128 + row]);
+        xpar ^= 1;
+        const float b_last = fmaf(slope2, (float)(k0 + (diag ? row : 127)), kLog2e);
+        const float m_new = fmaxf(m, fmaf(mx, SC, b_last));
         if (n > 0 && __any_sync(0xffffffffu, m_new > m)) {
-          // rare: rescale the accumulator (PV of the previous tile has completed: s_full was committed after it)
+          // rare: rescale this thread's half of the accumulator row (PV of the previous tile has completed:
+          // s_full was committed after it)
           const float alpha = ex2_fast(m - m_new);
           l *= alpha;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_o + c * 32, r);
-            tmem_ld_wait();
+          uint32_t r[32];
+          tmem_ld32(t_o, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(t_o + c * 32, r);
-          }
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st32(t_o, r);
         }
         m = m_new;
-        // pass B: p = 2^(t - m), row sum, P -> TMEM as bf16 pairs (column c holds keys 2c, 2c+1)
+        // pass B: p = 2^(t - m), partial row sum, P -> TMEM as bf16 pairs (column c holds keys 2c, 2c+1)
         const float base_m = base - m;
+        float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int ci = 0; ci < 2; ++ci) {
           uint32_t pk[16];
-          if (c < nchunks) {
+          if (ci < nvis) {
             uint32_t r[32];
-            tmem_ld32(t_s + c * 32, r);
+            tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
-            const float cb = fmaf(slope2, (float)(c * 32), base_m);
-            const bool edge = diag && c == quad;
-            float ps = 0.f;
+            const float cb = fmaf(slope2, (float)(ci * 32), base_m);
+            if (diag && g0 + ci == quad) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb)));
-              float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
-              if (edge && i > lane) p0 = 0.f;
-              if (edge && i + 1 > lane) p1 = 0.f;
-              ps += p0 + p1;
-              pk[i >> 1] = pack_bf16(p0, p1);
+              for (int i = 0; i < 32; i += 2) {
+                float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb)));
+                float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
+                if (i > lane) p0 = 0.f;
+                if (i + 1 > lane) p1 = 0.f;
+                ps0 += p0;
+                ps1 += p1;
+                pk[i >> 1] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb)));
+                const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
+                ps0 += p0;
+                ps1 += p1;
+                pk[i >> 1] = pack_bf16(p0, p1);
+              }
             }
-            l += ps;
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = 0u;
           }
-          tmem_st16(t_p + c * 16, pk);
+          tmem_st16(t_p + ci * 16, pk);
         }
+        l += ps0 + ps1;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full(s));
       }
-      // epilogue: O / l -> bf16 -> out[(seq*T + q), head*64 .. +64)
+      // epilogue: O / l -> bf16 -> out[(seq*T + q), head*64 + 32*ch .. +32)
+      xch[xpar * 256 + ch * 128 + row] = l;
+      slot_bar();
+      l += xch[xpar * 256 + (ch ^ 1) * 128 + row];
+      xpar ^= 1;
       mbar_wait(o_final(s), oc_cnt & 1u);
       ++oc_cnt;
       tc_fence_after();
       const float inv = 1.0f / l;
       const int q = it.qi * 128 + row;
-      __nv_bfloat16* dst = p.out + ((long long)it.seq * p.T + q) * kDim + head * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      __nv_bfloat16* dst = p.out + ((long long)it.seq * p.T + q) * kDim + head * 64 + ch * 32;
+      {
         uint32_t r[32];
-        tmem_ld32(t_o + c * 32, r);
+        tmem_ld32(t_o, r);
         tmem_ld_wait();
         if (q < p.T) {
 #pragma unroll
@@ -308,7 +345,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             u.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
             u.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
             u.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = u;
+            *reinterpret_cast<uint4*>(dst + 8 * i) = u;
           }
         }
       }
