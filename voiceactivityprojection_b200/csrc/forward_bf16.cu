@@ -268,8 +268,12 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
         out = H(p.act4) + (long long)s0 * L4 * kDim;
         e.out1_map = RowMap{L4 * kDim, kDim};
       }
-      cx.gemm(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
-              kDim, c.k * kDim, e, nullptr, out, CAT_CONV_GEMM);
+      if (i >= m.conv_lin_from)
+        cx.lin(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
+               kDim, c.k * kDim, e, nullptr, out, 1, CAT_CONV_GEMM);
+      else
+        cx.gemm(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
+                kDim, c.k * kDim, e, nullptr, out, CAT_CONV_GEMM);
     }
   }
 

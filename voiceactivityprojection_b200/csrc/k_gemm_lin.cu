@@ -498,6 +498,7 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
       VAPB_LIN_VARIANT(F_O1B | F_ACT),                                // FFN in + GELU
       VAPB_LIN_VARIANT(F_RESID | F_F32B | F_N2),                      // attention out-projection
       VAPB_LIN_VARIANT(F_RESID | F_F32B | F_O1B | F_N2),              // FFN out
+      VAPB_LIN_VARIANT(F_PRE | F_ACT | F_O1B),                        // gEncoder convs (bias + ChannelNorm + ReLU)
       VAPB_LIN_VARIANT(F_PRE | F_F32R),                               // vap_head
       VAPB_LIN_VARIANT(F_PRE | F_ACT | F_ACC | F_F32B | F_O1B),       // combinator
       VAPB_LIN_VARIANT(F_PRE | F_ACT | F_F32B | F_O1B | F_N2),        // downsample conv
