@@ -133,6 +133,7 @@ int vapb_create(int device, VapbHandle** out) {
   VapbHandle* h = new VapbHandle();
   h->m.device = device;
   cudaDeviceGetAttribute(&h->m.n_sm, cudaDevAttrMultiProcessorCount, device);
+  if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
   *out = h;
   return VAPB_OK;

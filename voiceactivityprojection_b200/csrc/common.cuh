@@ -83,6 +83,11 @@ int launch_conv0_v2(cudaStream_t st, const float* wav, int batch, long long n_sa
                     long long L0, const float* u, const float* d, const float* beta, const Conv0Stats& cs,
                     __nv_bfloat16* out, long long out_seq_stride, int out_pad_rows);
 
+// conv0 on the tensor cores (k_conv0_tc.cu): tf32 GEMM with K = 16 over an im2col tile built in shared memory
+int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq,
+                    long long L0, const float* u, const float* d, const float* beta, const Conv0Stats& cs,
+                    __nv_bfloat16* out, long long out_seq_stride, int out_pad_rows, int n_sm, std::string* err);
+
 int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
 
 int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);  // -1 on error

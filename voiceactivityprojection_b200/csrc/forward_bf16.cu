@@ -249,8 +249,16 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     const int n = (nseq - s0 < p.mb) ? nseq - s0 : p.mb;
     {
       ProfScope ps(m, st, CAT_CONV0);
-      m.launches += launch_conv0_v2(st, wav, g.batch, g.S, s0, n, g.L[0], s.c0_u, s.c0_d, w.c0_be, s.c0_stats,
-                                    H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0]);
+      if (m.conv0_tc) {
+        std::string err;
+        const int k = launch_conv0_tc(st, wav, g.batch, g.S, s0, n, g.L[0], s.c0_u, s.c0_d, w.c0_be, s.c0_stats,
+                                      H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0], m.n_sm, &err);
+        if (k < 0) { m.err = err; return -3; }
+        m.launches += k;
+      } else {
+        m.launches += launch_conv0_v2(st, wav, g.batch, g.S, s0, n, g.L[0], s.c0_u, s.c0_d, w.c0_be, s.c0_stats,
+                                      H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0]);
+      }
     }
     for (int i = 1; i <= 4; ++i) {
       const Conv& c = kConv[i];
