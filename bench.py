@@ -306,9 +306,17 @@ def main():
             peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
             peak_src = "fp32 CUDA-core FMA peak 148 SM x 128 FMA x 2 x sm_max_mhz (fp32 mode does not use the tensor pipe)"
         ach = fl[dom] * B / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
+        # DRAM bytes of the dominant family per step, from the committed ncu capture of this same command
+        traffic, traffic_src = None, None
+        tf = os.path.join(ROOT, "profiles", "r1_traffic_bf16.json")
+        if precision == "bf16" and B == 256 and os.path.exists(tf):
+            tj = json.load(open(tf))
+            if dom in tj:
+                traffic, traffic_src = tj[dom]["dram_bytes_per_step"], "profiles/r1_traffic_bf16.json: " + tj["_source"]
         roofline = {
             "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak if peak else None, "traffic": None, "peak_source": peak_src,
+            "frac": ach / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "ms_per_step": dom_ms, "launches_per_step": dom_n, "share_of_step": dom_ms / step_ms if step_ms else None,
             "families_ms_per_step": {k: round(v[0], 3) for k, v in fams.items()},
             "whole_step": {"achieved": fl["total"] * total_chunks * args.steps / (ms / 1e3) / 1e12 / world,
