@@ -178,7 +178,8 @@ int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_strid
  * cross != 0: K/V of sequence (seq + nseq/2) % nseq (the other speaker channel). */
 int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const void* k, const void* v,
                        int64_t kv_row_stride, void* out, int nseq, int T, int n_heads, const float* slopes,
-                       int cross, char* err, int err_len);
+                       int cross, char* err, int err_len,
+                       long long* dbg_clocks /* device [64][8] SM-clock samples of CTA 0, or NULL */);
 
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);

@@ -177,7 +177,7 @@ def test_attention_tc_matches_torch(nseq, T, cross, packed, scale):
     err = C.create_string_buffer(512)
     st = torch.cuda.current_stream().cuda_stream
     rc = lib.vapb_debug_attn_tc(st, q.data_ptr(), qs, k.data_ptr(), v.data_ptr(), ks, out.data_ptr(), nseq, T, 4,
-                                slopes.data_ptr(), cross, err, 512)
+                                slopes.data_ptr(), cross, err, 512, None)
     assert rc == 0, err.value.decode()
     torch.cuda.synchronize()
     ref = _attn_ref(q, k, v, slopes, cross)

@@ -212,3 +212,31 @@ def test_bf16_within_stated_tolerance_of_reference_golden(name):
             assert _maxerr(out[k], g[k]) <= BF16_TOL[k], k
     agree = (fwd["logits"].argmax(-1).cpu() == g["logits"].argmax(-1)).float().mean().item()
     assert agree >= 0.95, agree
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_full_size_batch_is_item_independent(precision):
+    """BASELINE configs[1] at full size (B=256 x 20 s): chunks are independent, so every item of the big batch must
+    equal the same item run in a batch of 2 (bit-identical: no kernel mixes sequences, none is order-dependent)."""
+    from oracle import synth
+
+    sd = synth.make_state_dict(0, "LSTM", 1, 2.0)
+    m = _model(sd, precision)
+    B, S = 256, 320000
+    g = torch.Generator(device="cuda").manual_seed(99)
+    wav = torch.randn((B, 2, S), device="cuda", generator=g) * 0.05
+    gate = (torch.rand((B, 2, S // 16000), device="cuda", generator=g) > 0.5).float().repeat_interleave(16000, dim=-1)
+    wav = wav * (0.1 + gate)  # speech-like on/off segments so VAD / classes are not degenerate
+    big = m.probs(wav)
+    assert big["probs"].shape == (B, 1000, 256) and big["loss"].shape == (B, 900)
+    assert torch.isfinite(big["probs"]).all() and torch.isfinite(big["vad"]).all()
+    assert (big["probs"].sum(-1) - 1).abs().max().item() <= 1e-4
+    for i0 in (0, 130, 254):
+        small = m.probs(wav[i0:i0 + 2].contiguous())
+        for k in ["probs", "vad", "p_now", "p_future", "H", "loss"]:
+            a, b = big[k][i0:i0 + 2], small[k]
+            assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)), (precision, k, i0)
+    # channel symmetry: every layer up to the VAD head applies the same weights to both speakers (the combinator, which
+    # feeds only the VAP head, does not), so swapping the input channels swaps the VAD columns
+    sw = m.probs(wav[:2].flip(1).contiguous())
+    assert _maxerr(sw["vad"], big["vad"][:2].flip(-1).cpu()) <= (1e-5 if precision == "fp32" else 3e-2)

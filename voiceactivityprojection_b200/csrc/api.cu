@@ -656,14 +656,14 @@ int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_strid
 
 int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const void* k, const void* v,
                        int64_t kv_row_stride, void* out, int nseq, int T, int n_heads, const float* slopes,
-                       int cross, char* err, int err_len) {
+                       int cross, char* err, int err_len, long long* dbg_clocks) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   std::string msg;
   typedef const __nv_bfloat16* bp;
   int rc = launch_attention_tc((cudaStream_t)stream, (bp)q, q_row_stride, (bp)k, (bp)v, kv_row_stride,
-                               reinterpret_cast<__nv_bfloat16*>(out), nseq, T, n_heads, slopes, cross, n_sm, &msg);
+                               reinterpret_cast<__nv_bfloat16*>(out), nseq, T, n_heads, slopes, cross, n_sm, &msg, dbg_clocks);
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }

@@ -113,7 +113,8 @@ int launch_attention_simt_bf16(cudaStream_t st, const __nv_bfloat16* q, long lon
 // tcgen05 fused attention (k_attn_tc.cu): bf16 in/out, rows of 256 = n_heads*64. Returns launches or -1.
 int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row_stride, const __nv_bfloat16* k,
                         const __nv_bfloat16* v, long long kv_row_stride, __nv_bfloat16* out, int nseq, int T,
-                        int n_heads, const float* slopes, int cross, int n_sm, std::string* err);
+                        int n_heads, const float* slopes, int cross, int n_sm, std::string* err,
+                        long long* dbg = nullptr);
 int launch_rnn_f32_bf16out(cudaStream_t st, int kind, const float* xproj, const float* whh_t, const float* bhn,
                            __nv_bfloat16* out, long long out_seq_stride, int nseq, int T);
 

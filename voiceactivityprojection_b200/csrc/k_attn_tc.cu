@@ -49,6 +49,7 @@ struct alignas(64) AttnParams {
   __nv_bfloat16* out;      // (nseq*T, 256)
   const float* slopes;     // [n_heads]
   int nseq, T, nqt, head_pairs, n_items, cross;
+  long long* dbg;  // optional [64][8] SM-clock samples of CTA 0 (diagnostics, tools/attn_probe.py)
   int pair_major;  // large batches: a CTA walks all query tiles of one (sequence, head pair) back to back, so the
                    // pair's K/V (re-read once per query tile) stay in L2; small batches: spread single tiles
 };
@@ -198,7 +199,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         }
         for (int n = 0; n < ntiles; ++n) {
           for (int s = 0; s < 2; ++s) {
+            const bool dbg = p.dbg && blockIdx.x == 0 && s == 0 && pc[0] >= 40 && pc[0] < 104;
+            if (dbg) p.dbg[(pc[0] - 40) * 8 + 5] = clock64();
             mbar_wait(p_full(s), pc[s] & 1u);
+            if (dbg) p.dbg[(pc[0] - 40) * 8 + 6] = clock64();
             ++pc[s];
             tc_fence_after();
             const int st = kvc[s] & 1;
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                            make_smem_desc_sw128(va + kk * 2048, 1024, 1024), idesc_pv, (n | kk) != 0);
             umma_commit(kv_empty(s, st));
             ++kvc[s];
+            if (dbg) p.dbg[(pc[0] - 41) * 8 + 7] = clock64();
             if (n + 1 < ntiles) {
               issue_qk(s);
             } else {
@@ -242,7 +247,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         const int g0 = 2 * ch;
         const int nvis = diag ? min(max(quad + 1 - g0, 0), 2) : 2;
         const float base = fmaf(slope2, (float)(k0 + 64 * ch), kLog2e);
+        const bool dbg = p.dbg && blockIdx.x == 0 && s == 0 && ch == 0 && quad == 0 && lane == 0 && sc_cnt >= 40 && sc_cnt < 104;
+        const uint32_t di = (sc_cnt - 40) * 8;
+        if (dbg) p.dbg[di + 0] = clock64();
         mbar_wait(s_full(s), sc_cnt & 1u);
+        if (dbg) p.dbg[di + 1] = clock64();
         ++sc_cnt;
         tc_fence_after();
         // pass A: upper bound of the row maximum (log2 domain): SC * max_j s_j + bias of the last visible key
@@ -260,8 +269,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
           }
         }
+        if (dbg) p.dbg[di + 2] = clock64();
         xch[xpar * 256 + ch * 128 + row] = mx;
         slot_bar();
+        if (dbg) p.dbg[di + 3] = clock64();
         mx = fmaxf(mx, xch[xpar * 256 + (ch ^ 1) * 128 + row]);
         xpar ^= 1;
         const float b_last = fmaf(slope2, (float)(k0 + (diag ? row : 127)), kLog2e);
@@ -278,14 +289,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
           tmem_st32(t_o, r);
         }
+        // ALiBi makes far tiles of the steep heads irrelevant: if even the tile's upper bound is more than 40 binades
+        // below the running maximum for every row of the warp, every p would be < 2^-40 of the row's largest term
+        // (fp32 cannot see it in the row sum or in O), so the exponentials are skipped and P is written as zeros.
+        const bool negligible = n > 0 && __all_sync(0xffffffffu, fmaf(mx, SC, b_last) < m - 40.0f);
         m = m_new;
         // pass B: p = 2^(t - m), partial row sum, P -> TMEM as bf16 pairs (column c holds keys 2c, 2c+1)
         const float base_m = base - m;
         float ps0 = 0.f, ps1 = 0.f;
+        const int nexp = negligible ? 0 : nvis;
 #pragma unroll 1
         for (int ci = 0; ci < 2; ++ci) {
           uint32_t pk[16];
-          if (ci < nvis) {
+          if (ci < nexp) {
             uint32_t r[32];
             tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
@@ -321,6 +337,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full(s));
+        if (dbg) p.dbg[di + 4] = clock64();
       }
       // epilogue: O / l -> bf16 -> out[(seq*T + q), head*64 + 32*ch .. +32)
       xch[xpar * 256 + ch * 128 + row] = l;
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 // q/k/v: bf16 rows of 256 (= n_heads*64) at ptr + (seq*T + t)*row_stride; out: dense (nseq*T, 256) bf16.
 int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row_stride, const __nv_bfloat16* k,
                         const __nv_bfloat16* v, long long kv_row_stride, __nv_bfloat16* out, int nseq, int T,
-                        int n_heads, const float* slopes, int cross, int n_sm, std::string* err) {
+                        int n_heads, const float* slopes, int cross, int n_sm, std::string* err, long long* dbg) {
   if (n_heads % 2 || n_heads * 64 != kDim) {
     if (err) *err = "attention_tc: needs an even number of heads of 64";
     return -1;
@@ -390,6 +407,7 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
   p.head_pairs = n_heads / 2;
   p.n_items = p.nqt * nseq * p.head_pairs;
   p.cross = cross;
+  p.dbg = dbg;
   p.pair_major = nseq * p.head_pairs >= 2 * n_sm;
   static bool configured = false;
   if (!configured) {

@@ -73,80 +73,120 @@ int launch_vad_head(cudaStream_t st, const float* x, const float* w, const float
   return 1;
 }
 
-// One warp per frame; lane owns classes lane*4..+3 and 128+lane*4..+3.
+// One warp handles PR frames at a time (independent shuffle chains interleave); lane owns classes
+// lane*4..+3 and 128+lane*4..+3, whose codebook bit counts are fixed per lane and computed once.
+constexpr int PR = 4;
 __global__ void __launch_bounds__(256)
 probs_kernel(const float* __restrict__ logits, long long rows, int now_lo, int now_hi, int fut_lo, int fut_hi,
              float* __restrict__ probs, float* __restrict__ p_now, float* __restrict__ p_future,
              float* __restrict__ H, float* __restrict__ lse, uint8_t* __restrict__ argmax) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PR;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* lr = logits + row * kClasses;
-  const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
-  const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
-  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-  float mx = v[0];
-  int best = 0;
-#pragma unroll
-  for (int j = 1; j < 8; ++j)
-    if (v[j] > mx) { mx = v[j]; best = j; }
-  int bidx = (best < 4 ? 0 : 128) + lane * 4 + (best & 3);
-  // warp argmax, first index wins ties (torch.argmax semantics on CPU)
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, mx, off);
-    const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
-    if (om > mx || (om == mx && oi < bidx)) { mx = om; bidx = oi; }
-  }
-  float e[8], s = 0.f;
+  if (row0 >= rows) return;
+  float wn0[8], wn1[8], wf0[8], wf1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    e[j] = expf(v[j] - mx);
-    s += e[j];
-  }
-  s = warp_sum(s);
-  const float inv = 1.0f / s;
-  float h = 0.f, pn0 = 0.f, pn1 = 0.f, pf0 = 0.f, pf1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float p = e[j] * inv;
-    e[j] = p;
-    h -= p * log2f(p);  // NaN when p underflows to 0, like the reference (model.py:201)
     const int cls = (j < 4 ? 0 : 128) + lane * 4 + (j & 3);
     int n0 = 0, n1 = 0, f0 = 0, f1 = 0;
     for (int b = now_lo; b <= now_hi; ++b) { n0 += (cls >> b) & 1; n1 += (cls >> (4 + b)) & 1; }
     for (int b = fut_lo; b <= fut_hi; ++b) { f0 += (cls >> b) & 1; f1 += (cls >> (4 + b)) & 1; }
-    pn0 = fmaf(p, (float)n0, pn0); pn1 = fmaf(p, (float)n1, pn1);
-    pf0 = fmaf(p, (float)f0, pf0); pf1 = fmaf(p, (float)f1, pf1);
+    wn0[j] = (float)n0; wn1[j] = (float)n1; wf0[j] = (float)f0; wf1[j] = (float)f1;
   }
-  h = warp_sum(h);
-  pn0 = warp_sum(pn0); pn1 = warp_sum(pn1);
-  pf0 = warp_sum(pf0); pf1 = warp_sum(pf1);
-  if (probs) {
-    float* pr = probs + row * kClasses;
-    *reinterpret_cast<float4*>(pr + lane * 4) = make_float4(e[0], e[1], e[2], e[3]);
-    *reinterpret_cast<float4*>(pr + 128 + lane * 4) = make_float4(e[4], e[5], e[6], e[7]);
+  float v[PR][8], mx[PR];
+  int bidx[PR];
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;  // tail rows recompute the last row, never stored
+    const float* lr = logits + row * kClasses;
+    const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
+    v[r][0] = a0.x; v[r][1] = a0.y; v[r][2] = a0.z; v[r][3] = a0.w;
+    v[r][4] = a1.x; v[r][5] = a1.y; v[r][6] = a1.z; v[r][7] = a1.w;
   }
-  if (lane == 0) {
-    if (H) H[row] = h;
-    if (p_now) {
-      const float d = (pn0 + pn1) + 1e-5f;
-      p_now[row * 2] = pn0 / d;
-      p_now[row * 2 + 1] = pn1 / d;
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    mx[r] = v[r][0];
+    int best = 0;
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+      if (v[r][j] > mx[r]) { mx[r] = v[r][j]; best = j; }
+    bidx[r] = (best < 4 ? 0 : 128) + lane * 4 + (best & 3);
+  }
+  // warp argmax, first index wins ties (torch.argmax semantics on CPU)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx[r], off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx[r], off);
+      if (om > mx[r] || (om == mx[r] && oi < bidx[r])) { mx[r] = om; bidx[r] = oi; }
     }
-    if (p_future) {
-      const float d = (pf0 + pf1) + 1e-5f;
-      p_future[row * 2] = pf0 / d;
-      p_future[row * 2 + 1] = pf1 / d;
+  }
+  float s[PR];
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    s[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[r][j] = expf(v[r][j] - mx[r]);
+      s[r] += v[r][j];
     }
-    if (lse) lse[row] = mx + logf(s);
-    if (argmax) argmax[row] = (uint8_t)bidx;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < PR; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
+  float acc[PR][5];  // H, p_now 0/1, p_future 0/1 partial sums
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const float inv = 1.0f / s[r];
+    float h = 0.f, pn0 = 0.f, pn1 = 0.f, pf0 = 0.f, pf1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p = v[r][j] * inv;
+      v[r][j] = p;
+      h -= p * log2f(p);  // NaN when p underflows to 0, like the reference (model.py:201)
+      pn0 = fmaf(p, wn0[j], pn0); pn1 = fmaf(p, wn1[j], pn1);
+      pf0 = fmaf(p, wf0[j], pf0); pf1 = fmaf(p, wf1[j], pf1);
+    }
+    acc[r][0] = h; acc[r][1] = pn0; acc[r][2] = pn1; acc[r][3] = pf0; acc[r][4] = pf1;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < PR; ++r)
+#pragma unroll
+      for (int q = 0; q < 5; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], off);
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const long long row = row0 + r;
+    if (row >= rows) break;
+    if (probs) {
+      float* pr = probs + row * kClasses;
+      *reinterpret_cast<float4*>(pr + lane * 4) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+      *reinterpret_cast<float4*>(pr + 128 + lane * 4) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+    }
+    if (lane == 0) {
+      if (H) H[row] = acc[r][0];
+      if (p_now) {
+        const float d = (acc[r][1] + acc[r][2]) + 1e-5f;
+        p_now[row * 2] = acc[r][1] / d;
+        p_now[row * 2 + 1] = acc[r][2] / d;
+      }
+      if (p_future) {
+        const float d = (acc[r][3] + acc[r][4]) + 1e-5f;
+        p_future[row * 2] = acc[r][3] / d;
+        p_future[row * 2 + 1] = acc[r][4] / d;
+      }
+      if (lse) lse[row] = mx[r] + logf(s[r]);
+      if (argmax) argmax[row] = (uint8_t)bidx[r];
+    }
   }
 }
 
 int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
                  int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse, uint8_t* argmax) {
-  probs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs,
+  probs_kernel<<<(unsigned)((rows + 8 * PR - 1) / (8 * PR)), 256, 0, st>>>(logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs,
                                                            p_now, p_future, H, lse, argmax);
   return 1;
 }
