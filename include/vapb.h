@@ -158,6 +158,14 @@ int vapb_debug_gemm_lin(void* stream, const void* A, int64_t a_seq_stride, int64
                         int f32_mode, void* out1_bf16, int norm2, const float* g2, const float* b2, void* out2_bf16,
                         char* err, int err_len);
 
+/* Unit-test hook for the fused FFN block (csrc/k_ffn_fused.cu): x_out = resid + W2 GELU(W1 z).
+ * z: device bf16 (M,256); w1: bf16 [768][256]; w2: bf16 [256][768]; resid / x_out: row-blocked
+ * fp32 (see vapb_debug_gemm_lin); xs: bf16 (M,256) copy of x_out; zn: bf16 (M,256) =
+ * LayerNorm(x_out; g2, b2), or NULL. */
+int vapb_debug_ffn_fused(void* stream, const void* z, const void* w1, const void* w2, const float* resid_blocked,
+                          float* x_out_blocked, void* xs, void* zn, const float* g2, const float* b2, int M, char* err,
+                          int err_len);
+
 /* Unit-test hooks for the tensor-core gAR recurrence (csrc/k_rnn_tc.cu).
  * vapb_debug_rnn_pack (host only): nn.LSTM / nn.GRU parameters of one layer
  * (weight_ih (G*256,256), weight_hh, bias_ih, bias_hh; kind 0 = LSTM, 1 = GRU) ->

@@ -309,3 +309,37 @@ def test_gemm_lin_implicit_conv_multi_seq():
     assert (out1 - v).abs().max().item() <= 2e-2
     assert (out1b.float() - v).abs().max().item() <= 4e-2
     assert (out2.float() - _norm(v, 2, g2, b2)).abs().max().item() <= 8e-2
+
+
+@pytest.mark.parametrize("M,with_ln", [(128, True), (1000 + 77, True), (5000, False)])
+def test_ffn_fused_matches_torch(M, with_ln):
+    """x + W2 GELU(W1 z) with the hidden activation kept on chip, + bf16 shadow + next LayerNorm."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M)
+    z = torch.randn((M, 256), device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn((768, 256), device="cuda", generator=g) * 0.06).bfloat16()
+    w2 = (torch.randn((256, 768), device="cuda", generator=g) * 0.04).bfloat16()
+    resid = torch.randn((M, 256), device="cuda", generator=g)
+    g2 = torch.randn(256, device="cuda", generator=g)
+    b2 = torch.randn(256, device="cuda", generator=g)
+    rb = _to_blocked(resid)
+    xo = _to_blocked(torch.full((M, 256), float("nan"), device="cuda"))
+    xs = torch.zeros((M, 256), device="cuda", dtype=torch.bfloat16)
+    zn = torch.zeros((M, 256), device="cuda", dtype=torch.bfloat16) if with_ln else None
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_ffn_fused(st, z.data_ptr(), w1.data_ptr(), w2.data_ptr(), rb.data_ptr(), xo.data_ptr(),
+                                  xs.data_ptr(), zn.data_ptr() if with_ln else None, g2.data_ptr(), b2.data_ptr(), M,
+                                  err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    h = F.gelu(z.float() @ w1.float().T).bfloat16().float()  # the kernel rounds the hidden activation to bf16
+    ref = resid + h @ w2.float().T
+    out = _from_blocked(xo, M)
+    assert (out - ref).abs().max().item() <= 1e-2, (out - ref).abs().max().item()
+    assert (out - ref).abs().mean().item() <= 1e-3
+    assert (xs.float() - ref).abs().max().item() <= 3e-2
+    if with_ln:
+        assert (zn.float() - _norm(ref, 2, g2, b2)).abs().max().item() <= 6e-2

@@ -133,6 +133,7 @@ int vapb_create(int device, VapbHandle** out) {
   VapbHandle* h = new VapbHandle();
   h->m.device = device;
   cudaDeviceGetAttribute(&h->m.n_sm, cudaDevAttrMultiProcessorCount, device);
+  if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
   *out = h;
@@ -618,6 +619,28 @@ int vapb_debug_gemm_lin(void* stream, const void* A, int64_t a_seq_stride, int64
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   std::string msg;
   int rc = launch_gemm_lin((cudaStream_t)stream, a, f32_mode, n_sm, &msg);
+  if (rc >= 0) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+  }
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
+int vapb_debug_ffn_fused(void* stream, const void* z, const void* w1, const void* w2, const float* resid_blocked,
+                          float* x_out_blocked, void* xs, void* zn, const float* g2, const float* b2, int M, char* err,
+                          int err_len) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  std::string msg;
+  typedef const __nv_bfloat16* bp;
+  int rc = launch_ffn_fused((cudaStream_t)stream, (bp)z, (bp)w1, (bp)w2, resid_blocked, x_out_blocked,
+                            reinterpret_cast<__nv_bfloat16*>(xs), reinterpret_cast<__nv_bfloat16*>(zn), g2, b2, M, n_sm,
+                            &msg);
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }

@@ -96,6 +96,11 @@ int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* 
 // accumulate use the row-blocked fp32 layout [row/128][col/4][row%128][4]; 2 = out1_f32 row-major via TMA.
 int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm, std::string* err);
 
+// Fused FFN block (k_ffn_fused.cu): x_out = resid + W2 GELU(W1 z); xs = bf16(x_out); zn = LayerNorm(x_out) or null
+int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
+                     const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
+                     const float* b2, int M, int n_sm, std::string* err);
+
 int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
                      long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence
 

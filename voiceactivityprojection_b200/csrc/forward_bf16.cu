@@ -390,21 +390,34 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       e.out2_map = d256;
       cx.lin(H(p.y), d256, lh.wproj_c, 1, MT, kDim, kDim, e, F(p.xb), nullptr);
     }
-    {
-      Epilogue e{};
-      e.act = ACT_GELU;
-      e.out1_map = dense(MT, kFfn);
-      cx.lin(H(p.z), d256, lh.w1, 1, MT, kFfn, kDim, e, nullptr, H(p.h));
-    }
-    {
-      Epilogue e{};
-      e.resid = F(p.xb);
-      e.resid_map = d256;
-      e.out1_map = d256;
-      first_ln(li + 1, &e.g2, &e.b2);
-      if (e.g2) { e.norm2 = NORM_LAYER; e.out2 = H(p.z); e.out2_map = d256; }
-      // bf16 shadow of the new residual stream: next cross layer's K/V source, or the combinator input
-      cx.lin(H(p.h), dense(MT, kFfn), lh.w2, 1, MT, kDim, kFfn, e, F(p.stage[li + 1]), H(p.xs));
+    const float *gn = nullptr, *bn = nullptr;
+    first_ln(li + 1, &gn, &bn);
+    if (m.ffn_fused) {
+      // FFN in one kernel: the 768-wide hidden activation stays on the SM. zn overwrites z in place (a tile's z is in
+      // shared memory long before its rows are rewritten).
+      if (cx.rc) return cx.rc;
+      ProfScope ps(m, st, CAT_LINEAR_GEMM);
+      std::string err;
+      const int n = launch_ffn_fused(st, H(p.z), lh.w1, lh.w2, F(p.xb), F(p.stage[li + 1]), H(p.xs),
+                                     gn ? H(p.z) : nullptr, gn, bn, MT, m.n_sm, &err);
+      if (n < 0) { m.err = err; return -3; }
+      m.launches += n;
+    } else {
+      {
+        Epilogue e{};
+        e.act = ACT_GELU;
+        e.out1_map = dense(MT, kFfn);
+        cx.lin(H(p.z), d256, lh.w1, 1, MT, kFfn, kDim, e, nullptr, H(p.h));
+      }
+      {
+        Epilogue e{};
+        e.resid = F(p.xb);
+        e.resid_map = d256;
+        e.out1_map = d256;
+        if (gn) { e.norm2 = NORM_LAYER; e.g2 = gn; e.b2 = bn; e.out2 = H(p.z); e.out2_map = d256; }
+        // bf16 shadow of the new residual stream: next cross layer's K/V source, or the combinator input
+        cx.lin(H(p.h), dense(MT, kFfn), lh.w2, 1, MT, kDim, kFfn, e, F(p.stage[li + 1]), H(p.xs));
+      }
     }
   }
 

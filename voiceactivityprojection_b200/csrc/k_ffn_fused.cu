@@ -1,0 +1,394 @@
+// Fused feed-forward block of a transformer layer on tcgen05:
+//   x_out = x + W2 GELU(W1 z),  xs = bf16(x_out),  z_next = LayerNorm_next(x_out)
+// (vap/modules.py:9-21 ffn_block without biases, :274 residual; z = ln_ffnetwork(x) comes from the
+// attention out-projection's epilogue.) The 768-wide hidden activation never leaves the SM: the
+// unfused pair of GEMMs wrote and re-read it through HBM (1.57 GB per layer at B = 256), which was
+// half of their traffic.
+//
+// One persistent CTA per SM, 128 rows per tile:
+//   Z   (A operand of GEMM 1, 4 k-blocks x 16 KB, TMA)            resident for the tile
+//   for j in 0..2 (hidden columns 256 j .. 256 j + 255):
+//     ACC_H = Z W1[j]^T          16 x tcgen05.mma M128 N256 K16, W1 k-blocks streamed through a ring
+//     H     = bf16(GELU(ACC_H))  epilogue warps: TMEM -> registers -> shared memory in the SW128 K-major
+//                                operand layout (what TMA would have written)
+//     ACC_O += H W2[:, j]^T      16 x tcgen05.mma, W2 k-blocks through the same ring
+//   final epilogue on ACC_O: + residual (row-blocked fp32) -> x_out, bf16 shadow, LayerNorm -> z_next
+// TMEM: ACC_H and ACC_O, 256 columns each. The staging tiles of the final epilogue alias the H buffer.
+#include <string>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace vapb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int FK_BYTES = 128 * 64 * 2;   // one A k-block: 128 rows x 64 k, 16 KB
+constexpr int FW_BYTES = 256 * 64 * 2;   // one W k-block: 256 n x 64 k, 32 KB
+constexpr int FW_STAGES = 3;
+constexpr int F_OFF_Z = 0;
+constexpr int F_OFF_H = 4 * FK_BYTES;                 // also: staging [half][2] x 8 KB, then LN vectors / partials
+constexpr int F_OFF_W = F_OFF_H + 4 * FK_BYTES;
+constexpr int F_OFF_BAR = F_OFF_W + FW_STAGES * FW_BYTES;
+constexpr int F_SMEM = F_OFF_BAR + 256 + 1024 /*alignment slack*/;
+constexpr int F_H_STG = 0, F_H_VEC = 32768;           // offsets inside the H region used by the final epilogue
+constexpr int F_THREADS = 384;
+
+struct alignas(64) FfnParams {
+  CUtensorMap tma_z;    // (256, M) bf16, box (64, 128)
+  CUtensorMap tma_w1;   // (256 k, 768 n) bf16, box (64, 256)
+  CUtensorMap tma_w2;   // (768 k, 256 n) bf16, box (64, 256)
+  CUtensorMap tma_xs;   // (256, M) bf16 out, box (32, 128), SW64
+  CUtensorMap tma_zn;   // (256, M) bf16 out (LayerNorm of x_out), box (32, 128), SW64
+  int M, num_tiles;
+  const float* resid;   // row-blocked fp32
+  float* x_out;         // row-blocked fp32
+  int has_ln;
+  const float *g2, *b2;
+};
+
+struct FfnVecs {
+  float g2[256], b2[256];
+  float part[2][128][2];
+};
+
+__device__ __forceinline__ float2 gelu_poly2_f(float2 x) {  // same polynomial as k_gemm_lin.cu
+  const float2 a = make_float2(fminf(fabsf(x.x), 4.0f), fminf(fabsf(x.y), 4.0f));
+  float2 acc = make_float2(6.604950176551938e-4f, 6.604950176551938e-4f);
+  acc = __ffma2_rn(acc, a, make_float2(-1.0183836333453655e-2f, -1.0183836333453655e-2f));
+  acc = __ffma2_rn(acc, a, make_float2(5.9112582355737686e-2f, 5.9112582355737686e-2f));
+  acc = __ffma2_rn(acc, a, make_float2(-1.445402055978775e-1f, -1.445402055978775e-1f));
+  acc = __ffma2_rn(acc, a, make_float2(4.981609806418419e-2f, 4.981609806418419e-2f));
+  acc = __ffma2_rn(acc, a, make_float2(3.8568615913391113e-1f, 3.8568615913391113e-1f));
+  acc = __ffma2_rn(acc, a, make_float2(-4.9917131662368774e-1f, -4.9917131662368774e-1f));
+  acc = __ffma2_rn(acc, a, make_float2(1.4609939171350561e-5f, 1.4609939171350561e-5f));
+  return __fadd2_rn(acc, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+
+__device__ __forceinline__ long long blocked_off_f(long long m, int c) {
+  return (((m >> 7) * 64 + (c >> 2)) * 128 + (m & 127)) * 4 + (c & 3);
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_constant__ FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + F_OFF_BAR;
+  const uint32_t z_full = bar_base, z_empty = bar_base + 8;
+  auto w_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (6 + s); };
+  const uint32_t acch_full = bar_base + 8 * 10;  // GEMM 1 of a chunk has completed
+  const uint32_t h_full = bar_base + 8 * 11;     // epilogue wrote the H chunk (and no longer reads ACC_H); 256 arrivals
+  const uint32_t h_empty = bar_base + 8 * 12;    // GEMM 2 of a chunk has completed (H may be overwritten)
+  const uint32_t acco_full = bar_base + 8 * 13;  // GEMM 2 of the last chunk has completed
+  const uint32_t acco_empty = bar_base + 8 * 14; // final epilogue no longer reads ACC_O; 256 arrivals
+  const uint32_t tmem_slot = bar_base + 8 * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tma_z);
+    prefetch_tmap(&p.tma_w1);
+    prefetch_tmap(&p.tma_w2);
+    mbar_init(z_full, 1);
+    mbar_init(z_empty, 1);
+    for (int s = 0; s < FW_STAGES; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    mbar_init(acch_full, 1);
+    mbar_init(h_full, 256);
+    mbar_init(h_empty, 1);
+    mbar_init(acco_full, 1);
+    mbar_init(acco_empty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t t_acch = tmem_base, t_acco = tmem_base + 256;
+
+  if (warp == 0) {
+    // ===== TMA producer: Z of the tile, then W1[0], W2[0], W1[1], W2[1], W1[2], W2[2] k-blocks in MMA order
+    if (lane == 0) {
+      uint32_t wc = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(z_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(z_full, 4 * FK_BYTES);
+        for (int kb = 0; kb < 4; ++kb)
+          tma_load_2d(smem_base + F_OFF_Z + kb * FK_BYTES, &p.tma_z, z_full, kb * 64, tile * 128);
+        for (int j = 0; j < 3; ++j) {
+          for (int g = 0; g < 2; ++g) {
+            for (int kb = 0; kb < 4; ++kb, ++wc) {
+              const int s = wc % FW_STAGES;
+              mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(w_full(s), FW_BYTES);
+              if (g == 0)
+                tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w1, w_full(s), kb * 64, j * 256);
+              else
+                tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s), j * 256 + kb * 64, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
+      uint32_t wc = 0, it = 0, hf = 0 /*h_full phases seen*/, n_o = 0;
+      auto gemm = [&](uint32_t a_base, uint32_t d_tmem, bool first_zero) {
+        for (int kb = 0; kb < 4; ++kb, ++wc) {
+          const int s = wc % FW_STAGES;
+          mbar_wait(w_full(s), (wc / FW_STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + kb * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
+                      idesc, !(first_zero && kb == 0 && k == 0));
+          umma_commit(w_empty(s));
+        }
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(z_full, it & 1u);
+        tc_fence_after();
+        // ACC_H is free: the epilogue of the previous tile's last chunk has arrived on h_full (waited below)
+        gemm(smem_base + F_OFF_Z, t_acch, true);
+        umma_commit(acch_full);
+        for (int j = 0; j < 3; ++j) {
+          mbar_wait(h_full, hf & 1u);  // H chunk j is in shared memory and ACC_H has been read
+          ++hf;
+          tc_fence_after();
+          if (j == 0) {
+            mbar_wait(acco_empty, (n_o & 1u) ^ 1u);  // previous tile's final epilogue has read ACC_O
+            tc_fence_after();
+          }
+          gemm(smem_base + F_OFF_H, t_acco, j == 0);
+          umma_commit(h_empty);
+          if (j < 2) {
+            gemm(smem_base + F_OFF_Z, t_acch, true);
+            umma_commit(acch_full);
+            if (j == 1) umma_commit(z_empty);  // last read of Z for this tile
+          } else {
+            umma_commit(acco_full);
+            ++n_o;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = (accumulator row, column half)
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const bool leader = (threadIdx.x - 128 - half * 128) == 0;
+    const int cbase = half * 128;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    uint8_t* h_gen = smem_gen + F_OFF_H;
+    const uint32_t sw128 = (uint32_t)(row & 7), sw64 = (uint32_t)((row >> 1) & 3);
+    FfnVecs& ev = *reinterpret_cast<FfnVecs*>(h_gen + F_H_VEC);
+    const uint32_t stg_addr = smem_base + F_OFF_H + F_H_STG + half * 16384;
+    uint8_t* stg_gen = h_gen + F_H_STG + half * 16384;
+    uint32_t stg_cnt = 0, n_h = 0 /*acch_full phases*/, n_he = 0 /*h_empty phases*/, n_o = 0;
+    auto bar_half = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
+    auto bar_epi = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto stage_bf16 = [&](const CUtensorMap* map, const float (&v)[32], int c0, int c1) {
+      if (leader) bulk_wait_read<1>();
+      bar_half();
+      const uint32_t boff = (stg_cnt & 1u) * 8192u;
+      uint8_t* rowp = stg_gen + boff + (uint32_t)row * 64u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
+      }
+      fence_proxy_async();
+      bar_half();
+      if (leader) {
+        tma_store_2d(map, stg_addr + boff, c0, c1);
+        bulk_commit();
+      }
+      ++stg_cnt;
+    };
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long m = (long long)tile * 128 + row;
+      const bool valid = m < p.M;
+      // ---- three hidden chunks: ACC_H -> GELU -> H (bf16, SW128 K-major k-blocks of 64)
+      for (int j = 0; j < 3; ++j) {
+        mbar_wait(acch_full, n_h & 1u);
+        ++n_h;
+        // H is free: GEMM 2 of the previous chunk has completed (first chunk ever: nothing to wait for) ...
+        mbar_wait(h_empty, (n_he & 1u) ^ 1u);
+        ++n_he;
+        // ... and, for the first chunk of a tile, the TMA stores of the previous final epilogue have drained it
+        if (j == 0) {
+          if (leader) bulk_wait_read<0>();
+          bar_epi();
+        }
+        tc_fence_after();
+        const uint32_t taddr = t_acch + lane_off + cbase;
+        uint32_t r[2][32];
+        tmem_ld32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+          // columns cbase + 32c .. +31 of the chunk = k-block (cbase + 32c) / 64, 16-byte chunks 4*(c&1) .. +3 of the row
+          uint8_t* rowp = h_gen + ((cbase + c * 32) >> 6) * FK_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 y[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              y[e] = gelu_poly2_f(make_float2(__uint_as_float(r[c & 1][8 * q + 2 * e]), __uint_as_float(r[c & 1][8 * q + 2 * e + 1])));
+            uint4 u;
+            u.x = pack_bf16(y[0].x, y[0].y);
+            u.y = pack_bf16(y[1].x, y[1].y);
+            u.z = pack_bf16(y[2].x, y[2].y);
+            u.w = pack_bf16(y[3].x, y[3].y);
+            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)((c & 1) * 4 + q)) ^ sw128) << 4)) = u;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(h_full);
+      }
+      // ---- final epilogue on ACC_O
+      mbar_wait(acco_full, n_o & 1u);
+      ++n_o;
+      tc_fence_after();
+      // GEMM 2 of the last chunk is complete, so the H region is free: LayerNorm vectors and staging live there
+      if (p.has_ln) {
+        const int e = threadIdx.x - 128;
+        ev.g2[e] = p.g2[e];
+        ev.b2[e] = p.b2[e];
+      }
+      bar_epi();
+      const uint32_t taddr = t_acco + lane_off + cbase;
+      float s2 = 0.f, ss2 = 0.f;
+      {
+        uint32_t r[2][32];
+        tmem_ld32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[c & 1][i]);
+          if (valid) {
+            const float* rp = p.resid + blocked_off_f(m, cbase + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = *reinterpret_cast<const float4*>(rp + i * 512);
+              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+            }
+            float* op = p.x_out + blocked_off_f(m, cbase + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(op + i * 512) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          stage_bf16(&p.tma_xs, v, cbase + c * 32, tile * 128);
+          if (p.has_ln) {
+            uint32_t w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              s2 += v[i];
+              ss2 = fmaf(v[i], v[i], ss2);
+              w[i] = __float_as_uint(v[i]);
+            }
+            tmem_st32(taddr + c * 32, w);  // keep v for the LayerNorm pass
+          }
+        }
+      }
+      if (p.has_ln) {
+        tmem_st_wait();
+        ev.part[half][row][0] = s2;
+        ev.part[half][row][1] = ss2;
+        bar_epi();
+        s2 += ev.part[half ^ 1][row][0];
+        ss2 += ev.part[half ^ 1][row][1];
+        const float mean2 = s2 * (1.0f / kDim);
+        const float var2 = fmaxf(ss2 - s2 * mean2, 0.f) * (1.0f / kDim);
+        const float rstd2 = rsqrtf(var2 + kEps);
+        uint32_t r[2][32];
+        tmem_ld32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(&ev.g2[cbase + c * 32 + i]);
+            const float4 b = *reinterpret_cast<const float4*>(&ev.b2[cbase + c * 32 + i]);
+            v[i] = fmaf((__uint_as_float(r[c & 1][i]) - mean2) * rstd2, g.x, b.x);
+            v[i + 1] = fmaf((__uint_as_float(r[c & 1][i + 1]) - mean2) * rstd2, g.y, b.y);
+            v[i + 2] = fmaf((__uint_as_float(r[c & 1][i + 2]) - mean2) * rstd2, g.z, b.z);
+            v[i + 3] = fmaf((__uint_as_float(r[c & 1][i + 3]) - mean2) * rstd2, g.w, b.w);
+          }
+          stage_bf16(&p.tma_zn, v, cbase + c * 32, tile * 128);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acco_empty);
+    }
+    if (leader) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// z: bf16 (M, 256) dense; w1: bf16 [768][256]; w2: bf16 [256][768]; resid / x_out: row-blocked fp32 (M padded to 128);
+// xs: bf16 (M, 256) = x_out; zn: bf16 (M, 256) = LayerNorm(x_out; g2, b2) or null.
+int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
+                     const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
+                     const float* b2, int M, int n_sm, std::string* err) {
+  FfnParams p{};
+  auto map2 = [&](CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t b0, uint32_t b1, int sw) {
+    const uint64_t dims[2] = {inner, outer};
+    const uint64_t strides[1] = {inner};
+    const uint32_t box[2] = {b0, b1};
+    return make_tmap(m, base, 2, 2, dims, strides, box, sw, err);
+  };
+  if (!map2(&p.tma_z, z, 256, (uint64_t)M, 64, 128, 128)) return -1;
+  if (!map2(&p.tma_w1, w1, 256, 768, 64, 256, 128)) return -1;
+  if (!map2(&p.tma_w2, w2, 768, 256, 64, 256, 128)) return -1;
+  if (!map2(&p.tma_xs, xs, 256, (uint64_t)M, 32, 128, 64)) return -1;
+  if (zn && !map2(&p.tma_zn, zn, 256, (uint64_t)M, 32, 128, 64)) return -1;
+  p.M = M;
+  p.num_tiles = (M + 127) / 128;
+  p.resid = resid;
+  p.x_out = x_out;
+  p.has_ln = zn != nullptr;
+  p.g2 = g2;
+  p.b2 = b2;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
+      if (err) *err = "ffn_fused: cannot reserve shared memory";
+      return -1;
+    }
+    configured = true;
+  }
+  const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
+  ffn_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(p);
+  return 1;
+}
+
+}  // namespace vapb
