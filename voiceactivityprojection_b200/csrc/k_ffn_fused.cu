@@ -7,13 +7,14 @@
 //
 // One persistent CTA per SM, 128 rows per tile:
 //   Z   (A operand of GEMM 1, 4 k-blocks x 16 KB, TMA)            resident for the tile
-//   for j in 0..2 (hidden columns 256 j .. 256 j + 255):
-//     ACC_H = Z W1[j]^T          16 x tcgen05.mma M128 N256 K16, W1 k-blocks streamed through a ring
-//     H     = bf16(GELU(ACC_H))  epilogue warps: TMEM -> registers -> shared memory in the SW128 K-major
-//                                operand layout (what TMA would have written)
-//     ACC_O += H W2[:, j]^T      16 x tcgen05.mma, W2 k-blocks through the same ring
+//   for j in 0..5 (hidden columns 128 j .. 128 j + 127), software-pipelined two chunks deep:
+//     ACC_H[j&1] = Z W1[j]^T          16 x tcgen05.mma M128 N128 K16, W1 k-blocks streamed through a ring
+//     H[j&1]     = bf16(GELU(ACC_H))  epilogue warps: TMEM -> registers -> shared memory in the SW128 K-major
+//                                     operand layout (what TMA would have written); runs while the tensor pipe
+//                                     computes ACC_H of the next chunk
+//     ACC_O     += H W2[:, j]^T       8 x tcgen05.mma M128 N256 K16, W2 k-blocks through the same ring
 //   final epilogue on ACC_O: + residual (row-blocked fp32) -> x_out, bf16 shadow, LayerNorm -> z_next
-// TMEM: ACC_H and ACC_O, 256 columns each. The staging tiles of the final epilogue alias the H buffer.
+// TMEM: ACC_H 2 x 128 columns, ACC_O 256 columns. The staging tiles of the final epilogue alias the H buffers.
 #include <string>
 
 #include "common.cuh"
@@ -38,7 +39,7 @@ constexpr int F_THREADS = 384;
 
 struct alignas(64) FfnParams {
   CUtensorMap tma_z;    // (256, M) bf16, box (64, 128)
-  CUtensorMap tma_w1;   // (256 k, 768 n) bf16, box (64, 256)
+  CUtensorMap tma_w1;   // (256 k, 768 n) bf16, box (64, 128)
   CUtensorMap tma_w2;   // (768 k, 256 n) bf16, box (64, 256)
   CUtensorMap tma_xs;   // (256, M) bf16 out, box (32, 128), SW64
   CUtensorMap tma_zn;   // (256, M) bf16 out (LayerNorm of x_out), box (32, 128), SW64
@@ -79,12 +80,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   const uint32_t z_full = bar_base, z_empty = bar_base + 8;
   auto w_full = [&](int s) { return bar_base + 8u * (2 + s); };
   auto w_empty = [&](int s) { return bar_base + 8u * (6 + s); };
-  const uint32_t acch_full = bar_base + 8 * 10;  // GEMM 1 of a chunk has completed
-  const uint32_t h_full = bar_base + 8 * 11;     // epilogue wrote the H chunk (and no longer reads ACC_H); 256 arrivals
-  const uint32_t h_empty = bar_base + 8 * 12;    // GEMM 2 of a chunk has completed (H may be overwritten)
-  const uint32_t acco_full = bar_base + 8 * 13;  // GEMM 2 of the last chunk has completed
-  const uint32_t acco_empty = bar_base + 8 * 14; // final epilogue no longer reads ACC_O; 256 arrivals
-  const uint32_t tmem_slot = bar_base + 8 * 16;
+  auto acch_full = [&](int b) { return bar_base + 8u * (10 + b); };  // GEMM 1 of a chunk has completed
+  auto h_full = [&](int b) { return bar_base + 8u * (12 + b); };     // epilogue wrote H[b] (and no longer reads ACC_H[b]); 256
+  auto h_empty = [&](int b) { return bar_base + 8u * (14 + b); };    // GEMM 2 of a chunk has completed (H[b] may be overwritten)
+  const uint32_t acco_full = bar_base + 8 * 16;  // GEMM 2 of the last chunk has completed
+  const uint32_t acco_empty = bar_base + 8 * 17; // final epilogue no longer reads ACC_O; 256 arrivals
+  const uint32_t tmem_slot = bar_base + 8 * 18;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -97,9 +98,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
       mbar_init(w_full(s), 1);
       mbar_init(w_empty(s), 1);
     }
-    mbar_init(acch_full, 1);
-    mbar_init(h_full, 256);
-    mbar_init(h_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acch_full(b), 1);
+      mbar_init(h_full(b), 256);
+      mbar_init(h_empty(b), 1);
+    }
     mbar_init(acco_full, 1);
     mbar_init(acco_empty, 256);
     fence_barrier_init();
@@ -110,71 +113,96 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t t_acch = tmem_base, t_acco = tmem_base + 256;
+  const uint32_t t_acch = tmem_base /* 2 x 128 columns */, t_acco = tmem_base + 256;
 
   if (warp == 0) {
-    // ===== TMA producer: Z of the tile, then W1[0], W2[0], W1[1], W2[1], W1[2], W2[2] k-blocks in MMA order
+    // ===== TMA producer: Z of the tile, then the W k-blocks in the order the MMA thread consumes them:
+    // W1[0], W1[1], then for j = 0..5: W2[j], W1[j+2] (ring slots are 32 KB; a W1 k-block uses half of one)
     if (lane == 0) {
       uint32_t wc = 0, it = 0;
+      auto load_w1 = [&](int j) {
+        for (int kb = 0; kb < 4; ++kb, ++wc) {
+          const int s = wc % FW_STAGES;
+          mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(w_full(s), FW_BYTES / 2);
+          tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w1, w_full(s), kb * 64, j * 128);
+        }
+      };
+      auto load_w2 = [&](int j) {
+        for (int kb = 0; kb < 2; ++kb, ++wc) {
+          const int s = wc % FW_STAGES;
+          mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(w_full(s), FW_BYTES);
+          tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s), j * 128 + kb * 64, 0);
+        }
+      };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(z_empty, (it & 1u) ^ 1u);
         mbar_arrive_expect_tx(z_full, 4 * FK_BYTES);
         for (int kb = 0; kb < 4; ++kb)
           tma_load_2d(smem_base + F_OFF_Z + kb * FK_BYTES, &p.tma_z, z_full, kb * 64, tile * 128);
-        for (int j = 0; j < 3; ++j) {
-          for (int g = 0; g < 2; ++g) {
-            for (int kb = 0; kb < 4; ++kb, ++wc) {
-              const int s = wc % FW_STAGES;
-              mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(w_full(s), FW_BYTES);
-              if (g == 0)
-                tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w1, w_full(s), kb * 64, j * 256);
-              else
-                tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s), j * 256 + kb * 64, 0);
-            }
-          }
+        load_w1(0);
+        load_w1(1);
+        for (int j = 0; j < 6; ++j) {
+          load_w2(j);
+          if (j + 2 < 6) load_w1(j + 2);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
-      uint32_t wc = 0, it = 0, hf = 0 /*h_full phases seen*/, n_o = 0;
-      auto gemm = [&](uint32_t a_base, uint32_t d_tmem, bool first_zero) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0), idesc2 = make_idesc_bf16(128, 256, 0, 0);
+      uint32_t wc = 0, it = 0, hcnt[2] = {0, 0} /*h_full phases seen per buffer*/, n_o = 0;
+      auto gemm1 = [&](int b) {  // ACC_H[b] = Z W1[chunk]^T
         for (int kb = 0; kb < 4; ++kb, ++wc) {
           const int s = wc % FW_STAGES;
           mbar_wait(w_full(s), (wc / FW_STAGES) & 1u);
           tc_fence_after();
-          const uint32_t a_addr = a_base + kb * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
+          const uint32_t a_addr = smem_base + F_OFF_Z + kb * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
-                      idesc, !(first_zero && kb == 0 && k == 0));
+            umma_bf16(t_acch + b * 128, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                      make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc1, (kb | k) != 0);
           umma_commit(w_empty(s));
         }
+        umma_commit(acch_full(b));
+      };
+      auto gemm2 = [&](int b, bool first) {  // ACC_O (+)= H[b] W2[:, chunk]^T
+        for (int kb = 0; kb < 2; ++kb, ++wc) {
+          const int s = wc % FW_STAGES;
+          mbar_wait(w_full(s), (wc / FW_STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + F_OFF_H + (b * 2 + kb) * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(t_acco, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
+                      idesc2, !(first && kb == 0 && k == 0));
+          umma_commit(w_empty(s));
+        }
+        umma_commit(h_empty(b));
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(z_full, it & 1u);
         tc_fence_after();
-        // ACC_H is free: the epilogue of the previous tile's last chunk has arrived on h_full (waited below)
-        gemm(smem_base + F_OFF_Z, t_acch, true);
-        umma_commit(acch_full);
-        for (int j = 0; j < 3; ++j) {
-          mbar_wait(h_full, hf & 1u);  // H chunk j is in shared memory and ACC_H has been read
-          ++hf;
+        // both ACC_H buffers are free: the epilogue of the previous tile's last two chunks arrived on h_full (waited)
+        gemm1(0);
+        gemm1(1);
+        for (int j = 0; j < 6; ++j) {
+          const int b = j & 1;
+          mbar_wait(h_full(b), hcnt[b] & 1u);  // H[b] is in shared memory and ACC_H[b] has been read
+          ++hcnt[b];
           tc_fence_after();
           if (j == 0) {
             mbar_wait(acco_empty, (n_o & 1u) ^ 1u);  // previous tile's final epilogue has read ACC_O
             tc_fence_after();
           }
-          gemm(smem_base + F_OFF_H, t_acco, j == 0);
-          umma_commit(h_empty);
-          if (j < 2) {
-            gemm(smem_base + F_OFF_Z, t_acch, true);
-            umma_commit(acch_full);
-            if (j == 1) umma_commit(z_empty);  // last read of Z for this tile
-          } else {
+          gemm2(b, j == 0);
+          if (j + 2 < 6) {
+            gemm1(b);
+            if (j + 2 == 5) umma_commit(z_empty);  // last read of Z for this tile
+          }
+          if (j == 5) {
             umma_commit(acco_full);
             ++n_o;
           }
@@ -193,7 +221,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
     FfnVecs& ev = *reinterpret_cast<FfnVecs*>(h_gen + F_H_VEC);
     const uint32_t stg_addr = smem_base + F_OFF_H + F_H_STG + half * 16384;
     uint8_t* stg_gen = h_gen + F_H_STG + half * 16384;
-    uint32_t stg_cnt = 0, n_h = 0 /*acch_full phases*/, n_he = 0 /*h_empty phases*/, n_o = 0;
+    uint32_t stg_cnt = 0, hcnt[2] = {0, 0} /*chunks done per ACC_H / H buffer*/, n_o = 0;
     auto bar_half = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
     auto bar_epi = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     auto stage_bf16 = [&](const CUtensorMap* map, const float (&v)[32], int c0, int c1) {
@@ -222,45 +250,51 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long m = (long long)tile * 128 + row;
       const bool valid = m < p.M;
-      // ---- three hidden chunks: ACC_H -> GELU -> H (bf16, SW128 K-major k-blocks of 64)
-      for (int j = 0; j < 3; ++j) {
-        mbar_wait(acch_full, n_h & 1u);
-        ++n_h;
-        // H is free: GEMM 2 of the previous chunk has completed (first chunk ever: nothing to wait for) ...
-        mbar_wait(h_empty, (n_he & 1u) ^ 1u);
-        ++n_he;
-        // ... and, for the first chunk of a tile, the TMA stores of the previous final epilogue have drained it
+      // pull this tile's residual rows into L2 now: the final epilogue reads them ~10 us later and used to stall on
+      // DRAM latency once per 32-column chunk (ncu: the residual adds were the top long-scoreboard stall)
+      if (valid && (lane & 7) == 0) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + blocked_off_f(m, cbase + c * 4)));
+      }
+      // ---- six hidden chunks of 128: ACC_H[b] -> GELU -> H[b] (bf16, SW128 K-major; this half writes k-block `half`)
+      for (int j = 0; j < 6; ++j) {
+        const int b = j & 1;
+        mbar_wait(acch_full(b), hcnt[b] & 1u);
+        // H[b] is free: GEMM 2 of the chunk that used it two chunks ago has completed (first uses: nothing to wait for) ...
+        mbar_wait(h_empty(b), (hcnt[b] & 1u) ^ 1u);
+        ++hcnt[b];
+        // ... and, for the first chunk of a tile, the TMA stores of the previous final epilogue have drained the region
         if (j == 0) {
           if (leader) bulk_wait_read<0>();
           bar_epi();
         }
         tc_fence_after();
-        const uint32_t taddr = t_acch + lane_off + cbase;
+        const uint32_t taddr = t_acch + lane_off + b * 128 + half * 64;
+        uint8_t* rowp = h_gen + (b * 2 + half) * FK_BYTES + (uint32_t)row * 128u;
         uint32_t r[2][32];
         tmem_ld32(taddr, r[0]);
+        tmem_ld32(taddr + 32, r[1]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-          // columns cbase + 32c .. +31 of the chunk = k-block (cbase + 32c) / 64, 16-byte chunks 4*(c&1) .. +3 of the row
-          uint8_t* rowp = h_gen + ((cbase + c * 32) >> 6) * FK_BYTES + (uint32_t)row * 128u;
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float2 y[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              y[e] = gelu_poly2_f(make_float2(__uint_as_float(r[c & 1][8 * q + 2 * e]), __uint_as_float(r[c & 1][8 * q + 2 * e + 1])));
+              y[e] = gelu_poly2_f(make_float2(__uint_as_float(r[c][8 * q + 2 * e]), __uint_as_float(r[c][8 * q + 2 * e + 1])));
             uint4 u;
             u.x = pack_bf16(y[0].x, y[0].y);
             u.y = pack_bf16(y[1].x, y[1].y);
             u.z = pack_bf16(y[2].x, y[2].y);
             u.w = pack_bf16(y[3].x, y[3].y);
-            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)((c & 1) * 4 + q)) ^ sw128) << 4)) = u;
+            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(c * 4 + q)) ^ sw128) << 4)) = u;
           }
         }
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(h_full);
+        mbar_arrive(h_full(b));
       }
       // ---- final epilogue on ACC_O
       mbar_wait(acco_full, n_o & 1u);
@@ -367,7 +401,7 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
     return make_tmap(m, base, 2, 2, dims, strides, box, sw, err);
   };
   if (!map2(&p.tma_z, z, 256, (uint64_t)M, 64, 128, 128)) return -1;
-  if (!map2(&p.tma_w1, w1, 256, 768, 64, 256, 128)) return -1;
+  if (!map2(&p.tma_w1, w1, 256, 768, 64, 128, 128)) return -1;
   if (!map2(&p.tma_w2, w2, 768, 256, 64, 256, 128)) return -1;
   if (!map2(&p.tma_xs, xs, 256, (uint64_t)M, 32, 128, 64)) return -1;
   if (zn && !map2(&p.tma_zn, zn, 256, (uint64_t)M, 32, 128, 64)) return -1;

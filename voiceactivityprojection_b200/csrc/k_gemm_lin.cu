@@ -296,6 +296,11 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
       const bool valid = t < p.rows_per_seq;
       const long long m = (long long)seq * p.rows_per_seq + t;  // dense row (blocked fp32 buffers)
       const int n0 = nt * LBN + cbase;                            // first global column of this thread
+      if (C_RESID && p.resid && valid && (lane & 7) == 0) {
+        // pull the residual rows of this tile into L2 while its MMAs run (the adds below stalled on DRAM latency)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + blocked_off(m, n0 + c * 4)));
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * LBN + cbase;
