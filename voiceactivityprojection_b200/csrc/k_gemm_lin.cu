@@ -31,7 +31,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int LBM = 128, LBN = 256, LBK = 64, LSTAGES = 3;
+constexpr int LBM = 128, LBN = 256, LBK = 64;
 constexpr int LA_BYTES = LBM * LBK * 2, LB_BYTES = LBN * LBK * 2;
 constexpr int LSTAGE_BYTES = LA_BYTES + LB_BYTES;   // 48 KB
 constexpr int LSTG_HALF = 128 * 128;                // staging per column half: 2 x (128 rows x 64 B) bf16 tiles (SW64),
@@ -40,11 +40,15 @@ constexpr int L_THREADS = 384, L_EPI_THREADS = 256;
 // shared-memory plan: [operand region][staging 2 x 16 KB][barriers 256 B][LinVecs]
 //   streaming:        3 stages x (A 16 KB + W 32 KB)
 //   weight-resident:  W 4 x 32 KB, then 3 stages x A 16 KB
-template <bool WRES>
+//   NST = 4 (the K >= 1024 convolutions: the tensor pipe idled 29 % of the time waiting for operands with 3 stages
+//   in flight, ncu) pays for the fourth stage with single-buffered bf16 staging (8 KB per half instead of 16)
+template <bool WRES, int NST>
 struct LinSmem {
-  static constexpr int OPERANDS = WRES ? 4 * LB_BYTES + LSTAGES * LA_BYTES : LSTAGES * LSTAGE_BYTES;
+  static constexpr int NSTG = NST == 4 ? 1 : 2;  // bf16 staging buffers per column half
+  static constexpr int OPERANDS = WRES ? 4 * LB_BYTES + NST * LA_BYTES : NST * LSTAGE_BYTES;
   static constexpr int OFF_STG = OPERANDS;
-  static constexpr int OFF_BAR = OFF_STG + 2 * LSTG_HALF;
+  static constexpr int STG_HALF = NSTG == 2 ? LSTG_HALF : LSTG_HALF / 2;
+  static constexpr int OFF_BAR = OFF_STG + 2 * STG_HALF;
   static constexpr int OFF_VEC = OFF_BAR + 256;
 };
 
@@ -52,8 +56,8 @@ struct LinVecs {
   float bias[256], g1[256], b1[256], g2[256], b2[256];
   float part[2][128][2];
 };
-template <bool WRES>
-constexpr int lin_smem_bytes() { return LinSmem<WRES>::OFF_VEC + (int)sizeof(LinVecs) + 1024 /*alignment slack*/; }
+template <bool WRES, int NST>
+constexpr int lin_smem_bytes() { return LinSmem<WRES, NST>::OFF_VEC + (int)sizeof(LinVecs) + 1024 /*alignment slack*/; }
 
 struct alignas(64) LinParams {
   CUtensorMap tma_a, tma_b;
@@ -124,11 +128,13 @@ enum : int {
   F_ALL = 255
 };
 
-template <bool WRES, int F>
+template <bool WRES, int F, int NST>
 __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_constant__ LinParams p) {
+  constexpr int LSTAGES = NST, NSTG = LinSmem<WRES, NST>::NSTG, STG_HALF = LinSmem<WRES, NST>::STG_HALF;
   constexpr bool C_PRE = F & F_PRE, C_ACT = F & F_ACT, C_RESID = F & F_RESID, C_ACC = F & F_ACC, C_F32B = F & F_F32B,
                  C_F32R = F & F_F32R, C_O1B = F & F_O1B, C_N2 = F & F_N2;
-  constexpr int L_OFF_STG = LinSmem<WRES>::OFF_STG, L_OFF_BAR = LinSmem<WRES>::OFF_BAR, L_OFF_VEC = LinSmem<WRES>::OFF_VEC;
+  constexpr int L_OFF_STG = LinSmem<WRES, NST>::OFF_STG, L_OFF_BAR = LinSmem<WRES, NST>::OFF_BAR,
+                L_OFF_VEC = LinSmem<WRES, NST>::OFF_VEC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -241,17 +247,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
     const int row_in_tile = quad * 32 + lane;
     const bool leader = (threadIdx.x - 128 - half * 128) == 0;  // issues this half's TMA stores
     const int cbase = half * 128;
-    const uint32_t stg_addr = smem_base + L_OFF_STG + half * LSTG_HALF;
-    uint8_t* stg_gen = smem_gen + L_OFF_STG + half * LSTG_HALF;
+    const uint32_t stg_addr = smem_base + L_OFF_STG + half * STG_HALF;
+    uint8_t* stg_gen = smem_gen + L_OFF_STG + half * STG_HALF;
     const uint32_t sw128 = (uint32_t)(row_in_tile & 7), sw64 = (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t stg_cnt = 0;
     // bf16 staging: 32 columns of the tile = 128 rows x 64 B (SWIZZLE_64B: chunk j of row r at r*64 + ((j ^ (r/2 & 3)) << 4),
     // conflict-free for 8 consecutive rows), two buffers. All 128 threads of the half write their row, then the
     // leader hands the tile to TMA; a buffer is reused once the store that read it two tiles ago has drained.
     auto stage_bf16 = [&](const CUtensorMap* map, const float (&v)[32], int c0, int c1, int c2) {
-      if (leader) bulk_wait_read<1>();
+      if (leader) bulk_wait_read<NSTG - 1>();
       bar_half(half);
-      const uint32_t boff = (stg_cnt & 1u) * 8192u;
+      const uint32_t boff = NSTG == 2 ? (stg_cnt & 1u) * 8192u : 0u;
       uint8_t* rowp = stg_gen + boff + (uint32_t)row_in_tile * 64u;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -517,27 +523,29 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
                    (e.resid ? F_RESID : 0) | (e.accumulate ? F_ACC : 0) | (p.f32_mode == 1 ? F_F32B : 0) |
                    (p.f32_mode == 2 ? F_F32R : 0) | (p.has_o1_bf16 ? F_O1B : 0) | (e.norm2 != NORM_NONE ? F_N2 : 0);
   typedef void (*KFn)(const LinParams);
-  struct Variant { int mask; KFn fn[2]; bool configured[2]; };
-#define VAPB_LIN_VARIANT(M) {M, {gemm_lin_kernel<false, M>, gemm_lin_kernel<true, M>}, {false, false}}
+  struct Variant { int mask; KFn fn[2]; bool configured[2]; int nst; };
+#define VAPB_LIN_VARIANT(M) {M, {gemm_lin_kernel<false, M, 3>, gemm_lin_kernel<true, M, 3>}, {false, false}, 3}
+#define VAPB_LIN_VARIANT4(M) {M, {gemm_lin_kernel<false, M, 4>, gemm_lin_kernel<true, M, 3>}, {false, false}, 4}
   static Variant variants[] = {
       VAPB_LIN_VARIANT(F_O1B),                                        // q/k/v, cross k/v, cross q
       VAPB_LIN_VARIANT(F_O1B | F_ACT),                                // FFN in + GELU
       VAPB_LIN_VARIANT(F_RESID | F_F32B | F_N2),                      // attention out-projection
       VAPB_LIN_VARIANT(F_RESID | F_F32B | F_O1B | F_N2),              // FFN out
-      VAPB_LIN_VARIANT(F_PRE | F_ACT | F_O1B),                        // gEncoder convs (bias + ChannelNorm + ReLU)
+      VAPB_LIN_VARIANT4(F_PRE | F_ACT | F_O1B),                       // gEncoder convs (bias + ChannelNorm + ReLU), 4 stages
       VAPB_LIN_VARIANT(F_PRE | F_F32R),                               // vap_head
       VAPB_LIN_VARIANT(F_PRE | F_ACT | F_ACC | F_F32B | F_O1B),       // combinator
       VAPB_LIN_VARIANT(F_PRE | F_ACT | F_F32B | F_O1B | F_N2),        // downsample conv
       VAPB_LIN_VARIANT(F_ALL),
   };
 #undef VAPB_LIN_VARIANT
+#undef VAPB_LIN_VARIANT4
   Variant* v = nullptr;
   for (auto& cand : variants)
     if ((need & ~cand.mask) == 0) { v = &cand; break; }
   const int tiles = p.nseq * p.tiles_per_seq * p.n_tiles_n;
   const int grid = tiles < n_sm ? tiles : n_sm;
   const int wres = (a.K == 4 * LBK && grid >= p.n_tiles_n) ? 1 : 0;
-  const int smem = wres ? lin_smem_bytes<true>() : lin_smem_bytes<false>();
+  const int smem = wres ? lin_smem_bytes<true, 3>() : (v->nst == 4 ? lin_smem_bytes<false, 4>() : lin_smem_bytes<false, 3>());
   if (!v->configured[wres]) {
     if (cudaFuncSetAttribute(v->fn[wres], cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       if (err) *err = "gemm_lin: cannot reserve shared memory";
