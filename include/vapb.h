@@ -148,6 +148,12 @@ int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_
                        float* out1_f32, void* out1_bf16, int norm2, const float* g2, const float* b2,
                        void* out2_bf16, char* err, int err_len);
 
+/* Unit-test hook for the CTA-pair (cta_group::2) conv GEMM (csrc/k_gemm_2sm.cu): N = 256,
+ * bias -> norm1 -> ReLU (act 1) -> dense bf16 (nseq*rows_per_seq, 256). Operands as vapb_debug_gemm_tc. */
+int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W,
+                        int nseq, int rows_per_seq, int K, const float* bias, int norm1, const float* g1,
+                        const float* b1, int act, void* out_bf16, char* err, int err_len);
+
 /* Unit-test hook for the linear-layer GEMM (csrc/k_gemm_lin.cu): same operands as
  * vapb_debug_gemm_tc; outputs are dense (nseq*rows_per_seq, N). f32_mode 1: out1_f32
  * and resid_blocked use the row-blocked fp32 layout [row/128][col/4][row%128][4]

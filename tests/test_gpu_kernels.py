@@ -343,3 +343,34 @@ def test_ffn_fused_matches_torch(M, with_ln):
     assert (xs.float() - ref).abs().max().item() <= 3e-2
     if with_ln:
         assert (zn.float() - _norm(ref, 2, g2, b2)).abs().max().item() <= 6e-2
+
+
+@pytest.mark.parametrize("nseq,L,k,s,pad", [(1, 1024, 4, 2, 1), (3, 1000, 8, 4, 2), (5, 4000, 4, 2, 1)])
+def test_gemm_2sm_conv_channelnorm_relu(nseq, L, k, s, pad):
+    """CTA-pair (cta_group::2) implicit-GEMM conv + ChannelNorm + ReLU vs torch."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(nseq * 100 + k)
+    Lout = (L + 2 * pad - k) // s + 1
+    Lpad = ((max(s * (Lout - 1) + k, pad + L) + s - 1) // s) * s
+    x = torch.randn((nseq, L, 256), device="cuda", generator=g).bfloat16()
+    buf = torch.zeros((nseq, Lpad, 256), device="cuda", dtype=torch.bfloat16)
+    buf[:, pad:pad + L] = x
+    w = torch.randn((256, 256, k), device="cuda", generator=g) * 0.03
+    Wp = w.permute(0, 2, 1).reshape(256, k * 256).contiguous().bfloat16()
+    bias = torch.randn(256, device="cuda", generator=g)
+    g1 = torch.randn(256, device="cuda", generator=g)
+    b1 = torch.randn(256, device="cuda", generator=g)
+    out = torch.full((nseq * Lout, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_gemm_2sm(st, buf.data_ptr(), Lpad * 256, s * 256, Wp.data_ptr(), nseq, Lout, k * 256,
+                                 bias.data_ptr(), 1, g1.data_ptr(), b1.data_ptr(), 1, out.data_ptr(), err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    wr = Wp.float().reshape(256, k, 256).permute(0, 2, 1)
+    y = F.conv1d(x.float().transpose(1, 2), wr, bias, stride=s, padding=pad).transpose(1, 2).reshape(nseq * Lout, 256)
+    ref = F.relu(_norm(y, 1, g1, b1))
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 4e-2

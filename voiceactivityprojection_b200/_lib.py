@@ -31,6 +31,7 @@ SYMBOLS = {
     "vapb_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "vapb_debug_gemm_tc": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, _i,
                                 _fp, _fp, _i, _fp, _fp, _fp, C.c_char_p, _i]),
+    "vapb_debug_gemm_2sm": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, C.c_char_p, _i]),
     "vapb_debug_gemm_lin": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, _i,
                                  _fp, _i, _fp, _i, _fp, _fp, _fp, C.c_char_p, _i]),
     "vapb_debug_ffn_fused": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, C.c_char_p, _i]),

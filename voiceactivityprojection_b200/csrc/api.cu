@@ -133,6 +133,7 @@ int vapb_create(int device, VapbHandle** out) {
   VapbHandle* h = new VapbHandle();
   h->m.device = device;
   cudaDeviceGetAttribute(&h->m.n_sm, cudaDevAttrMultiProcessorCount, device);
+  if (const char* v = getenv("VAPB_CONV_2SM")) h->m.conv_2sm = atoi(v);
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
@@ -579,6 +580,38 @@ int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   std::string msg;
   int rc = launch_gemm_tc((cudaStream_t)stream, a, n_sm, &msg);
+  if (rc >= 0) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+  }
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
+int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W, int nseq,
+                        int rows_per_seq, int K, const float* bias, int norm1, const float* g1, const float* b1, int act,
+                        void* out_bf16, char* err, int err_len) {
+  TcGemmArgs a{};
+  a.A = A;
+  a.a_map = RowMap{a_seq_stride, a_row_stride};
+  a.W = W;
+  a.nseq = nseq;
+  a.rows_per_seq = rows_per_seq;
+  a.N = 256;
+  a.K = K;
+  a.e.bias = bias;
+  a.e.norm1 = norm1; a.e.g1 = g1; a.e.b1 = b1;
+  a.e.act = act;
+  a.e.out1_map = RowMap{(long long)rows_per_seq * 256, 256};
+  a.out1_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  std::string msg;
+  int rc = launch_gemm_2sm((cudaStream_t)stream, a, n_sm, &msg);
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }

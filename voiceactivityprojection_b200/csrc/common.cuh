@@ -101,6 +101,9 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
                      const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
                      const float* b2, int M, int n_sm, std::string* err);
 
+// CTA-pair (cta_group::2) GEMM for the K >= 1024 convolutions (k_gemm_2sm.cu); conv epilogue only. Returns launches or -1.
+int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);
+
 int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
                      long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence
 

@@ -276,7 +276,18 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
         out = H(p.act4) + (long long)s0 * L4 * kDim;
         e.out1_map = RowMap{L4 * kDim, kDim};
       }
-      if (i >= m.conv_lin_from)
+      if (m.conv_2sm) {
+        if (cx.rc) return cx.rc;
+        TcGemmArgs a{};
+        a.A = H(p.act[i - 1]); a.a_map = RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}; a.W = s.conv_w[i];
+        a.nseq = n; a.rows_per_seq = (int)g.L[i]; a.N = kDim; a.K = c.k * kDim;
+        a.e = e; a.out1_bf16 = out;
+        ProfScope ps(m, st, CAT_CONV_GEMM);
+        std::string err;
+        const int k = launch_gemm_2sm(st, a, m.n_sm, &err);
+        if (k < 0) { m.err = err; return -3; }
+        m.launches += k;
+      } else if (i >= m.conv_lin_from)
         cx.lin(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
                kDim, c.k * kDim, e, nullptr, out, 1, CAT_CONV_GEMM);
       else

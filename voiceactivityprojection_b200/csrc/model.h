@@ -66,6 +66,7 @@ struct Model {
   Weights w32{};   // fp32 [K][N] packing (SIMT path)
   void* bf16_state = nullptr;  // tensor-path weights / tensor maps (forward_bf16.cu)
   int n_sm = 148;
+  int conv_2sm = 1;       // gEncoder convs on CTA pairs (k_gemm_2sm.cu, cta_group::2); env VAPB_CONV_2SM
   int ffn_fused = 1;      // FFN block as one kernel (k_ffn_fused.cu); 0 = two GEMMs (env VAPB_FFN_FUSED)
   int conv0_tc = 1;       // conv0 on the tensor cores (k_conv0_tc.cu); 0 = CUDA-core kernel (env VAPB_CONV0_TC)
   int conv_lin_from = 1;  // gEncoder convs >= this index use k_gemm_lin.cu's staged epilogue (env VAPB_CONV_LIN_FROM)
