@@ -170,7 +170,7 @@ int vapb_debug_gemm_lin(void* stream, const void* A, int64_t a_seq_stride, int64
  * LayerNorm(x_out; g2, b2), or NULL. */
 int vapb_debug_ffn_fused(void* stream, const void* z, const void* w1, const void* w2, const float* resid_blocked,
                           float* x_out_blocked, void* xs, void* zn, const float* g2, const float* b2, int M, char* err,
-                          int err_len);
+                          int err_len, long long* dbg_clocks /* device [32][16] SM-clock samples or NULL */);
 
 /* Unit-test hooks for the tensor-core gAR recurrence (csrc/k_rnn_tc.cu).
  * vapb_debug_rnn_pack (host only): nn.LSTM / nn.GRU parameters of one layer

@@ -332,7 +332,7 @@ def test_ffn_fused_matches_torch(M, with_ln):
     st = torch.cuda.current_stream().cuda_stream
     rc = lib.vapb_debug_ffn_fused(st, z.data_ptr(), w1.data_ptr(), w2.data_ptr(), rb.data_ptr(), xo.data_ptr(),
                                   xs.data_ptr(), zn.data_ptr() if with_ln else None, g2.data_ptr(), b2.data_ptr(), M,
-                                  err, 512)
+                                  err, 512, None)
     assert rc == 0, err.value.decode()
     torch.cuda.synchronize()
     h = F.gelu(z.float() @ w1.float().T).bfloat16().float()  # the kernel rounds the hidden activation to bf16

@@ -665,7 +665,7 @@ int vapb_debug_gemm_lin(void* stream, const void* A, int64_t a_seq_stride, int64
 
 int vapb_debug_ffn_fused(void* stream, const void* z, const void* w1, const void* w2, const float* resid_blocked,
                           float* x_out_blocked, void* xs, void* zn, const float* g2, const float* b2, int M, char* err,
-                          int err_len) {
+                          int err_len, long long* dbg_clocks) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -673,7 +673,7 @@ int vapb_debug_ffn_fused(void* stream, const void* z, const void* w1, const void
   typedef const __nv_bfloat16* bp;
   int rc = launch_ffn_fused((cudaStream_t)stream, (bp)z, (bp)w1, (bp)w2, resid_blocked, x_out_blocked,
                             reinterpret_cast<__nv_bfloat16*>(xs), reinterpret_cast<__nv_bfloat16*>(zn), g2, b2, M, n_sm,
-                            &msg);
+                            &msg, dbg_clocks);
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }

@@ -99,7 +99,7 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
 // Fused FFN block (k_ffn_fused.cu): x_out = resid + W2 GELU(W1 z); xs = bf16(x_out); zn = LayerNorm(x_out) or null
 int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
                      const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
-                     const float* b2, int M, int n_sm, std::string* err);
+                     const float* b2, int M, int n_sm, std::string* err, long long* dbg = nullptr);
 
 // CTA-pair (cta_group::2) GEMM for the K >= 1024 convolutions (k_gemm_2sm.cu); conv epilogue only. Returns launches or -1.
 int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);

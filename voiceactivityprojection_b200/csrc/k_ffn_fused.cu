@@ -27,20 +27,22 @@ using namespace tc;
 namespace {
 
 constexpr int FK_BYTES = 128 * 64 * 2;   // one A k-block: 128 rows x 64 k, 16 KB
-constexpr int FW_BYTES = 256 * 64 * 2;   // one W k-block: 256 n x 64 k, 32 KB
-constexpr int FW_STAGES = 3;
+constexpr int FW_BYTES = 128 * 64 * 2;   // one W tile: 128 n x 64 k, 16 KB (W2's 256-row k-blocks are loaded as two halves)
+constexpr int FW_STAGES = 5;
 constexpr int F_OFF_Z = 0;
 constexpr int F_OFF_H = 4 * FK_BYTES;                 // also: staging [half][2] x 8 KB, then LN vectors / partials
 constexpr int F_OFF_W = F_OFF_H + 4 * FK_BYTES;
-constexpr int F_OFF_BAR = F_OFF_W + FW_STAGES * FW_BYTES;
+constexpr int F_OFF_VEC = F_OFF_W + FW_STAGES * FW_BYTES;   // FfnVecs (resident)
+constexpr int F_OFF_BAR = F_OFF_VEC + 6144;
 constexpr int F_SMEM = F_OFF_BAR + 256 + 1024 /*alignment slack*/;
-constexpr int F_H_STG = 0, F_H_VEC = 32768;           // offsets inside the H region used by the final epilogue
-constexpr int F_THREADS = 384;
+constexpr int F_H_STG = 0;                            // the final epilogue's staging tiles alias the H region: [quarter][2] x 8 KB
+constexpr int F_THREADS = 640;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-19 epilogue (4 warps per TMEM lane quadrant)
+constexpr int F_EPI = 512;
 
 struct alignas(64) FfnParams {
   CUtensorMap tma_z;    // (256, M) bf16, box (64, 128)
   CUtensorMap tma_w1;   // (256 k, 768 n) bf16, box (64, 128)
-  CUtensorMap tma_w2;   // (768 k, 256 n) bf16, box (64, 256)
+  CUtensorMap tma_w2;   // (768 k, 256 n) bf16, box (64, 128)
   CUtensorMap tma_xs;   // (256, M) bf16 out, box (32, 128), SW64
   CUtensorMap tma_zn;   // (256, M) bf16 out (LayerNorm of x_out), box (32, 128), SW64
   int M, num_tiles;
@@ -48,11 +50,12 @@ struct alignas(64) FfnParams {
   float* x_out;         // row-blocked fp32
   int has_ln;
   const float *g2, *b2;
+  long long* dbg;  // optional [32 tiles][16] SM-clock samples of CTA 0's first epilogue thread (tools/ffn_probe.py)
 };
 
 struct FfnVecs {
   float g2[256], b2[256];
-  float part[2][128][2];
+  float part[4][128][2];
 };
 
 __device__ __forceinline__ float2 gelu_poly2_f(float2 x) {  // same polynomial as k_gemm_lin.cu
@@ -79,13 +82,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   const uint32_t bar_base = smem_base + F_OFF_BAR;
   const uint32_t z_full = bar_base, z_empty = bar_base + 8;
   auto w_full = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto w_empty = [&](int s) { return bar_base + 8u * (6 + s); };
-  auto acch_full = [&](int b) { return bar_base + 8u * (10 + b); };  // GEMM 1 of a chunk has completed
-  auto h_full = [&](int b) { return bar_base + 8u * (12 + b); };     // epilogue wrote H[b] (and no longer reads ACC_H[b]); 256
-  auto h_empty = [&](int b) { return bar_base + 8u * (14 + b); };    // GEMM 2 of a chunk has completed (H[b] may be overwritten)
-  const uint32_t acco_full = bar_base + 8 * 16;  // GEMM 2 of the last chunk has completed
-  const uint32_t acco_empty = bar_base + 8 * 17; // final epilogue no longer reads ACC_O; 256 arrivals
-  const uint32_t tmem_slot = bar_base + 8 * 18;
+  auto w_empty = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto acch_full = [&](int b) { return bar_base + 8u * (14 + b); };  // GEMM 1 of a chunk has completed
+  auto h_full = [&](int b) { return bar_base + 8u * (16 + b); };     // epilogue wrote H[b] (and no longer reads ACC_H[b]); 512
+  auto h_empty = [&](int b) { return bar_base + 8u * (18 + b); };    // GEMM 2 of a chunk has completed (H[b] may be overwritten)
+  const uint32_t acco_full = bar_base + 8 * 20;  // GEMM 2 of the last chunk has completed
+  const uint32_t acco_empty = bar_base + 8 * 21; // final epilogue no longer reads ACC_O; 512 arrivals
+  const uint32_t tmem_slot = bar_base + 8 * 22;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -100,11 +103,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acch_full(b), 1);
-      mbar_init(h_full(b), 256);
+      mbar_init(h_full(b), F_EPI);
       mbar_init(h_empty(b), 1);
     }
     mbar_init(acco_full, 1);
-    mbar_init(acco_empty, 256);
+    mbar_init(acco_empty, F_EPI);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -117,23 +120,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
 
   if (warp == 0) {
     // ===== TMA producer: Z of the tile, then the W k-blocks in the order the MMA thread consumes them:
-    // W1[0], W1[1], then for j = 0..5: W2[j], W1[j+2] (ring slots are 32 KB; a W1 k-block uses half of one)
+    // W1[0], W1[1], then for j = 0..5: W2[j], W1[j+2]; every load is a 128 n x 64 k tile (16 KB)
     if (lane == 0) {
       uint32_t wc = 0, it = 0;
       auto load_w1 = [&](int j) {
         for (int kb = 0; kb < 4; ++kb, ++wc) {
           const int s = wc % FW_STAGES;
           mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(w_full(s), FW_BYTES / 2);
+          mbar_arrive_expect_tx(w_full(s), FW_BYTES);
           tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w1, w_full(s), kb * 64, j * 128);
         }
       };
       auto load_w2 = [&](int j) {
-        for (int kb = 0; kb < 2; ++kb, ++wc) {
+        for (int i = 0; i < 4; ++i, ++wc) {  // (k-block, output-channel half)
           const int s = wc % FW_STAGES;
           mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(w_full(s), FW_BYTES);
-          tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s), j * 128 + kb * 64, 0);
+          tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s), j * 128 + (i >> 1) * 64, (i & 1) * 128);
         }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   } else if (warp == 1) {
     // ===== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0), idesc2 = make_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0);
       uint32_t wc = 0, it = 0, hcnt[2] = {0, 0} /*h_full phases seen per buffer*/, n_o = 0;
       auto gemm1 = [&](int b) {  // ACC_H[b] = Z W1[chunk]^T
         for (int kb = 0; kb < 4; ++kb, ++wc) {
@@ -169,15 +172,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
         umma_commit(acch_full(b));
       };
       auto gemm2 = [&](int b, bool first) {  // ACC_O (+)= H[b] W2[:, chunk]^T
-        for (int kb = 0; kb < 2; ++kb, ++wc) {
-          const int s = wc % FW_STAGES;
+        for (int i = 0; i < 4; ++i, ++wc) {  // (k-block, output-channel half): two N = 128 MMAs per K step
+          const int s = wc % FW_STAGES, kb = i >> 1, nh = i & 1;
           mbar_wait(w_full(s), (wc / FW_STAGES) & 1u);
           tc_fence_after();
           const uint32_t a_addr = smem_base + F_OFF_H + (b * 2 + kb) * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(t_acco, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
-                      idesc2, !(first && kb == 0 && k == 0));
+            umma_bf16(t_acco + nh * 128, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                      make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc1, !(first && kb == 0 && k == 0));
           umma_commit(w_empty(s));
         }
         umma_commit(h_empty(b));
@@ -210,23 +213,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread = (accumulator row, column half)
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+    // ===== epilogue: 16 warps, thread = (accumulator row, column quarter). Two warps per scheduler could not hide
+    // the latencies of this epilogue (ncu: 0.27 IPC per scheduler, 24 us per tile against 7.6 us of MMAs).
+    const int quad = warp & 3, qtr = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
-    const bool leader = (threadIdx.x - 128 - half * 128) == 0;
-    const int cbase = half * 128;
+    const bool leader = (warp == 4 + 4 * qtr) && lane == 0;  // issues this quarter's TMA stores
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     uint8_t* h_gen = smem_gen + F_OFF_H;
     const uint32_t sw128 = (uint32_t)(row & 7), sw64 = (uint32_t)((row >> 1) & 3);
-    FfnVecs& ev = *reinterpret_cast<FfnVecs*>(h_gen + F_H_VEC);
-    const uint32_t stg_addr = smem_base + F_OFF_H + F_H_STG + half * 16384;
-    uint8_t* stg_gen = h_gen + F_H_STG + half * 16384;
+    FfnVecs& ev = *reinterpret_cast<FfnVecs*>(smem_gen + F_OFF_VEC);
+    const uint32_t stg_addr = smem_base + F_OFF_H + F_H_STG + qtr * 16384;  // 2 x (128 rows x 64 B) per quarter
+    uint8_t* stg_gen = h_gen + F_H_STG + qtr * 16384;
     uint32_t stg_cnt = 0, hcnt[2] = {0, 0} /*chunks done per ACC_H / H buffer*/, n_o = 0;
-    auto bar_half = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
-    auto bar_epi = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    if (p.has_ln && threadIdx.x - 128 < 256) {  // LayerNorm affine vectors, resident for the kernel
+      ev.g2[threadIdx.x - 128] = p.g2[threadIdx.x - 128];
+      ev.b2[threadIdx.x - 128] = p.b2[threadIdx.x - 128];
+    }
+    auto bar_qtr = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + qtr) : "memory"); };
+    auto bar_epi = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
     auto stage_bf16 = [&](const CUtensorMap* map, const float (&v)[32], int c0, int c1) {
       if (leader) bulk_wait_read<1>();
-      bar_half();
+      bar_qtr();
       const uint32_t boff = (stg_cnt & 1u) * 8192u;
       uint8_t* rowp = stg_gen + boff + (uint32_t)row * 64u;
 #pragma unroll
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
         *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
       }
       fence_proxy_async();
-      bar_half();
+      bar_qtr();
       if (leader) {
         tma_store_2d(map, stg_addr + boff, c0, c1);
         bulk_commit();
@@ -247,20 +254,26 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
       ++stg_cnt;
     };
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int dbg_t = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++dbg_t) {
+      const bool dbg = p.dbg && blockIdx.x == 0 && threadIdx.x == 128 && dbg_t < 32;
+      long long* dq = p.dbg + dbg_t * 16;
+      if (dbg) dq[0] = clock64();
       const long long m = (long long)tile * 128 + row;
       const bool valid = m < p.M;
-      // pull this tile's residual rows into L2 now: the final epilogue reads them ~10 us later and used to stall on
-      // DRAM latency once per 32-column chunk (ncu: the residual adds were the top long-scoreboard stall)
+      const int cbase = qtr * 64;  // this thread's 64 output columns in the final epilogue
+      // pull this tile's residual rows into L2 now: the final epilogue reads them ~10 us later and otherwise stalls on
+      // DRAM latency (ncu: the residual adds were the top long-scoreboard stall)
       if (valid && (lane & 7) == 0) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
+        for (int c = 0; c < 16; ++c)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + blocked_off_f(m, cbase + c * 4)));
       }
-      // ---- six hidden chunks of 128: ACC_H[b] -> GELU -> H[b] (bf16, SW128 K-major; this half writes k-block `half`)
+      // ---- six hidden chunks of 128: ACC_H[b] -> GELU -> H[b] (bf16, SW128 K-major); this thread: 32 columns
       for (int j = 0; j < 6; ++j) {
         const int b = j & 1;
         mbar_wait(acch_full(b), hcnt[b] & 1u);
+        if (dbg && j == 0) dq[1] = clock64();
         // H[b] is free: GEMM 2 of the chunk that used it two chunks ago has completed (first uses: nothing to wait for) ...
         mbar_wait(h_empty(b), (hcnt[b] & 1u) ^ 1u);
         ++hcnt[b];
@@ -270,111 +283,100 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
           bar_epi();
         }
         tc_fence_after();
-        const uint32_t taddr = t_acch + lane_off + b * 128 + half * 64;
-        uint8_t* rowp = h_gen + (b * 2 + half) * FK_BYTES + (uint32_t)row * 128u;
-        uint32_t r[2][32];
-        tmem_ld32(taddr, r[0]);
-        tmem_ld32(taddr + 32, r[1]);
+        uint32_t r[32];
+        tmem_ld32(t_acch + lane_off + b * 128 + qtr * 32, r);
         tmem_ld_wait();
+        // columns 32 qtr .. +31 of the chunk: k-block qtr / 2, 16-byte chunks 4 (qtr & 1) .. +3 of the row
+        uint8_t* rowp = h_gen + (b * 2 + (qtr >> 1)) * FK_BYTES + (uint32_t)row * 128u;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int q = 0; q < 4; ++q) {
+          float2 y[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 y[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              y[e] = gelu_poly2_f(make_float2(__uint_as_float(r[c][8 * q + 2 * e]), __uint_as_float(r[c][8 * q + 2 * e + 1])));
-            uint4 u;
-            u.x = pack_bf16(y[0].x, y[0].y);
-            u.y = pack_bf16(y[1].x, y[1].y);
-            u.z = pack_bf16(y[2].x, y[2].y);
-            u.w = pack_bf16(y[3].x, y[3].y);
-            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(c * 4 + q)) ^ sw128) << 4)) = u;
-          }
+          for (int e = 0; e < 4; ++e)
+            y[e] = gelu_poly2_f(make_float2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1])));
+          uint4 u;
+          u.x = pack_bf16(y[0].x, y[0].y);
+          u.y = pack_bf16(y[1].x, y[1].y);
+          u.z = pack_bf16(y[2].x, y[2].y);
+          u.w = pack_bf16(y[3].x, y[3].y);
+          *reinterpret_cast<uint4*>(rowp + ((((uint32_t)((qtr & 1) * 4 + q)) ^ sw128) << 4)) = u;
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(h_full(b));
+        if (dbg) dq[2 + j] = clock64();
       }
-      // ---- final epilogue on ACC_O
+      // ---- final epilogue on ACC_O: this thread's 64 columns in two chunks of 32
       mbar_wait(acco_full, n_o & 1u);
+      if (dbg) dq[8] = clock64();
       ++n_o;
       tc_fence_after();
-      // GEMM 2 of the last chunk is complete, so the H region is free: LayerNorm vectors and staging live there
-      if (p.has_ln) {
-        const int e = threadIdx.x - 128;
-        ev.g2[e] = p.g2[e];
-        ev.b2[e] = p.b2[e];
-      }
-      bar_epi();
+      // GEMM 2 of the last chunk is complete, so the H region is free: the staging tiles live there
       const uint32_t taddr = t_acco + lane_off + cbase;
       float s2 = 0.f, ss2 = 0.f;
-      {
-        uint32_t r[2][32];
-        tmem_ld32(taddr, r[0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-          float v[32];
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[c & 1][i]);
-          if (valid) {
-            const float* rp = p.resid + blocked_off_f(m, cbase + c * 32);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (valid) {
+          const float* rp = p.resid + blocked_off_f(m, cbase + c * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = *reinterpret_cast<const float4*>(rp + i * 512);
-              v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
-            }
-            float* op = p.x_out + blocked_off_f(m, cbase + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(op + i * 512) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = *reinterpret_cast<const float4*>(rp + i * 512);
+            v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
           }
-          stage_bf16(&p.tma_xs, v, cbase + c * 32, tile * 128);
-          if (p.has_ln) {
-            uint32_t w[32];
+          float* op = p.x_out + blocked_off_f(m, cbase + c * 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              s2 += v[i];
-              ss2 = fmaf(v[i], v[i], ss2);
-              w[i] = __float_as_uint(v[i]);
-            }
-            tmem_st32(taddr + c * 32, w);  // keep v for the LayerNorm pass
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(op + i * 512) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        stage_bf16(&p.tma_xs, v, cbase + c * 32, tile * 128);
+        if (p.has_ln) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s2 += v[i];
+            ss2 = fmaf(v[i], v[i], ss2);
+            r[i] = __float_as_uint(v[i]);
           }
+          tmem_st32(taddr + c * 32, r);  // keep v for the LayerNorm pass
         }
       }
+      if (dbg) dq[9] = clock64();
       if (p.has_ln) {
         tmem_st_wait();
-        ev.part[half][row][0] = s2;
-        ev.part[half][row][1] = ss2;
+        ev.part[qtr][row][0] = s2;
+        ev.part[qtr][row][1] = ss2;
         bar_epi();
-        s2 += ev.part[half ^ 1][row][0];
-        ss2 += ev.part[half ^ 1][row][1];
+        s2 = (ev.part[0][row][0] + ev.part[1][row][0]) + (ev.part[2][row][0] + ev.part[3][row][0]);
+        ss2 = (ev.part[0][row][1] + ev.part[1][row][1]) + (ev.part[2][row][1] + ev.part[3][row][1]);
         const float mean2 = s2 * (1.0f / kDim);
         const float var2 = fmaxf(ss2 - s2 * mean2, 0.f) * (1.0f / kDim);
         const float rstd2 = rsqrtf(var2 + kEps);
-        uint32_t r[2][32];
-        tmem_ld32(taddr, r[0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 g = *reinterpret_cast<const float4*>(&ev.g2[cbase + c * 32 + i]);
             const float4 b = *reinterpret_cast<const float4*>(&ev.b2[cbase + c * 32 + i]);
-            v[i] = fmaf((__uint_as_float(r[c & 1][i]) - mean2) * rstd2, g.x, b.x);
-            v[i + 1] = fmaf((__uint_as_float(r[c & 1][i + 1]) - mean2) * rstd2, g.y, b.y);
-            v[i + 2] = fmaf((__uint_as_float(r[c & 1][i + 2]) - mean2) * rstd2, g.z, b.z);
-            v[i + 3] = fmaf((__uint_as_float(r[c & 1][i + 3]) - mean2) * rstd2, g.w, b.w);
+            v[i] = fmaf((__uint_as_float(r[i]) - mean2) * rstd2, g.x, b.x);
+            v[i + 1] = fmaf((__uint_as_float(r[i + 1]) - mean2) * rstd2, g.y, b.y);
+            v[i + 2] = fmaf((__uint_as_float(r[i + 2]) - mean2) * rstd2, g.z, b.z);
+            v[i + 3] = fmaf((__uint_as_float(r[i + 3]) - mean2) * rstd2, g.w, b.w);
           }
           stage_bf16(&p.tma_zn, v, cbase + c * 32, tile * 128);
         }
       }
       tc_fence_before();
       mbar_arrive(acco_empty);
+      if (dbg) dq[10] = clock64();
     }
     if (leader) bulk_wait<0>();
   }
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
 // xs: bf16 (M, 256) = x_out; zn: bf16 (M, 256) = LayerNorm(x_out; g2, b2) or null.
 int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
                      const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
-                     const float* b2, int M, int n_sm, std::string* err) {
+                     const float* b2, int M, int n_sm, std::string* err, long long* dbg) {
   FfnParams p{};
   auto map2 = [&](CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t b0, uint32_t b1, int sw) {
     const uint64_t dims[2] = {inner, outer};
@@ -402,7 +404,7 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
   };
   if (!map2(&p.tma_z, z, 256, (uint64_t)M, 64, 128, 128)) return -1;
   if (!map2(&p.tma_w1, w1, 256, 768, 64, 128, 128)) return -1;
-  if (!map2(&p.tma_w2, w2, 768, 256, 64, 256, 128)) return -1;
+  if (!map2(&p.tma_w2, w2, 768, 256, 64, 128, 128)) return -1;
   if (!map2(&p.tma_xs, xs, 256, (uint64_t)M, 32, 128, 64)) return -1;
   if (zn && !map2(&p.tma_zn, zn, 256, (uint64_t)M, 32, 128, 64)) return -1;
   p.M = M;
@@ -412,6 +414,7 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
   p.has_ln = zn != nullptr;
   p.g2 = g2;
   p.b2 = b2;
+  p.dbg = dbg;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
