@@ -14,9 +14,10 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsec
 
 
 def short(name):
+    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "").replace("vapb::", "")
     name = re.sub(r"\(.*", "", name)
     name = re.sub(r"<.*", "", name)
-    return name.replace("void ", "").replace("vapb::", "").replace("(anonymous namespace)::", "").strip()[:60]
+    return name.strip()[:60]
 
 
 def main():
