@@ -96,7 +96,7 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- #
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     """The reference's CPU implementation of the path (oracle port; the Python
     reference itself cannot travel to the GPU box), all host threads."""
     import torch
@@ -130,7 +130,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(args, precision):
@@ -162,7 +162,30 @@ def cpu_baseline(sample_batch=2, iters=2):
 
 
 # --------------------------------------------------------------------------- #
+def _bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs local to its GPU (NVML affinity mask) BEFORE pinned buffers are allocated, so
+    the host side of the H2D / D2H copies is first-touched on the GPU's own NUMA node (matters when 8 ranks stream
+    ~1 GB per step each through the same host)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints to fd 1 (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -177,7 +200,7 @@ def main():
     args.warmup = max(args.warmup, 0)
 
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, real_stdout)
         return
 
     import torch
@@ -195,6 +218,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    local_cpus = _bind_to_gpu_numa_node(local) if world > 1 else 0
 
     model = VapGPT(VapConfig()).to(dev)
     model.load_state_dict(synth.make_state_dict(0, "LSTM", 1, 2.0))
@@ -337,7 +361,9 @@ def main():
             "data": "synthetic", "config": workload_config(args, precision), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        if local_cpus:
+            line["config"]["host_affinity"] = f"rank bound to the {local_cpus} CPUs local to its GPU (NVML)"
+        print(json.dumps(line), file=real_stdout, flush=True)
     if dist:
         dist.destroy_process_group()
 
