@@ -194,6 +194,23 @@ def test_bulk_runner_equals_direct_calls(precision):
     assert runner.h2d_bytes == sum(sizes) * 2 * n * 4
 
 
+def test_bulk_runner_pcm16_input_matches_float_input():
+    """int16 PCM host batches (half the PCIe bytes) give exactly what the float path gives on x / 32768."""
+    from oracle import synth
+    from voiceactivityprojection_b200.bulk import BulkRunner
+
+    m = _model(synth.make_state_dict(3, "LSTM", 1, 2.0))
+    n = 40000
+    pcm = (synth.make_waveform(3, n, 5, "turns") * 20000).round().clamp(-32768, 32767).to(torch.int16).pin_memory()
+    ref = m.probs((pcm.float() / 32768.0).cuda())
+    got = {}
+    r = BulkRunner(m, 4, n, pcm16=True, stats=False)
+    r.run([pcm], sink=lambda i, b, o: got.update({k: v.clone() for k, v in o.items()}))
+    assert r.h2d_bytes == pcm.numel() * 2
+    for k in ["probs", "vad", "p_now", "p_future", "H", "loss"]:
+        assert torch.equal(got[k], ref[k].cpu()), k
+
+
 BF16_TOL = dict(probs=5e-3, vad=2e-2, p_now=2e-3, p_future=2e-3, logits=0.1)
 
 

@@ -84,7 +84,9 @@ class BulkRunner:
     """Pipelined `model.probs` over a stream of pinned host batches of shape (b <= batch, 2, n_samples)."""
 
     def __init__(self, model, batch: int, n_samples: int, precision: Optional[str] = None,
-                 keys: Sequence[str] = ALL_KEYS, stats: bool = True, depth: int = 2):
+                 keys: Sequence[str] = ALL_KEYS, stats: bool = True, depth: int = 2, pcm16: bool = False):
+        """pcm16=True: host batches are int16 PCM (what wav files hold; the reference converts to float on the CPU,
+        vap/audio.py:47); they cross PCIe at half the bytes and are scaled by 1/32768 on the device."""
         from . import _lib
 
         if model._device.type != "cuda":
@@ -94,7 +96,10 @@ class BulkRunner:
         self.dev = model._device
         _, self.T = _lib.frames(n_samples)
         want_argmax = stats or "argmax" in self.keys
-        self.din = [torch.empty((batch, 2, n_samples), dtype=torch.float32, device=self.dev) for _ in range(depth)]
+        self.pcm16 = pcm16
+        in_dtype = torch.int16 if pcm16 else torch.float32
+        self.din = [torch.empty((batch, 2, n_samples), dtype=in_dtype, device=self.dev) for _ in range(depth)]
+        self.dwav = torch.empty((batch, 2, n_samples), dtype=torch.float32, device=self.dev) if pcm16 else None
         self.dout = [model.alloc_outputs(batch, self.T, self.dev, argmax=want_argmax) for _ in range(depth)]
         host = model.alloc_outputs(batch, self.T, "cpu", argmax=True, pin_memory=True)
         self.hout = [{k: torch.empty_like(host[k], pin_memory=True) for k in self.keys} for _ in range(depth)]
@@ -119,7 +124,8 @@ class BulkRunner:
             s.wait_stream(cur)
         for i, hb in enumerate(batches):
             b = hb.shape[0]
-            if hb.device.type != "cpu" or b > self.batch or tuple(hb.shape[1:]) != (2, self.n_samples):
+            if (hb.device.type != "cpu" or b > self.batch or tuple(hb.shape[1:]) != (2, self.n_samples)
+                    or hb.dtype != self.din[0].dtype):
                 raise ValueError(f"batch {i}: expected a CPU tensor (<= {self.batch}, 2, {self.n_samples}), got "
                                  f"{tuple(hb.shape)} on {hb.device}")
             slot = i % self.depth
@@ -127,12 +133,18 @@ class BulkRunner:
                 self.s_h2d.wait_event(self.ev_cmp[slot])      # the forward that read din[slot] has finished
                 self.din[slot][:b].copy_(hb, non_blocking=True)
                 self.ev_h2d[slot].record(self.s_h2d)
-            self.h2d_bytes += hb.numel() * 4
+            self.h2d_bytes += hb.numel() * hb.element_size()
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self.ev_h2d[slot])
                 self.s_cmp.wait_event(self.ev_d2h[slot])      # dout[slot] has been copied out
                 o = {k: v[:b] for k, v in self.dout[slot].items()}
-                self.model.probs(self.din[slot][:b], out=o, **kw)
+                if self.pcm16:
+                    wav = self.dwav[:b]
+                    wav.copy_(self.din[slot][:b])
+                    wav.mul_(1.0 / 32768.0)
+                else:
+                    wav = self.din[slot][:b]
+                self.model.probs(wav, out=o, **kw)
                 if self.stats_on:
                     self._hist += torch.bincount(o["argmax"].reshape(-1).to(torch.int64), minlength=256)
                     self._vact += (o["vad"] >= 0.5).sum(dim=(0, 1))
