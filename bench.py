@@ -279,7 +279,7 @@ def main():
 
         host_wav = torch.empty((B, 2, CHUNK_SAMPLES), dtype=torch.float32, pin_memory=True)
         host_wav.copy_(wav)
-        runner = BulkRunner(model, B, CHUNK_SAMPLES, precision=precision, keys=ALL_KEYS, stats=False)
+        runner = BulkRunner(model, B, CHUNK_SAMPLES, precision=precision, keys=ALL_KEYS, stats=True)
         seen = []
         runner.run([host_wav] * 2, sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
         torch.cuda.synchronize()
@@ -288,7 +288,7 @@ def main():
         n_e2e = max(8, 2 * args.steps)  # the pipeline's fill (first H2D) and drain (last D2H) are inside the timed region
         runner.h2d_bytes = runner.d2h_bytes = 0
         t0 = time.perf_counter()
-        runner.run((host_wav for _ in range(n_e2e)), sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
+        stats = runner.run((host_wav for _ in range(n_e2e)), sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist:
@@ -298,6 +298,21 @@ def main():
         e2e = {"value": total_chunks * CHUNK_SECONDS * n_e2e / dt, "unit": UNIT,
                "h2d_bytes_per_step": runner.h2d_bytes // n_e2e, "d2h_bytes_per_step": runner.d2h_bytes // n_e2e,
                "steps": n_e2e, "api": "BulkRunner.run (pinned host batches in, pinned host outputs out, 3-stream pipeline)"}
+        # the only collectives of the path (BASELINE configs[3]): all-reduce of the shard counters and all-gather of the
+        # compact per-chunk outputs of the last batch, over NCCL on the devices (outside the timed region)
+        bulk = None
+        if dist:
+            from voiceactivityprojection_b200.bulk import gather_compact
+
+            tot = stats.all_reduce(device=dev)
+            last = runner.dout[(n_e2e - 1) % runner.depth]
+            comp = gather_compact({k: last[k] for k in ("vad", "p_now", "p_future", "H", "argmax")})
+            bulk = {"chunks": tot.chunks, "frames": tot.frames, "vad_active_frames": tot.vad_active.tolist(),
+                    "classes_seen": int((tot.class_hist > 0).sum()), "gathered_chunks": int(comp["p_now"].shape[0]),
+                    "gathered_bytes": int(sum(v.numel() * v.element_size() for v in comp.values())),
+                    "collectives": "ncclAllReduce(counters) + ncclAllGather(compact outputs)"}
+            assert tot.chunks == world * B * n_e2e and comp["p_now"].shape[0] == world * B
+            e2e["bulk"] = bulk
         del runner
     clocks = sampler.stop() if sampler else None  # sampled over both timed regions (device-timed steps and e2e)
 

@@ -108,6 +108,7 @@ class BulkRunner:
         self.ev_h2d, self.ev_cmp, self.ev_d2h = mk(), mk(), mk()
         self.h2d_bytes = self.d2h_bytes = 0
         self._hist = torch.zeros(256, dtype=torch.int64, device=self.dev)
+        self._ones = torch.ones(batch * self.T, dtype=torch.int64, device=self.dev)
         self._vact = torch.zeros(2, dtype=torch.int64, device=self.dev)
 
     def run(self, batches: Iterable[Tensor], sink: Optional[Callable[[int, int, Dict[str, Tensor]], None]] = None
@@ -146,7 +147,8 @@ class BulkRunner:
                     wav = self.din[slot][:b]
                 self.model.probs(wav, out=o, **kw)
                 if self.stats_on:
-                    self._hist += torch.bincount(o["argmax"].reshape(-1).to(torch.int64), minlength=256)
+                    # index_add_, not bincount: bincount reads its maximum back to the host and would stall the pipeline
+                    self._hist.index_add_(0, o["argmax"].reshape(-1).to(torch.int64), self._ones[: b * self.T])
                     self._vact += (o["vad"] >= 0.5).sum(dim=(0, 1))
                 self.ev_cmp[slot].record(self.s_cmp)
             with torch.cuda.stream(self.s_d2h):
