@@ -5,7 +5,7 @@
 // Two CTAs of a cluster (the two SMs of a TPC) share one MMA: each CTA holds ITS 128 rows of A and
 // HALF of the W tile (128 of the 256 output channels) in shared memory and gets its 128 accumulator
 // rows in its own TMEM. Per CTA a k-block is 16 KB of A + 16 KB of W instead of 16 + 32 KB, so the
-// same shared memory holds a 6-deep operand ring (the 1-CTA kernel idled the tensor pipe 29 % of the
+// same shared memory holds a 5-deep operand ring plus double-buffered output staging (the 1-CTA kernel idled the tensor pipe 29 % of the
 // time with 3 stages, 22 % with 4) and W is fetched from L2 once per CTA pair.
 //
 // Roles per CTA: warp 0 = TMA producer (both CTAs load; every transaction completes on the LEADER's
@@ -24,11 +24,11 @@ using namespace tc;
 
 namespace {
 
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 5;
 constexpr int G2_A_BYTES = 128 * 64 * 2, G2_B_BYTES = 128 * 64 * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB
-constexpr int G2_OFF_STG = G2_STAGES * G2_STAGE_BYTES;   // [half] x 8 KB (128 rows x 64 B, SW64), single-buffered
-constexpr int G2_OFF_BAR = G2_OFF_STG + 2 * 8192;
+constexpr int G2_OFF_STG = G2_STAGES * G2_STAGE_BYTES;   // [half][2] x 8 KB (128 rows x 64 B, SW64)
+constexpr int G2_OFF_BAR = G2_OFF_STG + 4 * 8192;
 constexpr int G2_OFF_VEC = G2_OFF_BAR + 256;
 constexpr int G2_THREADS = 384;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_2sm_kernel(const __grid_co
     const int row_in_tile = quad * 32 + lane;
     const bool leader = (threadIdx.x - 128 - half * 128) == 0;
     const int cbase = half * 128;
-    const uint32_t stg_addr = smem_base + G2_OFF_STG + half * 8192;
-    uint8_t* stg_gen = smem_gen + G2_OFF_STG + half * 8192;
+    const uint32_t stg_addr = smem_base + G2_OFF_STG + half * 16384;
+    uint8_t* stg_gen = smem_gen + G2_OFF_STG + half * 16384;
     const uint32_t sw64 = (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t stg_cnt = 0;
     auto bar_half = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_2sm_kernel(const __grid_co
               v[i + j] = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
             }
           }
-          if (leader) bulk_wait_read<0>();
+          if (leader) bulk_wait_read<1>();
           bar_half();
-          const uint32_t boff = 0u;
+          const uint32_t boff = (stg_cnt & 1u) * 8192u;
           uint8_t* rowp = stg_gen + boff + (uint32_t)row_in_tile * 64u;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
