@@ -338,7 +338,7 @@ def main():
         dom = max(("conv_gemm", "linear_gemm", "attention", "rnn", "conv0"), key=lambda k: fams[k][0])
         dom_ms, dom_n = fams[dom]
         step_ms = sum(v[0] for v in fams.values())
-        if precision == "bf16":
+        if precision in ("bf16", "fp16"):
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
         else:
@@ -348,7 +348,7 @@ def main():
         # DRAM bytes of the dominant family per step, from the committed ncu capture of this same command
         traffic, traffic_src = None, None
         tf = os.path.join(ROOT, "profiles", "r1_traffic_bf16.json")
-        if precision == "bf16" and B == 256 and os.path.exists(tf):
+        if precision in ("bf16", "fp16") and B == 256 and os.path.exists(tf):
             tj = json.load(open(tf))
             if dom in tj:
                 traffic, traffic_src = tj[dom]["dram_bytes_per_step"], "profiles/r1_traffic_bf16.json: " + tj["_source"]
@@ -372,7 +372,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16"}.get(precision, "f32"),
             "data": "synthetic", "config": workload_config(args, precision), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }

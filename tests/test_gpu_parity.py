@@ -166,7 +166,7 @@ def test_session_stitching_matches_reference_golden():
         assert torch.equal(out["probs"].argmax(-1).to(torch.uint8), g[f"{tag}_probs_argmax"])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_bulk_runner_equals_direct_calls(precision):
     """Pipelined H2D / forward / D2H over pinned host batches returns exactly what direct probs() calls return."""
     from oracle import synth
@@ -211,27 +211,30 @@ def test_bulk_runner_pcm16_input_matches_float_input():
         assert torch.equal(got[k], ref[k].cpu()), k
 
 
-BF16_TOL = dict(probs=5e-3, vad=2e-2, p_now=2e-3, p_future=2e-3, logits=0.1)
+# tensor-core modes vs the reference's fp32 outputs; fp16 operands carry 3 more mantissa bits
+TC_TOL = {"bf16": dict(probs=5e-3, vad=2e-2, p_now=2e-3, p_future=2e-3, logits=0.1, agree=0.95),
+          "fp16": dict(probs=1e-3, vad=4e-3, p_now=5e-4, p_future=5e-4, logits=2e-2, agree=0.99)}
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
 @pytest.mark.parametrize("name", CASE_NAMES)
-def test_bf16_within_stated_tolerance_of_reference_golden(name):
-    """bf16 tensor-core mode vs the reference's fp32 outputs."""
+def test_tensor_modes_within_stated_tolerance_of_reference_golden(name, precision):
     recipe, g = load_golden(name)
     sd, wav = golden_inputs(recipe, g)
-    m = _model(sd, "bf16")
+    m = _model(sd, precision)
+    tol = TC_TOL[precision]
     x = wav.cuda()
     fwd = m(x)
     out = m.probs(x)
-    assert _maxerr(fwd["logits"], g["logits"]) <= BF16_TOL["logits"]
+    assert _maxerr(fwd["logits"], g["logits"]) <= tol["logits"]
     for k in ["probs", "vad", "p_now", "p_future"]:
         if k in g:
-            assert _maxerr(out[k], g[k]) <= BF16_TOL[k], k
+            assert _maxerr(out[k], g[k]) <= tol[k], k
     agree = (fwd["logits"].argmax(-1).cpu() == g["logits"].argmax(-1)).float().mean().item()
-    assert agree >= 0.95, agree
+    assert agree >= tol["agree"], agree
 
 
-@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "fp32"])
 def test_full_size_batch_is_item_independent(precision):
     """BASELINE configs[1] at full size (B=256 x 20 s): chunks are independent, so every item of the big batch must
     equal the same item run in a batch of 2 (bit-identical: no kernel mixes sequences, none is order-dependent)."""

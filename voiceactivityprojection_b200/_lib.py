@@ -8,8 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvapb.so")
 
-MODE_FP32, MODE_BF16 = 0, 1
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+MODE_FP32, MODE_BF16, MODE_FP16 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "fp16": MODE_FP16}
 
 # every symbol include/vapb.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t

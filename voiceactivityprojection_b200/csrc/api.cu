@@ -389,7 +389,7 @@ struct Aux {  // api-level scratch appended to the path workspace
 int plan_all(const Model& m, int batch, int64_t n_samples, int mode, Geometry* g, size_t* path_bytes, Aux* aux,
              std::string* err) {
   if (batch < 1 || batch > 16384) { *err = "batch out of range"; return VAPB_E_INVALID; }
-  if (mode != VAPB_MODE_FP32 && mode != VAPB_MODE_BF16) { *err = "unknown mode"; return VAPB_E_INVALID; }
+  if (mode != VAPB_MODE_FP32 && mode != VAPB_MODE_BF16 && mode != VAPB_MODE_FP16) { *err = "unknown mode"; return VAPB_E_INVALID; }
   if (n_samples < 1 || make_geometry(batch, n_samples, g) != 0 || g->T < 1) {
     *err = "n_samples too small for the conv chain";
     return VAPB_E_INVALID;
@@ -410,7 +410,7 @@ int run_forward(Model& m, cudaStream_t st, const float* wav, const Geometry& g, 
                 float* vad_logits, float* vad_sig) {
   const float* comb = nullptr;
   return mode == VAPB_MODE_FP32 ? forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb)
-                                : forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb);
+                                : forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, mode == VAPB_MODE_FP16);
 }
 
 }  // namespace
@@ -519,7 +519,7 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
   if (rc) return fail(m, VAPB_E_INVALID, std::string("unknown stage ") + name);
   if (out_elems < (size_t)ref.nseq * ref.rows_per_seq * kDim) return fail(m, VAPB_E_INVALID, "stage output too small");
   CUDA_OK(m, cudaSetDevice(m.device));
-  m.launches += launch_to_f32((cudaStream_t)stream, ref.ptr, ref.is_bf16, ref.map, ref.nseq, ref.rows_per_seq, out, ref.blocked);
+  m.launches += launch_to_f32((cudaStream_t)stream, ref.ptr, ref.is_bf16 ? (mode == VAPB_MODE_FP16 ? 2 : 1) : 0, ref.map, ref.nseq, ref.rows_per_seq, out, ref.blocked);
   CUDA_OK(m, cudaPeekAtLastError());
   return VAPB_OK;
 }

@@ -9,7 +9,10 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "model.h"
+#include "tc_common.cuh"
 
 namespace vapb {
 
@@ -125,22 +128,50 @@ struct Ctx {
   }
 };
 
-std::vector<bf16> to_bf16(const std::vector<float>& v) {
+// 16-bit image of a weight vector: bf16 (fmt 0) or fp16 (fmt 1); both travel as 2-byte words
+std::vector<bf16> to_16(const std::vector<float>& v, int fp16) {
   std::vector<bf16> o(v.size());
-  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (fp16) {
+      const __half h = __float2half_rn(v[i]);
+      memcpy(&o[i], &h, 2);
+    } else {
+      o[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
   return o;
 }
+struct Fp16Scope {  // the 16-bit format of every launch issued by this thread while it lives
+  int prev;
+  explicit Fp16Scope(int v) : prev(g_fp16) { g_fp16 = v; }
+  ~Fp16Scope() { g_fp16 = prev; }
+};
 
 }  // namespace
 
+static int prepare_fmt(Model& m, State16* s, int fp16);
+
 int bf16_prepare(Model& m) {
-  State16* s = new State16();
+  State16* s = new State16[2];  // [0] bf16, [1] fp16 images of the same weights
+  for (int f = 0; f < 2; ++f) {
+    const int rc = prepare_fmt(m, &s[f], f);
+    if (rc) {
+      for (int k = 0; k < f; ++k) cudaFree(s[k].arena);
+      delete[] s;
+      return rc;
+    }
+  }
+  m.bf16_state = s;
+  return 0;
+}
+
+static int prepare_fmt(Model& m, State16* s, int fp16) {
   std::vector<char> host;
   struct Fix { const bf16** slot; size_t off; };
   std::vector<Fix> fixes;
   auto put = [&](const bf16** slot, const std::vector<float>& v) {
     const size_t off = (host.size() + 1023) / 1024 * 1024;
-    std::vector<bf16> b = to_bf16(v);
+    std::vector<bf16> b = to_16(v, fp16);
     host.resize(off + b.size() * 2);
     memcpy(host.data() + off, b.data(), b.size() * 2);
     fixes.push_back({slot, off});
@@ -201,28 +232,28 @@ int bf16_prepare(Model& m) {
   }
   if (cudaMalloc(&s->arena, host.size()) != cudaSuccess ||
       cudaMemcpy(s->arena, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-    m.err = "bf16 weight arena: CUDA allocation/copy failed";
-    delete s;
+    m.err = "16-bit weight arena: CUDA allocation/copy failed";
     return -3;
   }
   for (auto& f : fixes) *f.slot = reinterpret_cast<const bf16*>(static_cast<char*>(s->arena) + f.off);
-  m.bf16_state = s;
   return 0;
 }
 
 void bf16_release(Model& m) {
   State16* s = static_cast<State16*>(m.bf16_state);
   if (!s) return;
-  if (s->arena) cudaFree(s->arena);
-  delete s;
+  for (int f = 0; f < 2; ++f)
+    if (s[f].arena) cudaFree(s[f].arena);
+  delete[] s;
   m.bf16_state = nullptr;
 }
 
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g) { return make_plan(m, g).bytes; }
 
 int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float**) {
-  const State16& s = *static_cast<const State16*>(m.bf16_state);
+                 float* vad_logits, float* vad_sig, const float**, int fp16) {
+  const State16& s = static_cast<const State16*>(m.bf16_state)[fp16 ? 1 : 0];
+  Fp16Scope fmt_scope(fp16 ? 1 : 0);
   const Plan16 p = make_plan(m, g);
   const Weights& w = m.w32;  // fp32 vectors (biases, norm affine, slopes, va head) and conv0
   Ctx cx{m, st};
@@ -467,12 +498,12 @@ int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& n
   ref->map = RowMap{g.T * kDim, kDim};
   if (name == "conv") {
     ref->ptr = ws + p.act4;
-    ref->is_bf16 = 1;
+    ref->is_bf16 = 1;  // 16-bit buffer; api.cu turns this into the mode's format
     ref->rows_per_seq = (int)g.L[4];
     ref->map = RowMap{g.L[4] * kDim, kDim};
   } else if (name == "ar") {
     ref->ptr = reinterpret_cast<const bf16*>(ws + p.rnn[(m.ar_layers - 1) & 1]) + 4 * kDim;
-    ref->is_bf16 = 1;
+    ref->is_bf16 = 1;  // 16-bit buffer; api.cu turns this into the mode's format
     ref->rows_per_seq = (int)g.L[4];
     ref->map = RowMap{p.rnn_lpad * kDim, kDim};
   } else if (name == "enc") {

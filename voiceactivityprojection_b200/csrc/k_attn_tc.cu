@@ -49,6 +49,7 @@ struct alignas(64) AttnParams {
   __nv_bfloat16* out;      // (nseq*T, 256)
   const float* slopes;     // [n_heads]
   int nseq, T, nqt, head_pairs, n_items, cross;
+  int fp16;
   long long* dbg;  // optional [64][8] SM-clock samples of CTA 0 (diagnostics, tools/attn_probe.py)
   int pair_major;  // large batches: a CTA walks all query tiles of one (sequence, head pair) back to back, so the
                    // pair's K/V (re-read once per query tile) stay in L2; small batches: spread single tiles
@@ -175,8 +176,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   } else if (warp == 1) {
     // ===== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major (d contiguous)
+      const uint32_t idesc_qk = make_idesc_16(128, 128, 0, 0, p.fp16);
+      const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, p.fp16);  // B = V is MN-major (d contiguous)
       uint32_t n_item = 0, kvc[2] = {0, 0}, pc[2] = {0, 0};
       auto issue_qk = [&](int s) {
         const int st = kvc[s] & 1;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 if (i + 1 > lane) p1 = 0.f;
                 ps0 += p0;
                 ps1 += p1;
-                pk[i >> 1] = pack_bf16(p0, p1);
+                pk[i >> 1] = pack16(p0, p1, p.fp16);
               }
             } else {
 #pragma unroll
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
                 ps0 += p0;
                 ps1 += p1;
-                pk[i >> 1] = pack_bf16(p0, p1);
+                pk[i >> 1] = pack16(p0, p1, p.fp16);
               }
             }
           } else {
@@ -358,10 +359,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
-            u.x = pack_bf16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv);
-            u.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
-            u.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
-            u.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
+            u.x = pack16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv, p.fp16);
+            u.y = pack16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv, p.fp16);
+            u.z = pack16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv, p.fp16);
+            u.w = pack16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv, p.fp16);
             *reinterpret_cast<uint4*>(dst + 8 * i) = u;
           }
         }
@@ -408,6 +409,7 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
   p.n_items = p.nqt * nseq * p.head_pairs;
   p.cross = cross;
   p.dbg = dbg;
+  p.fp16 = g_fp16;
   p.pair_major = nseq * p.head_pairs >= 2 * n_sm;
   static bool configured = false;
   if (!configured) {

@@ -7,6 +7,8 @@
 // registers and the frame's mean/variance is two warp-shuffle reductions.
 // Output is channels-last (seq, pad + frame, 256) so that conv1's implicit-GEMM
 // rows are contiguous spans of it.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vapb {
@@ -125,7 +127,7 @@ int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long 
 }
 
 // Stage export for diagnostics: any activation -> dense fp32 (nseq, rows, 256).
-template <bool SRC_BF16>
+template <int SRC_FMT>  // 0 fp32, 1 bf16, 2 fp16
 __global__ void to_f32_kernel(const void* __restrict__ src, RowMap map, int rows_per_seq, float* __restrict__ dst,
                               long long total_rows, int blocked) {
   const long long r = (long long)blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
@@ -134,9 +136,12 @@ __global__ void to_f32_kernel(const void* __restrict__ src, RowMap map, int rows
   const long long off = blocked ? (((r >> 7) * 64 + (c4 >> 2)) * 128 + (r & 127)) * 4
                                 : (r / rows_per_seq) * map.seq_stride + (r % rows_per_seq) * map.row_stride + c4;
   float4 v;
-  if (SRC_BF16) {
+  if (SRC_FMT == 1) {
     const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src) + off;
     v = make_float4(__bfloat162float(s[0]), __bfloat162float(s[1]), __bfloat162float(s[2]), __bfloat162float(s[3]));
+  } else if (SRC_FMT == 2) {
+    const __half* s = reinterpret_cast<const __half*>(src) + off;
+    v = make_float4(__half2float(s[0]), __half2float(s[1]), __half2float(s[2]), __half2float(s[3]));
   } else {
     v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
   }
@@ -147,10 +152,12 @@ int launch_to_f32(cudaStream_t st, const void* src, int src_bf16, RowMap src_map
                   float* dst, int src_blocked) {
   const long long total = (long long)nseq * rows_per_seq;
   const unsigned grid = (unsigned)((total + 3) / 4);
-  if (src_bf16)
-    to_f32_kernel<true><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, 0);
+  if (src_bf16 == 2)
+    to_f32_kernel<2><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, 0);
+  else if (src_bf16)
+    to_f32_kernel<1><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, 0);
   else
-    to_f32_kernel<false><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, src_blocked);
+    to_f32_kernel<0><<<grid, 256, 0, st>>>(src, src_map, rows_per_seq, dst, total, src_blocked);
   return 1;
 }
 

@@ -47,6 +47,7 @@ struct alignas(64) Conv0TcParams {
   Conv0Stats cs;
   int batch, seq0, nseq, tiles_per_seq;
   long long n_samples, L0;
+  int fp16;
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -229,10 +230,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
           const float v1 = fmaf(__uint_as_float(r[c & 1][i + 1]), rstd, b.y);
           const float v2 = fmaf(__uint_as_float(r[c & 1][i + 2]), rstd, b.z);
           const float v3 = fmaf(__uint_as_float(r[c & 1][i + 3]), rstd, b.w);
-          __nv_bfloat162 q0 = __hmax2(__floats2bfloat162_rn(v0, v1), __floats2bfloat162_rn(0.f, 0.f));
-          __nv_bfloat162 q1 = __hmax2(__floats2bfloat162_rn(v2, v3), __floats2bfloat162_rn(0.f, 0.f));
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&q0);
-          pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&q1);
+          pk[i >> 1] = pack16(fmaxf(v0, 0.f), fmaxf(v1, 0.f), p.fp16);
+          pk[(i >> 1) + 1] = pack16(fmaxf(v2, 0.f), fmaxf(v3, 0.f), p.fp16);
         }
         // staging tile: 128 rows x 64 B, SWIZZLE_64B (chunk j of row r at r*64 + ((j ^ (r/2 & 3)) << 4)), two buffers
         if (leader) bulk_wait_read<1>();
@@ -287,6 +286,7 @@ int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_sa
   p.tiles_per_seq = (int)((L0 + 127) / 128);
   p.n_samples = n_samples;
   p.L0 = L0;
+  p.fp16 = g_fp16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM) != cudaSuccess) {

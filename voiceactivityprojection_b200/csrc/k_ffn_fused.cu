@@ -50,6 +50,7 @@ struct alignas(64) FfnParams {
   float* x_out;         // row-blocked fp32
   int has_ln;
   const float *g2, *b2;
+  int fp16;
   long long* dbg;  // optional [32 tiles][16] SM-clock samples of CTA 0's first epilogue thread (tools/ffn_probe.py)
 };
 
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   } else if (warp == 1) {
     // ===== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc1 = make_idesc_16(128, 128, 0, 0, p.fp16);
       uint32_t wc = 0, it = 0, hcnt[2] = {0, 0} /*h_full phases seen per buffer*/, n_o = 0;
       auto gemm1 = [&](int b) {  // ACC_H[b] = Z W1[chunk]^T
         for (int kb = 0; kb < 4; ++kb, ++wc) {
@@ -239,10 +240,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 u;
-        u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        u.x = pack16(v[8 * j], v[8 * j + 1], p.fp16);
+        u.y = pack16(v[8 * j + 2], v[8 * j + 3], p.fp16);
+        u.z = pack16(v[8 * j + 4], v[8 * j + 5], p.fp16);
+        u.w = pack16(v[8 * j + 6], v[8 * j + 7], p.fp16);
         *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
       }
       fence_proxy_async();
@@ -295,10 +296,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
           for (int e = 0; e < 4; ++e)
             y[e] = gelu_poly2_f(make_float2(__uint_as_float(r[8 * q + 2 * e]), __uint_as_float(r[8 * q + 2 * e + 1])));
           uint4 u;
-          u.x = pack_bf16(y[0].x, y[0].y);
-          u.y = pack_bf16(y[1].x, y[1].y);
-          u.z = pack_bf16(y[2].x, y[2].y);
-          u.w = pack_bf16(y[3].x, y[3].y);
+          u.x = pack16(y[0].x, y[0].y, p.fp16);
+          u.y = pack16(y[1].x, y[1].y, p.fp16);
+          u.z = pack16(y[2].x, y[2].y, p.fp16);
+          u.w = pack16(y[3].x, y[3].y, p.fp16);
           *reinterpret_cast<uint4*>(rowp + ((((uint32_t)((qtr & 1) * 4 + q)) ^ sw128) << 4)) = u;
         }
         fence_proxy_async();
@@ -415,6 +416,7 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
   p.g2 = g2;
   p.b2 = b2;
   p.dbg = dbg;
+  p.fp16 = g_fp16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {

@@ -48,6 +48,7 @@ struct alignas(64) G2Params {
   int norm1;
   const float *g1, *b1;
   int act;
+  int fp16;
 };
 
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_leader, int c0, int c1, int c2) {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_2sm_kernel(const __grid_co
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, 256, 0, 0);
+      const uint32_t idesc = make_idesc_16(256, 256, 0, 0, p.fp16);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters) {
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_2sm_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-            u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            u.x = pack16(v[8 * j], v[8 * j + 1], p.fp16);
+            u.y = pack16(v[8 * j + 2], v[8 * j + 3], p.fp16);
+            u.z = pack16(v[8 * j + 4], v[8 * j + 5], p.fp16);
+            u.w = pack16(v[8 * j + 6], v[8 * j + 7], p.fp16);
             *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
           }
           fence_proxy_async();
@@ -319,6 +320,7 @@ int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string*
   p.bias = e.bias;
   p.norm1 = e.norm1; p.g1 = e.g1; p.b1 = e.b1;
   p.act = e.act;
+  p.fp16 = g_fp16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM) != cudaSuccess) {

@@ -76,6 +76,7 @@ struct alignas(64) LinParams {
   int has_o1_bf16;
   int norm2;
   const float *g2, *b2;
+  int fp16;  // 16-bit operand / output format: 0 bf16, 1 fp16
 };
 
 // GELU(erf) for two values with packed fp32 FMAs and no MUFU: gelu(x) = relu(x) + g(|x|), where
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(LBM, LBN, 0, 0);
+      const uint32_t idesc = make_idesc_16(LBM, LBN, 0, 0, p.fp16);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       if (WRES && tile_first < num_tiles) {
@@ -262,10 +263,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 u;
-        u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        u.x = pack16(v[8 * j], v[8 * j + 1], p.fp16);
+        u.y = pack16(v[8 * j + 2], v[8 * j + 3], p.fp16);
+        u.z = pack16(v[8 * j + 4], v[8 * j + 5], p.fp16);
+        u.w = pack16(v[8 * j + 6], v[8 * j + 7], p.fp16);
         *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
       }
       fence_proxy_async();
@@ -519,6 +520,7 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
   p.f32_mode = a.out1_f32 ? f32_mode : 0;
   p.has_o1_bf16 = a.out1_bf16 != nullptr;
   p.norm2 = e.norm2; p.g2 = e.g2; p.b2 = e.b2;
+  p.fp16 = g_fp16;
   const int need = ((e.bias || e.norm1 != NORM_NONE) ? F_PRE : 0) | (e.act != ACT_NONE ? F_ACT : 0) |
                    (e.resid ? F_RESID : 0) | (e.accumulate ? F_ACC : 0) | (p.f32_mode == 1 ? F_F32B : 0) |
                    (p.f32_mode == 2 ? F_F32R : 0) | (p.has_o1_bf16 ? F_O1B : 0) | (e.norm2 != NORM_NONE ? F_N2 : 0);

@@ -72,6 +72,7 @@ struct alignas(64) RnnParams {
   CUtensorMap tma_out;  // (256 k, T, nseq) bf16, no swizzle, box (32, 1, NB)
   const float* bias;    // [8][128]
   int nseq, T;
+  int fp16;
   long long* dbg;  // optional [steps][8] clock samples of cluster 0 / rank 0 / group 0 (diagnostics)
 };
 
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(RnnCfg<NG, NB>::THREADS, 1) rnn_tc_kernel(cons
     // streams at 64 B/clk), so the input half W_ih x_t is issued ONCE per step for all groups (N = NG*NB)
     // and only the recurrent half W_hh h_{t-1} is per group.
     if (lane == 0) {
-      constexpr uint32_t idesc_h = make_idesc_bf16(128, NB, 0, 0);
-      constexpr uint32_t idesc_x = make_idesc_bf16(128, NG * NB, 0, 0);
+      const uint32_t idesc_h = make_idesc_16(128, NB, 0, 0, p.fp16);
+      const uint32_t idesc_x = make_idesc_16(128, NG * NB, 0, 0, p.fp16);
       auto acc_col = [&](int t, int g) { return tmem_base + R_ACC_COL + (t & 1) * (NG * NB) + g * NB; };
       auto x_part = [&](int t) {
         const int s = t % RXST;
@@ -283,16 +284,16 @@ __global__ void __launch_bounds__(RnnCfg<NG, NB>::THREADS, 1) rnn_tc_kernel(cons
       }
       if (UPT == 4) {
         uint2 pk;
-        pk.x = pack_bf16(h[0], h[1]);
-        pk.y = pack_bf16(h[2], h[3]);
+        pk.x = pack16(h[0], h[1], p.fp16);
+        pk.y = pack16(h[2], h[3], p.fp16);
         *reinterpret_cast<uint2*>(stg_gen + par * R_SLICE + stg_off) = pk;
         *reinterpret_cast<uint2*>(ostg_gen + par * Cfg::OSTG + ostg_off) = pk;
       } else {
         uint4 pk;
-        pk.x = pack_bf16(h[0], h[1]);
-        pk.y = pack_bf16(h[2], h[3]);
-        pk.z = pack_bf16(h[4 % UPT], h[5 % UPT]);
-        pk.w = pack_bf16(h[6 % UPT], h[7 % UPT]);
+        pk.x = pack16(h[0], h[1], p.fp16);
+        pk.y = pack16(h[2], h[3], p.fp16);
+        pk.z = pack16(h[4 % UPT], h[5 % UPT], p.fp16);
+        pk.w = pack16(h[6 % UPT], h[7 % UPT], p.fp16);
         *reinterpret_cast<uint4*>(stg_gen + par * R_SLICE + stg_off) = pk;
         *reinterpret_cast<uint4*>(ostg_gen + par * Cfg::OSTG + ostg_off) = pk;
       }
@@ -403,6 +404,7 @@ int launch_rnn_tc(cudaStream_t st, int kind, const __nv_bfloat16* x, long long x
                   int nseq, int T, std::string* err, long long* dbg, int shape) {
   RnnParams p{};
   p.dbg = dbg;
+  p.fp16 = g_fp16;
   p.w_cat = w_cat;
   p.bias = bias;
   p.nseq = nseq;

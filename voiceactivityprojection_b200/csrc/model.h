@@ -131,7 +131,7 @@ int bf16_prepare(Model& m);   // pack bf16 weights after the fp32 arena is built
 void bf16_release(Model& m);
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g);
 int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float** comb_out);
+                 float* vad_logits, float* vad_sig, const float** comb_out, int fp16);
 int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
 }  // namespace vapb

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -151,6 +152,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+// The tensor path stores 16-bit operands as bf16 or as fp16 (same bytes, same kernels, same TMA maps): only the
+// packing below and the a/b format fields of the instruction descriptor differ. fp16 has 3 more mantissa bits (every
+// activation of this model is O(1..100) after a norm, far inside its range), which buys ~8x lower error at equal speed.
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fp16) {
+  if (fp16) {
+    __half2 p = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+  }
+  return pack_bf16(a, b);
+}
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 
 // ---- more TMA / cluster primitives (recurrence and attention kernels) ------------
@@ -255,6 +270,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint
 }
 
 }  // namespace tc
+
+// Host side: the 16-bit format of the launches issued by this thread (set by forward_bf16 for the duration of a call;
+// the unit-test hooks leave it at 0 = bf16). Launchers copy it into their kernel parameters.
+extern thread_local int g_fp16;
 
 // ---- host: tensor maps ----------------------------------------------------------
 // Tiled tensor map over bf16 data, 128-byte swizzle. dims / strides are in

@@ -12,8 +12,9 @@ Differences a caller can see:
     inferred from the state dict in `load_state_dict`.
   * `forward(..., attention=True)` raises NotImplementedError (attention maps are
     never materialised).
-  * `precision="fp32"` (default; CUDA-core FMA, parity with the reference) or
-    `"bf16"` (tcgen05 tensor cores) — constructor keyword, attribute, or env
+  * `precision="fp32"` (default; CUDA-core FMA, parity with the reference),
+    `"bf16"` or `"fp16"` (tcgen05 tensor cores; same kernels and speed, fp16
+    operands give ~8x lower error) — constructor keyword, attribute, or env
     VAPB_PRECISION.
 """
 from __future__ import annotations
