@@ -212,7 +212,7 @@ def test_bulk_runner_pcm16_input_matches_float_input():
 
 
 # tensor-core modes vs the reference's fp32 outputs; fp16 operands carry 3 more mantissa bits
-TC_TOL = {"bf16": dict(probs=5e-3, vad=2e-2, p_now=2e-3, p_future=2e-3, logits=0.1, agree=0.95),
+TC_TOL = {"bf16": dict(probs=5e-3, vad=3e-2, p_now=2e-3, p_future=2e-3, logits=0.1, agree=0.95),
           "fp16": dict(probs=1e-3, vad=4e-3, p_now=5e-4, p_future=5e-4, logits=2e-2, agree=0.99)}
 
 
@@ -260,3 +260,24 @@ def test_full_size_batch_is_item_independent(precision):
     # feeds only the VAP head, does not), so swapping the input channels swaps the VAD columns
     sw = m.probs(wav[:2].flip(1).contiguous())
     assert _maxerr(sw["vad"], big["vad"][:2].flip(-1).cpu()) <= (1e-5 if precision == "fp32" else 3e-2)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_tensor_modes_on_ragged_lengths_and_batches(precision):
+    """Lengths that are not multiples of 320 / 128-row tiles, odd batches, GRU and 2-layer recurrences, through every
+    TMA-tiled kernel of the tensor path (partial tiles, clipped stores, CTA-pair tiles with an empty second half)."""
+    from oracle import synth
+    from oracle import vap_oracle as O
+
+    tol = TC_TOL[precision]
+    for seed, mode, layers, batch, n in [(31, "LSTM", 1, 3, 33333), (32, "GRU", 1, 1, 32159), (33, "LSTM", 2, 2, 48001),
+                                         (34, "GRU", 2, 5, 81234)]:
+        sd = synth.make_state_dict(seed, mode, layers, 2.0)
+        m = _model(sd, precision)
+        wav = synth.make_waveform(batch, n, 9, "turns")
+        ref = O.probs(sd, wav)
+        out = m.probs(wav.cuda())
+        for k in ["probs", "vad", "p_now", "p_future"]:
+            assert out[k].shape == ref[k].shape
+            assert torch.isfinite(out[k]).all()
+            assert _maxerr(out[k], ref[k]) <= tol[k], (precision, mode, layers, batch, n, k, _maxerr(out[k], ref[k]))
