@@ -281,3 +281,34 @@ def test_tensor_modes_on_ragged_lengths_and_batches(precision):
             assert out[k].shape == ref[k].shape
             assert torch.isfinite(out[k]).all()
             assert _maxerr(out[k], ref[k]) <= tol[k], (precision, mode, layers, batch, n, k, _maxerr(out[k], ref[k]))
+
+
+def test_run_cli_writes_reference_json(tmp_path):
+    """python -m voiceactivityprojection_b200.run on a wav file + a saved state dict reproduces the JSON the
+    reference's run.py would write (keys, order, nesting, values within the fp32 tolerance)."""
+    import json
+
+    from scipy.io import wavfile
+
+    from voiceactivityprojection_b200.run import main
+
+    recipe, g = load_golden("example_wav_T117")
+    sd, wav = golden_inputs(recipe, g)  # (1, 2, 37392): the example wav at 16 kHz + the silent second channel
+    pcm = (wav[0, 0] * 32768.0).round().clamp(-32768, 32767).to(torch.int16).numpy()
+    wav_path, sd_path, out_path = str(tmp_path / "a.wav"), str(tmp_path / "sd.pt"), str(tmp_path / "out.json")
+    wavfile.write(wav_path, 16000, pcm)  # mono, like the reference's example: run.py appends the zero channel
+    torch.save(sd, sd_path)
+    main(["--audio", wav_path, "--state_dict", sd_path, "--filename", out_path])
+    d = json.load(open(out_path))
+    assert list(d.keys()) == ["probs", "vad", "p_now", "p_future", "H", "loss"]
+    # the wav round trip quantises the waveform to int16, so compare with our own forward on the same samples ...
+    m = _model(sd)
+    x = torch.from_numpy(pcm.astype("float32") / 32768.0)[None, None]
+    ref = m.probs(torch.cat((x, torch.zeros_like(x)), dim=1).cuda())
+    for k in d:
+        got = torch.tensor(d[k])
+        assert got.shape == ref[k].shape, k
+        assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(ref[k].cpu())), k
+    # ... and with the reference's golden output on the unquantised waveform (int16 quantisation noise ~1.5e-5 per sample)
+    assert _maxerr(torch.tensor(d["p_now"]), g["p_now"]) <= 2e-3
+    assert torch.tensor(d["probs"]).shape == g["probs"].shape == (1, 117, 256)
