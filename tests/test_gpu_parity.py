@@ -312,3 +312,29 @@ def test_run_cli_writes_reference_json(tmp_path):
     # ... and with the reference's golden output on the unquantised waveform (int16 quantisation noise ~1.5e-5 per sample)
     assert _maxerr(torch.tensor(d["p_now"]), g["p_now"]) <= 2e-3
     assert torch.tensor(d["probs"]).shape == g["probs"].shape == (1, 117, 256)
+
+
+def test_streaming_rolling_window_matches_reference_loop():
+    """sds/run_sds.py semantics: roll the window by each int16 chunk, recompute the whole window, publish
+    mean(p_now[-25:, 0]); compared with the oracle on the same rolled float window."""
+    from oracle import synth
+    from oracle import vap_oracle as O
+    from voiceactivityprojection_b200.streaming import StreamingVAP
+
+    sd = synth.make_state_dict(5, "LSTM", 1, 2.0)
+    m = _model(sd)
+    s = StreamingVAP(m, context_time=2.5, tt_time=0.5)  # short context keeps the CPU oracle cheap; T = 125 > 100
+    g = torch.Generator().manual_seed(1)
+    ring = torch.zeros(1, 2, s.n_samples)
+    for n in (4000, 16000, 1234, 40000, 50000):  # the last chunk is longer than the window
+        pcm = (torch.randn(2 * n, generator=g) * 3000).round().clamp(-32768, 32767).to(torch.int16)
+        s.add_audio_bytes(pcm.numpy().tobytes())
+        ch = pcm.view(n, 2).t().float() / 32768.0
+        k = min(n, s.n_samples)
+        ring = ring.roll(-k, -1)
+        ring[0, :, -k:] = ch[:, -k:]
+        assert torch.equal(s.x.cpu(), ring)
+    got = s.step()
+    ref = O.probs(sd, ring)
+    assert _maxerr(got["out"]["p_now"], ref["p_now"]) <= 1e-5
+    assert abs(got["p_now_mean"] - ref["p_now"][0, -25:, 0].mean().item()) <= 1e-5
