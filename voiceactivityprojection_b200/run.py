@@ -6,7 +6,7 @@ Same flags (`--audio/-a`, `--state_dict/-sd`, `--checkpoint/-c`, `--filename/-f`
 `--chunk_time`, `--step_time`, `--chunk`, `--plot`, all `--vap_*`), same JSON:
 keys `probs, vad, p_now, p_future, H, loss` as nested lists. Files longer than
 160 s switch to 25 s / 5 s chunked extraction like the reference (run.py:223-229).
-`--precision fp32|bf16` is the one addition. CUDA is required.
+`--precision fp32|bf16|fp16` is the one addition. CUDA is required.
 """
 from __future__ import annotations
 
@@ -33,7 +33,7 @@ def get_args(argv=None):
     parser.add_argument("--step_time", type=float, default=5, help="Increment to process in a step")
     parser.add_argument("--chunk", action="store_true", help="Process the audio in chunks (longer > 164s on 24Gb GPU audio)")
     parser.add_argument("--plot", action="store_true", help="Visualize output (matplotlib)")
-    parser.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    parser.add_argument("--precision", default=None, choices=["fp32", "bf16", "fp16"])
     parser, _ = VapConfig.add_argparse_args(parser, [])
     args = parser.parse_args(argv)
     return args, VapConfig.args_to_conf(args)
