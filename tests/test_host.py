@@ -163,3 +163,15 @@ def test_vad_postprocessing_run_length_filters():
     o = vad_omit_spikes(v.clone(), max_omit_time=0.02, frame_hz=50)    # 1-frame activity removed
     assert o[:, 1].tolist() == [0, 0, 0, 0, 0, 0, 0]
     assert o[:, 0].tolist() == [0, 0, 1, 1, 0, 0, 0]
+
+
+def test_load_state_dict_strict_false_drops_foreign_keys():
+    from oracle import synth
+    from voiceactivityprojection_b200 import VapConfig, VapGPT
+
+    sd = dict(synth.make_state_dict(0))
+    sd["VAP.codebook.emb.weight"] = torch.zeros(256, 8)
+    sd["some_callback.state"] = torch.zeros(3)
+    m = VapGPT(VapConfig())
+    m.load_state_dict(sd, strict=False)
+    assert "some_callback.state" not in m.state_dict() and "vap_head.weight" in m.state_dict()

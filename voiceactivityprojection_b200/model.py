@@ -123,6 +123,11 @@ class VapGPT(nn.Module):
         GRU, depth) is taken from the tensor shapes; errors are raised with the
         library's message, in nn.Module.load_state_dict's wording."""
         sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
+        if not strict:
+            # nn.Module.load_state_dict(strict=False) ignores keys the module does not own (the reference loads older
+            # Lightning checkpoints this way, vap/model.py:455); missing weights still cannot be invented
+            known = ("encoder.", "ar_channel.", "ar.", "objective.codebook.", "va_classifier.", "vap_head.")
+            sd = {k: v for k, v in sd.items() if k.startswith(known)}
         self._release()
         self._sd = sd
         if self._device.type == "cuda":
