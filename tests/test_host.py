@@ -175,3 +175,46 @@ def test_load_state_dict_strict_false_drops_foreign_keys():
     m = VapGPT(VapConfig())
     m.load_state_dict(sd, strict=False)
     assert "some_callback.state" not in m.state_dict() and "vap_head.weight" in m.state_dict()
+
+
+def _reference_extractor_loop(wav, model, skip_last):
+    """vap/extraction.py:182-258 restated: range(1, len(folds[1:])) skips the last unfold window."""
+    cs, ss, sf = 400000, 80000, 250
+    folds = wav.unfold(dimension=-1, size=cs, step=ss).permute(2, 0, 1, 3)
+    out = model.probs(folds[0])
+    keys = ["vad", "p_now", "p_future", "probs", "H"]
+    stop = len(folds[1:]) if skip_last else len(folds)
+    for ii in range(1, stop):
+        o = model.probs(folds[ii])
+        for k in keys:
+            out[k] = torch.cat([out[k], o[k][:, -sf:]], dim=1)
+    expected = round(round(wav.shape[-1] / 16000, 2) * 50)
+    if expected != out["p_now"].shape[1]:
+        om = expected - out["p_now"].shape[1]
+        o = model.probs(wav[..., -cs:])
+        for k in keys:
+            out[k] = torch.cat([out[k], o[k][:, -om:]], dim=1)
+    return out
+
+
+@pytest.mark.parametrize("skip_last", [False, True])
+def test_vap_extractor_stitching_and_minimal_outputs(tmp_path, skip_last):
+    from voiceactivityprojection_b200.extraction import VapExtractor, get_minimal_output_json, write_minimal_csv
+
+    m = _FakeModel()
+    m.probs_orig = m.probs
+    ex = VapExtractor(model=m, max_batch=3, compat_skip_last_fold=skip_last)
+    ex.device = "cpu"
+    wav = torch.randn(1, 2, int(47.3 * 16000), generator=torch.Generator().manual_seed(3))
+    got = ex.step_extraction(wav)
+    ref = _reference_extractor_loop(wav, m, skip_last)
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+    mo = get_minimal_output_json(got, vad=None)
+    assert list(mo.keys()) == ["p_now", "p_future", "model_vad0", "model_vad1", "H", "loss"]
+    assert len(mo["p_now"]) == got["p_now"].shape[1] and len(mo["loss"]) == got["loss"].shape[1]
+    p = str(tmp_path / "min.csv")
+    write_minimal_csv(mo, p)
+    lines = open(p).read().strip().splitlines()
+    assert lines[0] == "p_now,p_future,model_vad0,model_vad1,H,loss" and len(lines) == 1 + len(mo["p_now"])
+    assert lines[-1].endswith(",0")  # loss is shorter than the frame axis: padded with 0 like json_data_to_df
