@@ -92,16 +92,20 @@ rnn_f32_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_t,
 template <int KIND, typename TOut>
 static int launch_kind(cudaStream_t st, const float* xproj, const float* whh_t, const float* bhn, TOut* out,
                        long long out_seq_stride, int nseq, int T, int n_sm) {
-  // sequences per CTA: as few as keeps every SM busy (W_hh streaming is per CTA)
+  // sequences per CTA: as few as keeps every SM busy, but every CTA streams all of W_hh (1 MB) from L2 each step and
+  // the kernel is bound by that aggregate L2 traffic, so large batches trade CTAs for reuse (8 sequences per CTA)
   int nb = 1;
   while (nb < 4 && (nseq + nb - 1) / nb > n_sm) nb *= 2;
+  if (nb == 4 && nseq >= 8 * 48) nb = 8;
   const unsigned grid = (unsigned)((nseq + nb - 1) / nb);
   if (nb == 1)
     rnn_f32_kernel<KIND, 1, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
   else if (nb == 2)
     rnn_f32_kernel<KIND, 2, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
-  else
+  else if (nb == 4)
     rnn_f32_kernel<KIND, 4, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
+  else
+    rnn_f32_kernel<KIND, 8, TOut><<<grid, 256, 0, st>>>(xproj, whh_t, bhn, out, out_seq_stride, nseq, T);
   return 1;
 }
 
