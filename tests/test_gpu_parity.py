@@ -338,3 +338,57 @@ def test_streaming_rolling_window_matches_reference_loop():
     ref = O.probs(sd, ring)
     assert _maxerr(got["out"]["p_now"], ref["p_now"]) <= 1e-5
     assert abs(got["p_now_mean"] - ref["p_now"][0, -25:, 0].mean().item()) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_probs_is_cuda_graph_capturable_and_replays_bit_identically(precision):
+    """all work is enqueued on the caller's stream with no allocation or sync inside, so a call can be
+    captured in a CUDA graph; replays on new input contents equal eager calls bit for bit."""
+    from oracle import synth
+
+    m = _model(synth.make_state_dict(3, "LSTM", 1, 2.0), precision)
+    g = torch.Generator().manual_seed(11)
+    B, S = 3, 48000
+    xs = [(torch.randn((B, 2, S), generator=g) * 0.05).cuda() for _ in range(2)]
+    eager = [{k: v.clone() for k, v in m.probs(x).items()} for x in xs]
+    static_in = xs[0].clone()
+    out = m.alloc_outputs(B, 150, "cuda", argmax=True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        m.probs(static_in, out=out)  # warm-up on the capture stream (allocates its scratch arena)
+        graph = torch.cuda.CUDAGraph()
+        n0 = m.launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            m.probs(static_in, out=out)
+        assert m.launch_count() > n0
+    torch.cuda.current_stream().wait_stream(side)
+    for x, ref in zip(xs[::-1], eager[::-1]):
+        static_in.copy_(x)
+        for v in out.values():
+            v.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+
+
+def test_one_model_is_reentrant_across_streams():
+    """§8(b): 're-entrant across streams when workspaces differ' — the facade keeps one scratch arena per stream."""
+    from oracle import synth
+
+    m = _model(synth.make_state_dict(4, "GRU", 1, 2.0), "bf16")
+    g = torch.Generator().manual_seed(12)
+    xs = [(torch.randn((6, 2, 64000), generator=g) * 0.05).cuda() for _ in range(2)]
+    ref = [{k: v.clone() for k, v in m.probs(x).items()} for x in xs]
+    streams = [torch.cuda.Stream() for _ in xs]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        outs = []
+        for x, s in zip(xs, streams):
+            with torch.cuda.stream(s):
+                outs.append(m.probs(x))
+        torch.cuda.synchronize()
+        for o, r in zip(outs, ref):
+            for k in r:
+                assert torch.equal(o[k], r[k]), k

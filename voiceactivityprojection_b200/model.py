@@ -107,7 +107,7 @@ class VapGPT(nn.Module):
         self._device = torch.device("cpu")
         self._handle = None
         self._handle_device = None
-        self._ws = None
+        self._ws = {}
         self.objective._owner = self
 
     # ------------------------------------------------------------------ state
@@ -164,7 +164,7 @@ class VapGPT(nn.Module):
         if self._handle is not None:
             _lib.load().vapb_destroy(self._handle)
         self._handle = None
-        self._ws = None
+        self._ws = {}
 
     def __del__(self):
         try:
@@ -224,10 +224,14 @@ class VapGPT(nn.Module):
         lib, h = _lib.load(), self._ensure_handle()
         need = C.c_size_t()
         _lib.check(lib, h, lib.vapb_workspace_bytes(h, batch, n_samples, mode, C.byref(need)))
-        if self._ws is None or self._ws.numel() < need.value or self._ws.device != self._device:
-            self._ws = None
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=self._device)
-        return self._ws
+        # one scratch arena per (device, stream): calls on different streams may overlap, so they must not share it
+        key = (str(self._device), torch.cuda.current_stream(self._device).cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need.value:
+            self._ws.pop(key, None)
+            ws = None  # release the old arena before allocating its replacement
+            ws = self._ws[key] = torch.empty(need.value, dtype=torch.uint8, device=self._device)
+        return ws
 
     def _mode(self, precision=None) -> int:
         return _lib.MODES[precision or self.precision]
