@@ -392,3 +392,52 @@ def test_one_model_is_reentrant_across_streams():
         for o, r in zip(outs, ref):
             for k in r:
                 assert torch.equal(o[k], r[k]), k
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_no_kernel_reads_scratch_it_did_not_write(precision):
+    """Poisons the caller-owned workspace (0xFF bytes = NaN in every format, then zeros) before a call: outputs must
+    not change by a bit, i.e. nothing depends on what an earlier call left behind."""
+    from oracle import synth
+
+    m = _model(synth.make_state_dict(5, "LSTM", 1, 2.0), precision)
+    g = torch.Generator().manual_seed(13)
+    x = (torch.randn((5, 2, 47360), generator=g) * 0.05).cuda()
+    ref = {k: v.clone() for k, v in m.probs(x).items()}
+    for fill in (0xFF, 0x00):
+        for ws in m._ws.values():
+            ws.fill_(fill)
+        out = m.probs(x)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), (k, fill)
+
+
+def test_item_group_pipeline_is_bit_identical_to_the_unsplit_call(monkeypatch):
+    """VAPB_PIPE (experimental, off by default): groups of items on concurrent streams. Besides checking the pipeline's
+    own bookkeeping this is a concurrency stress: it is how the conv0 rstd-ring race was found."""
+    from oracle import synth
+
+    sd = synth.make_state_dict(6, "LSTM", 1, 2.0)
+    g = torch.Generator().manual_seed(14)
+    B, S = 50, 96000
+    x = (torch.randn((B, 2, S), generator=g) * 0.05).cuda()
+    monkeypatch.setenv("VAPB_PIPE", "1")
+    m1 = _model(sd, "bf16")
+    ref = {k: v.clone() for k, v in m1.probs(x, out=m1.alloc_outputs(B, 300, "cuda", argmax=True)).items()}
+    ref_fwd = m1(x)
+    monkeypatch.setenv("VAPB_PIPE", "3")
+    monkeypatch.setenv("VAPB_PIPE_MIN", "8")
+    m3 = _model(sd, "bf16")
+    out = m3.alloc_outputs(B, 300, "cuda", argmax=True)
+    for _ in range(6):
+        for v in out.values():
+            v.zero_()
+        m3.probs(x, out=out)
+        fwd = m3(x)
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+        assert torch.equal(fwd["logits"], ref_fwd["logits"]) and torch.equal(fwd["vad"], ref_fwd["vad"])
+    with pytest.raises(RuntimeError, match="pipelined"):
+        m3.stage("enc", x)
+    assert m3.stage("enc", x[:4]).shape == (8, 300, 256)  # below the group threshold: not pipelined

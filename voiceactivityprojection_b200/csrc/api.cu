@@ -137,6 +137,9 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
+  if (const char* v = getenv("VAPB_PIPE")) h->m.pipe = atoi(v);
+  if (const char* v = getenv("VAPB_PIPE_MIN")) h->m.pipe_min_items = atoi(v);
+  if (const char* v = getenv("VAPB_PIPE_TRACE")) h->m.pipe_trace = atoi(v);
   *out = h;
   return VAPB_OK;
 }
@@ -353,6 +356,10 @@ int vapb_destroy(VapbHandle* h) {
   if (!h) return VAPB_OK;
   for (auto& r : h->m.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->m.event_pool) cudaEventDestroy(e);
+  for (auto e : h->m.pipe_conv) cudaEventDestroy(e);
+  for (auto e : h->m.pipe_join) cudaEventDestroy(e);
+  if (h->m.pipe_fork) cudaEventDestroy(h->m.pipe_fork);
+  for (auto st : h->m.pipe_st) cudaStreamDestroy(st);
   bf16_release(h->m);
   if (h->m.arena) cudaFree(h->m.arena);
   delete h;
@@ -385,9 +392,27 @@ namespace {
 struct Aux {  // api-level scratch appended to the path workspace
   size_t logits, vad_sig, lse, bytes;
 };
+struct Group {  // items [b0, b0 + g.batch) of a pipelined call and where their path workspace starts
+  int b0;
+  Geometry g;
+  size_t off;
+};
+struct CallPlan {
+  Geometry g;
+  std::vector<Group> groups;  // size 1: not pipelined
+  Aux aux;
+};
 
-int plan_all(const Model& m, int batch, int64_t n_samples, int mode, Geometry* g, size_t* path_bytes, Aux* aux,
-             std::string* err) {
+int n_groups_for(const Model& m, int batch, int mode) {
+  if (mode == VAPB_MODE_FP32 || m.pipe <= 1) return 1;
+  int n = batch / (m.pipe_min_items > 0 ? m.pipe_min_items : 1);
+  if (n > m.pipe) n = m.pipe;
+  return n < 1 ? 1 : n;
+}
+
+int plan_all(const Model& m, int batch, int64_t n_samples, int mode, CallPlan* cp, std::string* err) {
+  Geometry* g = &cp->g;
+  Aux* aux = &cp->aux;
   if (batch < 1 || batch > 16384) { *err = "batch out of range"; return VAPB_E_INVALID; }
   if (mode != VAPB_MODE_FP32 && mode != VAPB_MODE_BF16 && mode != VAPB_MODE_FP16) { *err = "unknown mode"; return VAPB_E_INVALID; }
   if (n_samples < 1 || make_geometry(batch, n_samples, g) != 0 || g->T < 1) {
@@ -395,9 +420,26 @@ int plan_all(const Model& m, int batch, int64_t n_samples, int mode, Geometry* g
     return VAPB_E_INVALID;
   }
   if ((long long)g->nseq * g->L[1] > 2000000000LL) { *err = "batch * n_samples too large for one call"; return VAPB_E_INVALID; }
-  *path_bytes = mode == VAPB_MODE_FP32 ? workspace_bytes_fp32(m, *g) : workspace_bytes_bf16(m, *g);
-  if (*path_bytes == 0) { *err = "mode not available in this build"; return VAPB_E_UNSUPPORTED; }
-  size_t off = (*path_bytes + 1023) / 1024 * 1024;
+  size_t path_bytes = mode == VAPB_MODE_FP32 ? workspace_bytes_fp32(m, *g) : workspace_bytes_bf16(m, *g);
+  if (path_bytes == 0) { *err = "mode not available in this build"; return VAPB_E_UNSUPPORTED; }
+  const int ng = n_groups_for(m, batch, mode);
+  cp->groups.clear();
+  if (ng <= 1) {
+    cp->groups.push_back(Group{0, *g, 0});
+  } else {
+    size_t off = 0;
+    for (int k = 0; k < ng; ++k) {
+      Group gr{};
+      gr.b0 = (int)((long long)batch * k / ng);
+      const int b1 = (int)((long long)batch * (k + 1) / ng);
+      if (make_geometry(b1 - gr.b0, n_samples, &gr.g) != 0) { *err = "bad group geometry"; return VAPB_E_INVALID; }
+      gr.off = off;
+      off = (off + workspace_bytes_bf16(m, gr.g) + 1023) / 1024 * 1024;
+      cp->groups.push_back(gr);
+    }
+    if (off > path_bytes) path_bytes = off;  // the unsplit layout (used while profiling) fits too
+  }
+  size_t off = (path_bytes + 1023) / 1024 * 1024;
   const size_t rows = (size_t)batch * g->T;
   aux->logits = off;  off += (rows * kClasses * 4 + 1023) / 1024 * 1024;
   aux->vad_sig = off; off += (rows * 2 * 4 + 1023) / 1024 * 1024;
@@ -407,10 +449,91 @@ int plan_all(const Model& m, int batch, int64_t n_samples, int mode, Geometry* g
 }
 
 int run_forward(Model& m, cudaStream_t st, const float* wav, const Geometry& g, int mode, char* ws, float* logits,
-                float* vad_logits, float* vad_sig) {
+                float* vad_logits, float* vad_sig, cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr) {
   const float* comb = nullptr;
   return mode == VAPB_MODE_FP32 ? forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb)
-                                : forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, mode == VAPB_MODE_FP16);
+                                : forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb,
+                                               mode == VAPB_MODE_FP16, conv_wait, conv_done);
+}
+
+// Streams and events of the item-group pipeline (created on first use, owned by the handle).
+int ensure_pipe(Model& m, int ng) {
+  if (!m.pipe_fork && cudaEventCreateWithFlags(&m.pipe_fork, cudaEventDisableTiming) != cudaSuccess) return -1;
+  while ((int)m.pipe_st.size() < ng - 1) {
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    m.pipe_st.push_back(s);
+  }
+  while ((int)m.pipe_conv.size() < ng) {
+    cudaEvent_t a, b;
+    if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess) return -1;
+    m.pipe_conv.push_back(a);
+    if (cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) return -1;
+    m.pipe_join.push_back(b);
+  }
+  return 0;
+}
+
+struct ProbsOut {  // vapb_probs's optional outputs; every pointer addresses item 0 of the call
+  float *logits, *vad_logits, *probs, *vad, *p_now, *p_future, *H, *loss;
+  uint8_t* argmax;
+  int now_lo, now_hi, fut_lo, fut_hi;
+  bool want_probs;  // false: vapb_forward (logits + vad logits only)
+};
+
+// Forward (+ the probs()/loss kernels) of items [b0, b0 + g.batch) on `st`.
+int run_items(Model& m, cudaStream_t st, const float* wav, int b0, const Geometry& g, int mode, char* ws_path,
+              char* ws_all, const Aux& aux, const ProbsOut& o, cudaEvent_t conv_wait, cudaEvent_t conv_done) {
+  const long long T = g.T, r0 = (long long)b0 * T;
+  auto at = [](float* p, long long n) { return p ? p + n : nullptr; };
+  float* lg = o.logits ? o.logits + r0 * kClasses : reinterpret_cast<float*>(ws_all + aux.logits) + r0 * kClasses;
+  float* vs = nullptr;
+  if (o.want_probs) vs = o.vad ? o.vad + r0 * 2 : reinterpret_cast<float*>(ws_all + aux.vad_sig) + r0 * 2;
+  float* lse = reinterpret_cast<float*>(ws_all + aux.lse) + r0;
+  const int rc = run_forward(m, st, wav + (long long)b0 * 2 * g.S, g, mode, ws_path, lg, at(o.vad_logits, r0 * 2), vs,
+                             conv_wait, conv_done);
+  if (rc || !o.want_probs) return rc;
+  const long long rows = (long long)g.batch * T;
+  ProfScope ps(m, st, CAT_HEADS);
+  m.launches += launch_probs(st, lg, rows, o.now_lo, o.now_hi, o.fut_lo, o.fut_hi, at(o.probs, r0 * kClasses),
+                             at(o.p_now, r0 * 2), at(o.p_future, r0 * 2), at(o.H, r0), o.loss ? lse : nullptr,
+                             o.argmax ? o.argmax + r0 : nullptr);
+  if (o.loss) m.launches += launch_loss(st, lg, vs, lse, g.batch, (int)T, o.loss + (long long)b0 * (T - 100));
+  return 0;
+}
+
+// One call = one group on the caller's stream, or the item-group pipeline (model.h) forked from / joined to it.
+int run_call(Model& m, cudaStream_t st, const float* wav, const CallPlan& cp, int mode, char* ws, const ProbsOut& o) {
+  const int ng = (int)cp.groups.size();
+  if (ng <= 1 || m.profiling)  // per-family event timing needs one stream
+    return run_items(m, st, wav, 0, cp.g, mode, ws, ws, cp.aux, o, nullptr, nullptr);
+  if (ensure_pipe(m, ng) != 0) { m.err = "cannot create the pipeline's streams/events"; return VAPB_E_CUDA; }
+  cudaEventRecord(m.pipe_fork, st);
+  m.trace(st, "fork");
+  int rc = 0;
+  for (int k = 0; k < ng; ++k) {
+    const Group& gr = cp.groups[k];
+    cudaStream_t sk = k == 0 ? st : m.pipe_st[k - 1];
+    if (k) cudaStreamWaitEvent(sk, m.pipe_fork, 0);
+    m.trace_group = k;
+    if (!rc)
+      rc = run_items(m, sk, wav, gr.b0, gr.g, mode, ws + gr.off, ws, cp.aux, o, k ? m.pipe_conv[k - 1] : nullptr,
+                     m.pipe_conv[k]);
+    m.trace(sk, "g" + std::to_string(k) + " end");
+    if (k) cudaEventRecord(m.pipe_join[k], sk);
+  }
+  for (int k = 1; k < ng; ++k) cudaStreamWaitEvent(st, m.pipe_join[k], 0);  // always join what was forked
+  if (m.pipe_trace && !m.trace_ev.empty()) {
+    cudaStreamSynchronize(st);
+    for (auto& te : m.trace_ev) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, m.trace_ev[0].second, te.second);
+      fprintf(stderr, "[pipe] %-16s %8.3f ms\n", te.first.c_str(), ms);
+    }
+    for (auto& te : m.trace_ev) cudaEventDestroy(te.second);
+    m.trace_ev.clear();
+  }
+  return rc;
 }
 
 }  // namespace
@@ -421,13 +544,11 @@ int vapb_workspace_bytes(const VapbHandle* h, int batch, int64_t n_samples, int 
   if (!h || !bytes) return VAPB_E_INVALID;
   Model& m = const_cast<Model&>(h->m);
   if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
-  Geometry g;
-  size_t pb;
-  Aux aux;
+  CallPlan cp;
   std::string err;
-  const int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  const int rc = plan_all(m, batch, n_samples, mode, &cp, &err);
   if (rc) return fail(m, rc, err);
-  *bytes = aux.bytes;
+  *bytes = cp.aux.bytes;
   return VAPB_OK;
 }
 
@@ -436,15 +557,16 @@ int vapb_forward(VapbHandle* h, void* stream, const float* wav, int batch, int64
   if (!h || !wav || !workspace || !logits || !vad_logits) return VAPB_E_INVALID;
   Model& m = h->m;
   if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
-  Geometry g;
-  size_t pb;
-  Aux aux;
+  CallPlan cp;
   std::string err;
-  int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  int rc = plan_all(m, batch, n_samples, mode, &cp, &err);
   if (rc) return fail(m, rc, err);
-  if (workspace_bytes < aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  if (workspace_bytes < cp.aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
   CUDA_OK(m, cudaSetDevice(m.device));
-  rc = run_forward(m, (cudaStream_t)stream, wav, g, mode, (char*)workspace, logits, vad_logits, nullptr);
+  ProbsOut o{};
+  o.logits = logits;
+  o.vad_logits = vad_logits;
+  rc = run_call(m, (cudaStream_t)stream, wav, cp, mode, (char*)workspace, o);
   if (rc) return rc;
   CUDA_OK(m, cudaPeekAtLastError());
   return VAPB_OK;
@@ -459,29 +581,18 @@ int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t
   if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
   if (now_lo < 0 || now_hi > 3 || now_lo > now_hi || fut_lo < 0 || fut_hi > 3 || fut_lo > fut_hi)
     return fail(m, VAPB_E_INVALID, "bin limits must satisfy 0 <= lo <= hi <= 3");
-  Geometry g;
-  size_t pb;
-  Aux aux;
+  CallPlan cp;
   std::string err;
-  int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  int rc = plan_all(m, batch, n_samples, mode, &cp, &err);
   if (rc) return fail(m, rc, err);
-  if (workspace_bytes < aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
-  if (loss && g.T <= 100)
+  if (workspace_bytes < cp.aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  if (loss && cp.g.T <= 100)
     return fail(m, VAPB_E_INVALID, "loss needs more than 100 frames (maximum size for tensor at dimension 1 is " +
-                                       std::to_string(g.T - 1) + " but size is 100)");
+                                       std::to_string(cp.g.T - 1) + " but size is 100)");
   CUDA_OK(m, cudaSetDevice(m.device));
-  cudaStream_t st = (cudaStream_t)stream;
-  char* ws = (char*)workspace;
-  float* lg = logits ? logits : reinterpret_cast<float*>(ws + aux.logits);
-  float* vs = vad ? vad : reinterpret_cast<float*>(ws + aux.vad_sig);
-  float* lse = reinterpret_cast<float*>(ws + aux.lse);
-  rc = run_forward(m, st, wav, g, mode, ws, lg, vad_logits, vs);
+  ProbsOut o{logits, vad_logits, probs, vad, p_now, p_future, H, loss, argmax, now_lo, now_hi, fut_lo, fut_hi, true};
+  rc = run_call(m, (cudaStream_t)stream, wav, cp, mode, (char*)workspace, o);
   if (rc) return rc;
-  const long long rows = (long long)batch * g.T;
-  ProfScope ps(m, st, CAT_HEADS);
-  m.launches += launch_probs(st, lg, rows, now_lo, now_hi, fut_lo, fut_hi, probs, p_now, p_future, H,
-                             loss ? lse : nullptr, argmax);
-  if (loss) m.launches += launch_loss(st, lg, vs, lse, batch, (int)g.T, loss);
   CUDA_OK(m, cudaPeekAtLastError());
   return VAPB_OK;
 }
@@ -506,13 +617,15 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
   if (!h || !name || !workspace || !out) return VAPB_E_INVALID;
   Model& m = h->m;
   if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
-  Geometry g;
-  size_t pb;
-  Aux aux;
+  CallPlan cp;
   std::string err;
-  int rc = plan_all(m, batch, n_samples, mode, &g, &pb, &aux, &err);
+  int rc = plan_all(m, batch, n_samples, mode, &cp, &err);
   if (rc) return fail(m, rc, err);
-  if (workspace_bytes < aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  const Geometry& g = cp.g;
+  if (workspace_bytes < cp.aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  if (cp.groups.size() > 1)
+    return fail(m, VAPB_E_UNSUPPORTED, "stage export is not available for a pipelined call (batch >= " +
+                                           std::to_string(2 * m.pipe_min_items) + "); use a smaller batch or VAPB_PIPE=1");
   StageRef ref{};
   rc = mode == VAPB_MODE_FP32 ? stage_fp32(m, g, (char*)workspace, name, &ref)
                               : stage_bf16(m, g, (char*)workspace, name, &ref);

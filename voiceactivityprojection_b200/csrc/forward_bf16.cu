@@ -251,7 +251,8 @@ void bf16_release(Model& m) {
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g) { return make_plan(m, g).bytes; }
 
 int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float**, int fp16) {
+                 float* vad_logits, float* vad_sig, const float**, int fp16, cudaEvent_t conv_wait,
+                 cudaEvent_t conv_done) {
   const State16& s = static_cast<const State16*>(m.bf16_state)[fp16 ? 1 : 0];
   Fp16Scope fmt_scope(fp16 ? 1 : 0);
   const Plan16 p = make_plan(m, g);
@@ -275,7 +276,9 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     }
   }
 
-  // ---- CPC gEncoder
+  // ---- CPC gEncoder (pipelined calls: after the previous item group's, see api.cu)
+  if (conv_wait) cudaStreamWaitEvent(st, conv_wait, 0);
+  m.trace(st, "g" + std::to_string(m.trace_group) + " conv_begin");
   for (int s0 = 0; s0 < nseq; s0 += p.mb) {
     const int n = (nseq - s0 < p.mb) ? nseq - s0 : p.mb;
     {
@@ -327,6 +330,10 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     }
   }
 
+  if (cx.rc) return cx.rc;
+  if (conv_done) cudaEventRecord(conv_done, st);
+  m.trace(st, "g" + std::to_string(m.trace_group) + " conv_end");
+
   // ---- gAR
   const bf16* rnn_in = H(p.act4);
   RowMap rnn_in_map{L4 * kDim, kDim};
@@ -343,6 +350,8 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     rnn_in = rnn_out;
     rnn_in_map = RowMap{p.rnn_lpad * kDim, kDim};
   }
+
+  m.trace(st, "g" + std::to_string(m.trace_group) + " rnn_end");
 
   // ---- downsample
   const int n_layers = m.channel_layers + m.cross_layers;

@@ -167,8 +167,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
         for (int l = 0; l < 10; ++l) y = fmaf(p.cs.G[k][l], xv[l], y);
         ss = fmaf(xv[k], y, ss);
       }
-      rs[(it & 3) * 128 + r] = rsqrtf(fmaxf(ss, 0.f) * (1.0f / (kDim - 1)) + kEps);
+      const float rstd = rsqrtf(fmaxf(ss, 0.f) * (1.0f / (kDim - 1)) + kEps);
       mbar_wait(a_empty(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      // rs is a ring of 4 tiles. Stored only after a_empty(it): MMA(it-2) has completed, so the epilogue released the
+      // accumulator of tile it-4 and is done with this slot. (Stored before the wait, the slot could still be unread by
+      // a late epilogue warp of tile it-4: a rare, timing-dependent wrong rstd for 32 frames.)
+      rs[(it & 3) * 128 + r] = rstd;
       uint8_t* arow = smem_gen + CT_OFF_A + buf * CT_A_BYTES + r * 16;
       *reinterpret_cast<float4*>(arow) = make_float4(to_tf32(xv[0]), to_tf32(xv[1]), to_tf32(xv[2]), to_tf32(xv[3]));
       *reinterpret_cast<float4*>(arow + 2048) = make_float4(to_tf32(xv[4]), to_tf32(xv[5]), to_tf32(xv[6]), to_tf32(xv[7]));

@@ -70,6 +70,27 @@ struct Model {
   int ffn_fused = 1;      // FFN block as one kernel (k_ffn_fused.cu); 0 = two GEMMs (env VAPB_FFN_FUSED)
   int conv0_tc = 1;       // conv0 on the tensor cores (k_conv0_tc.cu); 0 = CUDA-core kernel (env VAPB_CONV0_TC)
   int conv_lin_from = 1;  // gEncoder convs >= this index use k_gemm_lin.cu's staged epilogue (env VAPB_CONV_LIN_FROM)
+  // Item-group pipelining of 16-bit-mode calls (api.cu): a large batch is cut into up to `pipe` groups of items, each
+  // on its own stream. The groups' gEncoder phases run one after another (event chain), so one group's gAR recurrence
+  // (latency-bound on a fraction of the SMs) and transformer overlap the next group's convolutions. env VAPB_PIPE
+  // (1 = off), VAPB_PIPE_MIN (fewest items per group).
+  int pipe = 1;
+  int pipe_min_items = 16;
+  std::vector<cudaStream_t> pipe_st;   // streams of groups 1.. (group 0 runs on the caller's stream)
+  std::vector<cudaEvent_t> pipe_conv;  // group k's gEncoder is done
+  std::vector<cudaEvent_t> pipe_join;  // group k (>= 1) is done
+  cudaEvent_t pipe_fork = nullptr;
+  // env VAPB_PIPE_TRACE=1 (diagnostics): timestamps of each group's phases, printed to stderr after a host sync
+  int pipe_trace = 0;
+  std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
+  void trace(cudaStream_t st, const std::string& tag) {
+    if (!pipe_trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    trace_ev.emplace_back(tag, e);
+  }
+  int trace_group = 0;
   unsigned long long launches = 0;
   std::string err;
 };
@@ -131,7 +152,8 @@ int bf16_prepare(Model& m);   // pack bf16 weights after the fp32 arena is built
 void bf16_release(Model& m);
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g);
 int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float** comb_out, int fp16);
+                 float* vad_logits, float* vad_sig, const float** comb_out, int fp16,
+                 cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr);
 int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
 }  // namespace vapb
