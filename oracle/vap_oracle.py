@@ -155,9 +155,9 @@ def alibi_mask(m: Tensor, T: int) -> Tensor:
     """vap/modules.py:169-187. (1, H, T, T): 1.0 + m_h*j on/below the diagonal,
     -inf above (the tril's 1.0 entries survive the masked_fill)."""
     H = m.shape[0]
-    rel = torch.arange(T, dtype=m.dtype).view(1, 1, -1).expand(1, H, -1)
+    rel = torch.arange(T, dtype=m.dtype, device=m.device).view(1, 1, -1).expand(1, H, -1)
     alibi = rel * m.unsqueeze(0).unsqueeze(-1)
-    mask = torch.tril(torch.ones((T, T), dtype=m.dtype)).view(1, 1, T, T).repeat(1, H, 1, 1)
+    mask = torch.tril(torch.ones((T, T), dtype=m.dtype, device=m.device)).view(1, 1, T, T).repeat(1, H, 1, 1)
     mask.masked_fill_(mask == 0, float("-inf"))
     return alibi.unsqueeze(-2) + mask
 
@@ -261,7 +261,7 @@ def code_vectors(total_bins: int = 8) -> Tensor:
 
 def probs_next_speaker_aggregate(probs: Tensor, from_bin: int, to_bin: int) -> Tensor:
     """vap/objective.py:184-204."""
-    states = code_vectors(8).to(probs.dtype).view(256, 2, 4)  # decode: (c b) -> c b
+    states = code_vectors(8).to(probs.dtype).to(probs.device).view(256, 2, 4)  # decode: (c b) -> c b
     abp = states[:, :, from_bin: to_bin + 1].sum(-1)
     p_all = torch.einsum("bid,dc->bic", probs, abp)
     p_all = p_all / (p_all.sum(-1, keepdim=True) + 1e-5)
@@ -280,7 +280,7 @@ def get_labels(va: Tensor) -> Tensor:
         start += b
     pw = torch.stack(bins, dim=-1)  # (B, N, 2, 4)
     flat = pw.reshape(-1, 8)
-    embed = code_vectors(8).to(va.dtype).T
+    embed = code_vectors(8).to(va.dtype).to(va.device).T
     dist = -(flat.pow(2).sum(1, keepdim=True) - 2 * flat @ embed + embed.pow(2).sum(0, keepdim=True))
     return dist.max(dim=-1).indices.view(*pw.shape[:-2])
 
