@@ -197,6 +197,19 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
                        int cross, char* err, int err_len,
                        long long* dbg_clocks /* device [64][8] SM-clock samples of CTA 0, or NULL */);
 
+/* Input path: rational polyphase resampling on the device, the arithmetic of
+ * torchaudio.functional.resample (sinc_interp_hann) that vap/audio.py:65-68 applies after decoding a file.
+ * orig/new are the two rates divided by their gcd. Input: `items` x `channels` rows of n_in samples, float32
+ * (x_fmt 0) or int16 PCM scaled by 1/32768 (x_fmt 1); sample i of (item, ch) is at
+ * x[item*item_stride + ch*chan_stride + i*elem_stride] (elements), so planar and interleaved buffers both fit.
+ * bank: device float32 [new][2*width + orig] windowed-sinc filters (host-computed, see audio.py). Row (item, ch)
+ * of the output starts at out + (item*channels + ch)*out_row_stride and holds n_out <= ceil(new*n_in/orig)
+ * samples: the (B, 2, n) layout vapb_forward takes. `h` may be NULL (stateless; errors then land in
+ * vapb_last_error(NULL)). */
+int vapb_resample(VapbHandle* h, void* stream, const void* x, int x_fmt, int64_t items, int channels, int64_t n_in,
+                  int64_t item_stride, int64_t chan_stride, int64_t elem_stride, int orig, int new_rate, int width,
+                  const float* bank, float* out, int64_t n_out, int64_t out_row_stride);
+
 /* Number of kernels this handle has launched since creation. */
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches);
 

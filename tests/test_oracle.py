@@ -106,3 +106,41 @@ def test_oracle_bit_identical_to_imported_reference():
     mine = O.probs(sd, wav)
     for k in ref:
         assert torch.equal(ref[k], mine[k]), k
+
+
+# --------------------------------------------------------------------------- #
+# resampler oracle (input path)                           #
+# --------------------------------------------------------------------------- #
+def test_resample_oracle_matches_torchaudio_golden():
+    import numpy as np
+
+    from conftest import GOLDEN_DIR
+    from oracle import resample_oracle as R
+
+    g = np.load(f"{GOLDEN_DIR}/resample_example_24k_16k.npz")
+    assert np.abs(R.resample(g["pcm_24k"], 24000, 16000) - g["y_24k"]).max() <= 1e-6
+    for rate in (48000, 44100, 8000):
+        y = R.resample(g[f"x_{rate}"], rate, 16000)
+        assert y.shape == g[f"y_{rate}"].shape
+        assert np.abs(y - g[f"y_{rate}"]).max() <= 1e-6
+
+
+def test_resample_bank_is_torchaudios_and_oracle_matches_torchaudio_live():
+    import math
+
+    import numpy as np
+
+    from oracle import resample_oracle as R
+    from voiceactivityprojection_b200.audio import sinc_resample_bank
+
+    taf = pytest.importorskip("torchaudio.functional")
+    rng = np.random.default_rng(0)
+    for rate, n in ((24000, 1000), (24000, 1), (48000, 3333), (44100, 900), (8000, 555), (32000, 77), (16000 * 3, 10)):
+        bank, width, orig, new = sinc_resample_bank(rate, 16000)
+        kb, w = taf.functional._get_sinc_resample_kernel(rate, 16000, math.gcd(rate, 16000), dtype=torch.float32)
+        assert w == width and torch.equal(kb[:, 0], bank)
+        assert np.abs(R.bank(rate, 16000)[0] - bank.numpy()).max() <= 2e-7
+        x = (rng.random((2, n), dtype=np.float32) * 2 - 1)
+        ref = taf.resample(torch.from_numpy(x), rate, 16000).numpy()
+        got = R.resample(x, rate, 16000)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-6

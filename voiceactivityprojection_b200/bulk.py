@@ -84,9 +84,13 @@ class BulkRunner:
     """Pipelined `model.probs` over a stream of pinned host batches of shape (b <= batch, 2, n_samples)."""
 
     def __init__(self, model, batch: int, n_samples: int, precision: Optional[str] = None,
-                 keys: Sequence[str] = ALL_KEYS, stats: bool = True, depth: int = 2, pcm16: bool = False):
+                 keys: Sequence[str] = ALL_KEYS, stats: bool = True, depth: int = 2, pcm16: bool = False,
+                 input_rate: Optional[int] = None):
         """pcm16=True: host batches are int16 PCM (what wav files hold; the reference converts to float on the CPU,
-        vap/audio.py:47); they cross PCIe at half the bytes and are scaled by 1/32768 on the device."""
+        vap/audio.py:47); they cross PCIe at half the bytes and are scaled by 1/32768 on the device.
+        input_rate: sample rate of the host batches when it is not the model's 16 kHz; they are then
+        (b, 2, n_in) with ceil(16000 * n_in / input_rate) == n_samples and are resampled on the device
+        (audio.resample_device; the reference resamples on the CPU, vap/audio.py:65-68)."""
         from . import _lib
 
         if model._device.type != "cuda":
@@ -98,8 +102,15 @@ class BulkRunner:
         want_argmax = stats or "argmax" in self.keys
         self.pcm16 = pcm16
         in_dtype = torch.int16 if pcm16 else torch.float32
-        self.din = [torch.empty((batch, 2, n_samples), dtype=in_dtype, device=self.dev) for _ in range(depth)]
-        self.dwav = torch.empty((batch, 2, n_samples), dtype=torch.float32, device=self.dev) if pcm16 else None
+        self.input_rate = None if input_rate in (None, model.sample_rate) else int(input_rate)
+        self.n_in = n_samples
+        if self.input_rate:
+            # the same duration at the input rate (its resampled length, ceil(16000 * n_in / rate), is >= n_samples;
+            # the resampler writes the first n_samples)
+            self.n_in = -(-n_samples * self.input_rate // model.sample_rate)
+        self.din = [torch.empty((batch, 2, self.n_in), dtype=in_dtype, device=self.dev) for _ in range(depth)]
+        self.dwav = (torch.empty((batch, 2, n_samples), dtype=torch.float32, device=self.dev)
+                     if pcm16 or self.input_rate else None)
         self.dout = [model.alloc_outputs(batch, self.T, self.dev, argmax=want_argmax) for _ in range(depth)]
         host = model.alloc_outputs(batch, self.T, "cpu", argmax=True, pin_memory=True)
         self.hout = [{k: torch.empty_like(host[k], pin_memory=True) for k in self.keys} for _ in range(depth)]
@@ -125,10 +136,10 @@ class BulkRunner:
             s.wait_stream(cur)
         for i, hb in enumerate(batches):
             b = hb.shape[0]
-            if (hb.device.type != "cpu" or b > self.batch or tuple(hb.shape[1:]) != (2, self.n_samples)
+            if (hb.device.type != "cpu" or b > self.batch or tuple(hb.shape[1:]) != (2, self.n_in)
                     or hb.dtype != self.din[0].dtype):
-                raise ValueError(f"batch {i}: expected a CPU tensor (<= {self.batch}, 2, {self.n_samples}), got "
-                                 f"{tuple(hb.shape)} on {hb.device}")
+                raise ValueError(f"batch {i}: expected a CPU {self.din[0].dtype} tensor (<= {self.batch}, 2, "
+                                 f"{self.n_in}), got {hb.dtype} {tuple(hb.shape)} on {hb.device}")
             slot = i % self.depth
             with torch.cuda.stream(self.s_h2d):
                 self.s_h2d.wait_event(self.ev_cmp[slot])      # the forward that read din[slot] has finished
@@ -139,7 +150,11 @@ class BulkRunner:
                 self.s_cmp.wait_event(self.ev_h2d[slot])
                 self.s_cmp.wait_event(self.ev_d2h[slot])      # dout[slot] has been copied out
                 o = {k: v[:b] for k, v in self.dout[slot].items()}
-                if self.pcm16:
+                if self.input_rate:
+                    from .audio import resample_device
+
+                    wav = resample_device(self.din[slot][:b], self.input_rate, self.model.sample_rate, out=self.dwav[:b])
+                elif self.pcm16:
                     wav = self.dwav[:b]
                     wav.copy_(self.din[slot][:b])
                     wav.mul_(1.0 / 32768.0)

@@ -844,6 +844,27 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
   return VAPB_OK;
 }
 
+int vapb_resample(VapbHandle* h, void* stream, const void* x, int x_fmt, int64_t items, int channels, int64_t n_in,
+                  int64_t item_stride, int64_t chan_stride, int64_t elem_stride, int orig, int new_rate, int width,
+                  const float* bank, float* out, int64_t n_out, int64_t out_row_stride) {
+  std::string err;
+  int rc = VAPB_OK;
+  if (!x || !bank || !out) {
+    err = "resample: NULL buffer";
+    rc = VAPB_E_INVALID;
+  } else {
+    if (h) cudaSetDevice(h->m.device);
+    const int n = launch_resample((cudaStream_t)stream, x, x_fmt, items, channels, n_in, item_stride, chan_stride,
+                                  elem_stride, orig, new_rate, width, bank, out, n_out, out_row_stride, &err);
+    if (n < 0) rc = VAPB_E_INVALID;
+    else if (h) h->m.launches += n;
+  }
+  if (rc) {
+    if (h) h->m.err = err; else g_create_err = err;
+  }
+  return rc;
+}
+
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches) {
   if (!h || !launches) return VAPB_E_INVALID;
   *launches = h->m.launches;
