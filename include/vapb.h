@@ -197,6 +197,13 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
                        int cross, char* err, int err_len,
                        long long* dbg_clocks /* device [64][8] SM-clock samples of CTA 0, or NULL */);
 
+/* VapGPT.vad()'s post-processing (vap/model.py:240-247 -> vad_fill_silences / vad_omit_spikes,
+ * vap/utils.py:239-272) on the device. vad01: device fp32 (batch, T, 2) holding 0/1 (the caller thresholds
+ * sigmoid(vad) >= cutoff); silence runs of <= max_fill_frames become 1, then activity runs of <= max_omit_frames
+ * of the result become 0. out may alias vad01. `h` may be NULL. */
+int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, int64_t T, int max_fill_frames,
+                    int max_omit_frames, float* out);
+
 /* Input path: rational polyphase resampling on the device, the arithmetic of
  * torchaudio.functional.resample (sinc_interp_hann) that vap/audio.py:65-68 applies after decoding a file.
  * orig/new are the two rates divided by their gcd. Input: `items` x `channels` rows of n_in samples, float32

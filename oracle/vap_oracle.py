@@ -350,3 +350,33 @@ def step_extraction(sd, waveform: Tensor, sample_rate=16000, frame_hz=50,
         for k in keys:
             out[k] = torch.cat([out[k], o[k][:, -omitted:]], dim=1)
     return out
+
+
+# --------------------------------------------------------------------------- #
+# VapGPT.vad() post-processing                                                 #
+# --------------------------------------------------------------------------- #
+def _runs(x: Tensor):
+    """vap/utils.py:21-49 find_island_idx_len as a plain loop: (start, length, value) of every run."""
+    out, n, s = [], len(x), 0
+    for t in range(1, n + 1):
+        if t == n or x[t] != x[s]:
+            out.append((s, t - s, float(x[s])))
+            s = t
+    return out
+
+
+def vad_filter(vad: Tensor, max_fill_time: float = 0.02, max_omit_time: float = 0.02, frame_hz: float = 50) -> Tensor:
+    """vap/model.py:240-247: per item vad_fill_silences (vap/utils.py:239-254) then vad_omit_spikes (:257-272).
+    vad (B, T, 2) binary float; returns a new tensor."""
+    v = vad.clone()
+    fill, omit = round(max_fill_time * frame_hz), round(max_omit_time * frame_hz)
+    for b in range(v.shape[0]):
+        for ch in range(2):
+            for s, d, val in _runs(v[b, :, ch]):
+                if val == 0 and d <= fill:
+                    v[b, s: s + d, ch] = 1.0
+        for ch in range(2):
+            for s, d, val in _runs(v[b, :, ch]):
+                if val == 1 and d <= omit:
+                    v[b, s: s + d, ch] = 0.0
+    return v

@@ -441,3 +441,30 @@ def test_item_group_pipeline_is_bit_identical_to_the_unsplit_call(monkeypatch):
     with pytest.raises(RuntimeError, match="pipelined"):
         m3.stage("enc", x)
     assert m3.stage("enc", x[:4]).shape == (8, 300, 256)  # below the group threshold: not pipelined
+
+
+def test_vad_filter_kernel_is_bit_exact_with_reference_golden_and_oracle():
+    """VapGPT.vad()'s fill-silence / omit-spike filters (vap/utils.py:239-272) as one kernel: integer run-length
+    work, bit-exact against the reference's outputs (tests/golden/vad_filter.npz) and the oracle on random input."""
+    import numpy as np
+
+    from conftest import GOLDEN_DIR
+    from oracle import synth
+    from oracle import vap_oracle as O
+
+    m = _model(synth.make_state_dict(8, "LSTM", 1, 1.0))
+    g = np.load(f"{GOLDEN_DIR}/vad_filter.npz")
+    for n in sorted(k[:-3] for k in g.files if k.endswith("_in")):
+        fill, omit = (float(x) for x in g[n + "_par"])
+        got = m.vad_filter(torch.from_numpy(g[n + "_in"]).cuda(), fill, omit)
+        assert torch.equal(got.cpu(), torch.from_numpy(g[n + "_out"])), n
+    gen = torch.Generator().manual_seed(5)
+    v = ((torch.rand((256, 1000, 2), generator=gen) < 0.1).long().cumsum(1) % 2).float()
+    v[:, 400:403, 0] = 1 - v[:, 399:400, 0]  # short runs in every item
+    got = m.vad_filter(v.clone().cuda(), 0.04, 0.06)
+    assert torch.equal(got.cpu(), O.vad_filter(v, 0.04, 0.06))
+    # end to end: model.vad() = threshold + the same filters
+    x = (torch.randn((3, 2, 64000), generator=gen) * 0.05).cuda()
+    raw = (m(x)["vad"].sigmoid() >= 0.5).float()
+    assert torch.equal(m.vad(x).cpu(), O.vad_filter(raw.cpu()))
+    assert m.vad_filter(torch.empty((0, 10, 2), device="cuda")).shape == (0, 10, 2)

@@ -144,3 +144,17 @@ def test_resample_bank_is_torchaudios_and_oracle_matches_torchaudio_live():
         ref = taf.resample(torch.from_numpy(x), rate, 16000).numpy()
         got = R.resample(x, rate, 16000)
         assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-6
+
+
+def test_vad_filter_oracle_matches_reference_golden():
+    import numpy as np
+
+    from conftest import GOLDEN_DIR
+
+    g = np.load(f"{GOLDEN_DIR}/vad_filter.npz")
+    names = sorted(k[:-3] for k in g.files if k.endswith("_in"))
+    assert len(names) == 5
+    for n in names:
+        fill, omit = g[n + "_par"]
+        got = O.vad_filter(torch.from_numpy(g[n + "_in"]), float(fill), float(omit))
+        assert torch.equal(got, torch.from_numpy(g[n + "_out"])), n

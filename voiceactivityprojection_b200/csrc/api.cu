@@ -844,6 +844,18 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
   return VAPB_OK;
 }
 
+int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, int64_t T, int max_fill_frames,
+                    int max_omit_frames, float* out) {
+  if (!vad01 || !out || batch < 0 || T < 0 || T > 0x3fffffff || max_fill_frames < 0 || max_omit_frames < 0) {
+    if (h) h->m.err = "vad_filter: invalid argument"; else g_create_err = "vad_filter: invalid argument";
+    return VAPB_E_INVALID;
+  }
+  if (h) cudaSetDevice(h->m.device);
+  const int n = launch_vad_filter((cudaStream_t)stream, vad01, batch, (int)T, max_fill_frames, max_omit_frames, out);
+  if (h) h->m.launches += n;
+  return cudaPeekAtLastError() == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
+}
+
 int vapb_resample(VapbHandle* h, void* stream, const void* x, int x_fmt, int64_t items, int channels, int64_t n_in,
                   int64_t item_stride, int64_t chan_stride, int64_t elem_stride, int orig, int new_rate, int width,
                   const float* bank, float* out, int64_t n_out, int64_t out_row_stride) {

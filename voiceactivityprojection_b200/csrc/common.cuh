@@ -141,6 +141,7 @@ int launch_vad_head(cudaStream_t st, const float* x /*[2B][T][256] channel-major
 int launch_resample(cudaStream_t st, const void* x, int x_fmt, long long items, int channels, long long n_in,
                     long long item_stride, long long chan_stride, long long elem_stride, int orig, int new_, int width,
                     const float* bank, float* out, long long n_out, long long out_row_stride, std::string* err);
+int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out);
 int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
                  int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse,
                  uint8_t* argmax);

@@ -227,4 +227,48 @@ int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, cons
   return 1;
 }
 
+// VapGPT.vad()'s run-length filters (vap/model.py:227-247 -> vap/utils.py:239-272): on a binary (batch, T, 2)
+// activity tensor, first every silence run of <= max_fill frames becomes active (vad_fill_silences; runs touching
+// either end of the sequence included, as find_island_idx_len reports them), then every activity run of <= max_omit
+// frames of the RESULT becomes silence (vad_omit_spikes). One thread per (item, channel) sequence: 2 x T sequential
+// steps on 8 KB of data per item is microseconds, and the reference's per-run Python loop is what this replaces.
+__global__ void __launch_bounds__(128)
+vad_filter_kernel(const float* vad, int nseq, int T, int max_fill, int max_omit, float* out) {  // out may alias vad
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseq) return;
+  const float* x = vad + (long long)(s >> 1) * T * 2 + (s & 1);
+  float* y = out + (long long)(s >> 1) * T * 2 + (s & 1);
+  // pass 1: fill short silences (reads x, writes y; in place is fine: a run is rewritten after it has been read)
+  int run0 = 0;
+  bool cur = T > 0 && x[0] != 0.f;
+  for (int t = 1; t <= T; ++t) {
+    const bool v = t < T ? (x[2LL * t] != 0.f) : !cur;
+    if (v != cur) {
+      const float w = (cur || t - run0 <= max_fill) ? 1.f : 0.f;
+      for (int k = run0; k < t; ++k) y[2LL * k] = w;
+      run0 = t;
+      cur = v;
+    }
+  }
+  // pass 2: drop short activity runs of the filled sequence
+  run0 = 0;
+  cur = T > 0 && y[0] != 0.f;
+  for (int t = 1; t <= T; ++t) {
+    const bool v = t < T ? (y[2LL * t] != 0.f) : !cur;
+    if (v != cur) {
+      if (cur && t - run0 <= max_omit)
+        for (int k = run0; k < t; ++k) y[2LL * k] = 0.f;
+      run0 = t;
+      cur = v;
+    }
+  }
+}
+
+int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out) {
+  const int nseq = batch * 2;
+  if (nseq <= 0 || T <= 0) return 0;
+  vad_filter_kernel<<<(unsigned)((nseq + 127) / 128), 128, 0, st>>>(vad01, nseq, T, max_fill, max_omit, out);
+  return 1;
+}
+
 }  // namespace vapb

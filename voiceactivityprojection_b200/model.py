@@ -325,10 +325,22 @@ class VapGPT(nn.Module):
             vad_cutoff: float = 0.5) -> Tensor:
         """vap/model.py:227-247."""
         v = (self(waveform)["vad"].sigmoid() >= vad_cutoff).float()
-        for b in range(v.shape[0]):
-            v[b] = vad_fill_silences(v[b], max_fill_time=max_fill_silence_time, frame_hz=self.frame_hz)
-            v[b] = vad_omit_spikes(v[b], max_omit_time=max_omit_spike_time, frame_hz=self.frame_hz)
-        return v
+        return self.vad_filter(v, max_fill_silence_time, max_omit_spike_time)
+
+    def vad_filter(self, vad01: Tensor, max_fill_silence_time: float = 0.02, max_omit_spike_time: float = 0.02
+                   ) -> Tensor:
+        """vad_fill_silences then vad_omit_spikes (vap/utils.py:239-272) for every item of a binary (B, T, 2)
+        CUDA tensor, in place, in one kernel (vapb_vad_filter) instead of the reference's per-run Python loops."""
+        if vad01.device.type != "cuda":
+            raise RuntimeError("vad_filter needs a CUDA tensor (no CPU fallback); utils.vad_fill_silences works on the host")
+        assert vad01.ndim == 3 and vad01.shape[-1] == 2 and vad01.dtype == torch.float32 and vad01.is_contiguous()
+        lib, h = _lib.load(), self._ensure_handle()
+        st = torch.cuda.current_stream(vad01.device).cuda_stream
+        if vad01.numel():
+            _lib.check(lib, h, lib.vapb_vad_filter(h, st, vad01.data_ptr(), vad01.shape[0], vad01.shape[1],
+                                                   round(max_fill_silence_time * self.frame_hz),
+                                                   round(max_omit_spike_time * self.frame_hz), vad01.data_ptr()))
+        return vad01
 
     # ------------------------------------------------------------------ diagnostics
     @torch.no_grad()
