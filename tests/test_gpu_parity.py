@@ -468,3 +468,26 @@ def test_vad_filter_kernel_is_bit_exact_with_reference_golden_and_oracle():
     raw = (m(x)["vad"].sigmoid() >= 0.5).float()
     assert torch.equal(m.vad(x).cpu(), O.vad_filter(raw.cpu()))
     assert m.vad_filter(torch.empty((0, 10, 2), device="cuda")).shape == (0, 10, 2)
+
+
+def test_one_minute_chunk_in_every_mode():
+    """run.py sends up to 160 s (8000 frames) in one call; tools/long_probe.py checks that size by hand. Here 60 s
+    (3000 frames, 24 query tiles per sequence): fp32 against the oracle at fp32 tolerance with exact decisions, the
+    tensor modes against fp32 mode at their stated tolerances."""
+    from oracle import synth
+    from oracle import vap_oracle as O
+
+    sd = synth.make_state_dict(9, "GRU", 1, 2.0)
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn((1, 2, 960000), generator=g) * 0.05
+    with torch.no_grad():
+        ref = O.probs(sd, x)
+    out32 = {k: v.cpu() for k, v in _model(sd).probs(x.cuda()).items()}
+    for k in ("probs", "vad", "p_now", "p_future", "H"):
+        assert _maxerr(out32[k], ref[k]) <= TOL32[k], k
+    assert torch.equal(out32["probs"].argmax(-1), ref["probs"].argmax(-1))
+    assert torch.equal(out32["vad"] >= 0.5, ref["vad"] >= 0.5)
+    for prec in ("bf16", "fp16"):
+        out = _model(sd, prec).probs(x.cuda())
+        for k in ("probs", "vad", "p_now", "p_future"):
+            assert _maxerr(out[k], out32[k]) <= TC_TOL[prec][k], (prec, k)

@@ -137,6 +137,8 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
+  if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
+  if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
   if (const char* v = getenv("VAPB_PIPE")) h->m.pipe = atoi(v);
   if (const char* v = getenv("VAPB_PIPE_MIN")) h->m.pipe_min_items = atoi(v);
   if (const char* v = getenv("VAPB_PIPE_TRACE")) h->m.pipe_trace = atoi(v);

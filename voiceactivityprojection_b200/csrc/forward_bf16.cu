@@ -50,7 +50,7 @@ struct Plan16 {
 Plan16 make_plan(const Model& m, const Geometry& g) {
   Plan16 p{};
   const long long per_seq0 = (g.L[0] + 16) * kDim * 2;
-  long long mb = (4LL << 30) / per_seq0;
+  long long mb = (m.conv_mb_bytes > 0 ? m.conv_mb_bytes : (4LL << 30)) / per_seq0;
   if (mb < 1) mb = 1;
   if (mb > g.nseq) mb = g.nseq;
   p.mb = (int)mb;
@@ -286,7 +286,8 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       if (m.conv0_tc) {
         std::string err;
         const int k = launch_conv0_tc(st, wav, g.batch, g.S, s0, n, g.L[0], s.c0_u, s.c0_d, w.c0_be, s.c0_stats,
-                                      H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0], m.n_sm, &err);
+                                      H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0],
+                                      m.conv0_sms > 0 ? m.conv0_sms : m.n_sm, &err);
         if (k < 0) { m.err = err; return -3; }
         m.launches += k;
       } else {

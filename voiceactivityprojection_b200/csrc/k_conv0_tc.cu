@@ -13,7 +13,9 @@
 //   D[128][256] fp32   in TMEM (two accumulators)
 // and the per-frame 1/sqrt(var + eps) is the closed form x'Gx + 2h.x + s evaluated by the thread
 // that builds the frame's A row. The epilogue is one FMA per output (acc * rstd_f + beta_c), ReLU,
-// bf16 pack into a swizzled staging tile and one TMA store per 128 x 32 block.
+// bf16 pack into a swizzled staging tile and a TMA store. Every epilogue warp stages and stores its own 32 rows x 64
+// channels (4 KB, two buffers): no barrier couples the warps, so their TMEM loads, math and stores overlap freely
+// (with one 128-row store per column block and two named barriers per block the tile took ~3500 clk, latency-bound).
 #include <string>
 
 #include "common.cuh"
@@ -25,21 +27,25 @@ using namespace tc;
 
 namespace {
 
-constexpr int CT_THREADS = 416;  // warps 0-3 build A, warp 4 issues MMAs (and owns TMEM), warps 5-12 epilogue
+constexpr int CT_SPLIT = 4;                      // column groups of the epilogue: 4 warps (TMEM lane quadrants) each
+constexpr int CT_EPI_WARPS = 4 * CT_SPLIT;
+constexpr int CT_CHUNKS = 8 / CT_SPLIT;          // 32-column chunks per epilogue thread
+constexpr int CT_THREADS = (5 + CT_EPI_WARPS) * 32;  // warps 0-3 build A, warp 4 issues MMAs (and owns TMEM), then epilogue
 constexpr int CT_A_BYTES = 4 * 128 * 16;   // [k chunk of 4][128 rows][16 B]
 constexpr int CT_W_BYTES = 4 * 256 * 16;   // [k chunk of 4][256 ch][16 B]
 constexpr int CT_XS = 648;                 // samples of one tile (645 used)
 constexpr int CT_OFF_A = 0;                         // [2]
 constexpr int CT_OFF_W = 2 * CT_A_BYTES;
-constexpr int CT_OFF_STG = CT_OFF_W + CT_W_BYTES;   // [half][2] x (128 rows x 64 B)
-constexpr int CT_OFF_XS = CT_OFF_STG + 4 * 8192;    // float [2][CT_XS]
+static_assert(CT_CHUNKS == 2, "the staging tile is 32 rows x 128 B (64 channels per warp), SWIZZLE_128B");
+constexpr int CT_OFF_STG = CT_OFF_W + CT_W_BYTES;   // [epilogue warp][2] x (32 rows x 128 B)
+constexpr int CT_OFF_XS = CT_OFF_STG + CT_EPI_WARPS * 8192;    // float [2][CT_XS]
 constexpr int CT_OFF_RS = CT_OFF_XS + 2 * CT_XS * 4;  // float [4][128]
 constexpr int CT_OFF_BE = CT_OFF_RS + 4 * 128 * 4;    // float [256]
 constexpr int CT_OFF_BAR = CT_OFF_BE + 256 * 4;
 constexpr int CT_SMEM = CT_OFF_BAR + 128 + 1024 /*alignment slack*/;
 
 struct alignas(64) Conv0TcParams {
-  CUtensorMap tma_out;  // (256, L0, nseq) bf16 over the padded activation buffer, box (32, 128, 1), SW64
+  CUtensorMap tma_out;  // (256, L0, nseq) bf16 over the padded activation buffer, box (64, 32, 1), SW128
   const float* wav;
   const float* u;     // [10][256] folded taps
   const float* d;     // [256] folded offsets
@@ -92,7 +98,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
       mbar_init(a_full(b), 128);
       mbar_init(a_empty(b), 1);
       mbar_init(tfull(b), 1);
-      mbar_init(tempty(b), 256);
+      mbar_init(tempty(b), CT_EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -203,14 +209,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ===== epilogue: thread = (accumulator row, column half)
-    const int quad = warp & 3, half = (warp - 5) >> 2;
+    // ===== epilogue: thread = (accumulator row, column group); each warp stores its own 32 rows
+    const int quad = warp & 3, grp = (warp - 5) >> 2;
     const int row = quad * 32 + lane;
-    const bool leader = (warp == 5 + 4 * half) && lane == 0;
-    const int cbase = half * 128;
-    const uint32_t stg_addr = smem_base + CT_OFF_STG + half * 16384;
-    uint8_t* stg_gen = smem_gen + CT_OFF_STG + half * 16384;
-    const uint32_t sw64 = (uint32_t)((row >> 1) & 3);
+    const int cbase = grp * (32 * CT_CHUNKS);
+    const uint32_t stg_addr = smem_base + CT_OFF_STG + (uint32_t)(warp - 5) * 8192u;
+    uint8_t* stg_gen = smem_gen + CT_OFF_STG + (warp - 5) * 8192;
+    const uint32_t sw128 = (uint32_t)(lane & 7);
     uint32_t stg_cnt = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -222,10 +227,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 256 + cbase;
       uint32_t r[2][32];
       tmem_ld32(taddr, r[0]);
+      // warp staging tile: 32 rows x 128 B (this warp's 64 channels), SWIZZLE_128B (16-byte chunk j of row r at
+      // r*128 + ((j ^ (r & 7)) << 4)), two buffers: the store that read this buffer two tiles ago must have drained it
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const uint32_t boff = (stg_cnt & 1u) * 4096u;
+      uint8_t* rowp = stg_gen + boff + (uint32_t)lane * 128u;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CT_CHUNKS; ++c) {
         tmem_ld_wait();
-        if (c < 3) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        if (c + 1 < CT_CHUNKS) tmem_ld32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -237,27 +248,22 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
           pk[i >> 1] = pack16(fmaxf(v0, 0.f), fmaxf(v1, 0.f), p.fp16);
           pk[(i >> 1) + 1] = pack16(fmaxf(v2, 0.f), fmaxf(v3, 0.f), p.fp16);
         }
-        // staging tile: 128 rows x 64 B, SWIZZLE_64B (chunk j of row r at r*64 + ((j ^ (r/2 & 3)) << 4)), two buffers
-        if (leader) bulk_wait_read<1>();
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-        const uint32_t boff = (stg_cnt & 1u) * 8192u;
-        uint8_t* rowp = stg_gen + boff + (uint32_t)row * 64u;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) =
+          *reinterpret_cast<uint4*>(rowp + (((uint32_t)(c * 4 + j) ^ sw128) << 4)) =
               make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        fence_proxy_async();
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-        if (leader) {
-          tma_store_3d(&p.tma_out, stg_addr + boff, cbase + c * 32, f0, lseq);
-          bulk_commit();
-        }
-        ++stg_cnt;
       }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&p.tma_out, stg_addr + boff, cbase, f0 + quad * 32, lseq);
+        bulk_commit();
+      }
+      ++stg_cnt;
       tc_fence_before();
       mbar_arrive(tempty(buf));
     }
-    if (leader) bulk_wait<0>();
+    if (lane == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -276,8 +282,8 @@ int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_sa
   {
     const uint64_t dims[3] = {(uint64_t)kDim, (uint64_t)L0, (uint64_t)nseq};
     const uint64_t strides[2] = {(uint64_t)kDim, (uint64_t)out_seq_stride};
-    const uint32_t box[3] = {32, 128, 1};
-    if (!make_tmap(&p.tma_out, out + (long long)out_pad_rows * kDim, 2, 3, dims, strides, box, 64, err)) return -1;
+    const uint32_t box[3] = {64, 32, 1};
+    if (!make_tmap(&p.tma_out, out + (long long)out_pad_rows * kDim, 2, 3, dims, strides, box, 128, err)) return -1;
   }
   p.wav = wav;
   p.u = u;
