@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvapb.so")
+LIB_PATH = os.environ.get("VAPB_LIB") or os.path.join(_HERE, "libvapb.so")  # VAPB_LIB: A/B a second build
 
 MODE_FP32, MODE_BF16, MODE_FP16 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "fp16": MODE_FP16}
