@@ -35,3 +35,15 @@ for i in range(1, 27):
     r = [int(x) for x in d[i]]
     ch = [r[2] - r[1]] + [r[2 + j] - r[1 + j] for j in range(1, 6)]
     print(f"{i:3d} | {r[1]-r[0]:6d} | " + " ".join(f"{c:5d}" for c in ch) + f" | {r[8]-r[7]:6d} | {r[9]-r[8]:6d} | {r[10]-r[9]:6d} | {r[10]-r[0]:6d}")
+
+ts = []
+for _ in range(10):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    lib.vapb_debug_ffn_fused(st, z.data_ptr(), w1.data_ptr(), w2.data_ptr(), rb.data_ptr(), xo.data_ptr(), xs.data_ptr(),
+                             zn.data_ptr(), g2.data_ptr(), b2.data_ptr(), M, err, 512, None)
+    b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+ts.sort()
+print(f"kernel time (median of 10): {ts[5] * 1e3:.1f} us")

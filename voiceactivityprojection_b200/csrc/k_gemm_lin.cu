@@ -20,6 +20,7 @@
 // (measured: 2.36 GB through L2 for a 1 GB qkv GEMM). CTAs that share an M tile but own different W slices
 // walk the M tiles in lockstep, so A is fetched from HBM once.
 // TMEM loads are double-buffered against the math; GELU is a packed-FMA polynomial (gelu_poly2).
+#include <cstdlib>
 #include <string>
 
 #include "common.cuh"
@@ -77,6 +78,7 @@ struct alignas(64) LinParams {
   int norm2;
   const float *g2, *b2;
   int fp16;  // 16-bit operand / output format: 0 bf16, 1 fp16
+  int prefetch;  // L2-prefetch the A rows of the tile this many tiles ahead (env VAPB_LIN_PREFETCH; 0 = off)
 };
 
 // GELU(erf) for two values with packed fp32 FMAs and no MUFU: gelu(x) = relu(x) + g(|x|), where
@@ -200,6 +202,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
         mbar_arrive_expect_tx(w_full, 4 * LB_BYTES);
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem_base + kb * LB_BYTES, &p.tma_b, w_full, kb * LBK, my_nt * LBN);
       }
+      // The ring holds 3-4 k-blocks (48-64 KB) per SM; at ~1.5 us of DRAM latency that is ~32 GB/s per SM, which is
+      // what the K = 256 GEMMs ran at (ncu: the epilogue warps idle on tfull, the tensor pipe 44 % active). The A rows
+      // of the tile PF tiles ahead are therefore pulled into L2 while this tile loads.
+      const int PF = p.prefetch;
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= num_tiles) return;
+        const int mt = tile_mt(tile);
+        const int seq = mt / p.tiles_per_seq, t0 = (mt % p.tiles_per_seq) * LBM;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_prefetch_3d(&p.tma_a, kb * LBK, t0, seq);
+      };
+      for (int i = 1; i < PF; ++i) prefetch_tile(tile_first + i * tile_stride);
       for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
         const int mt = tile_mt(tile), nt = tile_nt(tile);
         const int seq = mt / p.tiles_per_seq, t0 = (mt % p.tiles_per_seq) * LBM;
@@ -211,6 +224,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
           if (!WRES) tma_load_2d(a_dst + LA_BYTES, &p.tma_b, full_bar(stage), kb * LBK, nt * LBN);
           if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
         }
+        if (PF) prefetch_tile(tile + PF * tile_stride);  // behind this tile's own loads in the TMA queue
       }
     }
   } else if (warp == 1) {
@@ -521,6 +535,13 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
   p.has_o1_bf16 = a.out1_bf16 != nullptr;
   p.norm2 = e.norm2; p.g2 = e.g2; p.b2 = e.b2;
   p.fp16 = g_fp16;
+  {
+    // measured on 512 000 x 256 inputs (tools/lin_probe.py): N = 768 243 -> 191 us and N = 512 169 -> 133 us two tiles
+    // ahead, N = 256 97 -> 90 us one tile ahead (two: 95, three or more: slower than none)
+    static const int env_pf = [] { const char* v = getenv("VAPB_LIN_PREFETCH"); return v ? atoi(v) : -1; }();
+    const int auto_pf = a.N > LBN ? 2 : 1;
+    p.prefetch = a.K <= 512 ? (env_pf >= 0 ? env_pf : auto_pf) : 0;  // long-K tiles would park hundreds of KB per SM in L2
+  }
   const int need = ((e.bias || e.norm1 != NORM_NONE) ? F_PRE : 0) | (e.act != ACT_NONE ? F_ACT : 0) |
                    (e.resid ? F_RESID : 0) | (e.accumulate ? F_ACC : 0) | (p.f32_mode == 1 ? F_F32B : 0) |
                    (p.f32_mode == 2 ? F_F32R : 0) | (p.has_o1_bf16 ? F_O1B : 0) | (e.norm2 != NORM_NONE ? F_N2 : 0);
