@@ -539,7 +539,8 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
     // measured on 512 000 x 256 inputs (tools/lin_probe.py): N = 768 243 -> 191 us and N = 512 169 -> 133 us two tiles
     // ahead, N = 256 97 -> 90 us one tile ahead (two: 95, three or more: slower than none)
     static const int env_pf = [] { const char* v = getenv("VAPB_LIN_PREFETCH"); return v ? atoi(v) : -1; }();
-    const int auto_pf = a.N > LBN ? 2 : 1;
+    // with a residual the epilogue already prefetches 128 KB of fp32 rows per tile and A prefetch costs 2-9 %
+    const int auto_pf = a.e.resid ? 0 : (a.N > LBN ? 2 : 1);
     p.prefetch = a.K <= 512 ? (env_pf >= 0 ? env_pf : auto_pf) : 0;  // long-K tiles would park hundreds of KB per SM in L2
   }
   const int need = ((e.bias || e.norm1 != NORM_NONE) ? F_PRE : 0) | (e.act != ACT_NONE ? F_ACT : 0) |
