@@ -3,6 +3,10 @@
 launch list: per-kernel launch count, total device time, share and (when captured) DRAM traffic.
 
     python tools/summarize_launches.py gpurun_out/launches.csv [--skip N] [--each] > profiles/<name>.md
+    python tools/summarize_launches.py gpurun_out/launches.csv --skip N --traffic-json profiles/<name>.json --steps K
+(--traffic-json: DRAM bytes and ncu time per kernel family and per bench step, the file bench.py reads for
+`roofline.traffic`; families as in csrc/model.h ProfCat, the downsample GEMM — the first gemm_lin after the
+recurrence — counted with the conv GEMMs as the live profile does.)
 """
 import csv
 import re
@@ -33,6 +37,33 @@ def main():
         d[r["Metric Name"]] = v
     rows = [d for i, d in launches.items() if i >= skip]
     have_dram = any("dram__bytes_read.sum" in d for d in rows)
+    if "--traffic-json" in sys.argv:
+        import json
+
+        out = sys.argv[sys.argv.index("--traffic-json") + 1]
+        steps = int(sys.argv[sys.argv.index("--steps") + 1])
+        fam_of = {"conv0_tc_kernel": "conv0", "gemm_2sm_kernel": "conv_gemm", "rnn_tc_kernel": "rnn",
+                  "attention_tc_kernel": "attention", "gemm_lin_kernel": "linear_gemm", "ffn_fused_kernel": "linear_gemm",
+                  "probs_kernel": "heads", "loss_kernel": "heads", "vad_head_blocked_kernel": "heads"}
+        fams, after_rnn = {}, False
+        for d in rows:
+            fam = fam_of.get(d["name"], "other")
+            if d["name"] == "rnn_tc_kernel":
+                after_rnn = True
+            elif after_rnn and d["name"] == "gemm_lin_kernel":
+                fam, after_rnn = "conv_gemm", False
+            f = fams.setdefault(fam, {"dram_bytes_per_step": 0.0, "launches": 0, "ncu_ms": 0.0})
+            f["dram_bytes_per_step"] += (d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)) / steps
+            f["launches"] += 1
+            f["ncu_ms"] += d.get("gpu__time_duration.sum", 0.0) / 1e3 / steps
+        for f in fams.values():
+            f["launches"] = f["launches"] // steps
+            f["ncu_ms"] = round(f["ncu_ms"], 3)
+        fams["_source"] = (f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over {steps} "
+                           f"step(s) of bench.py (bf16, B=256, 1 GPU; {path}, first {skip} launches skipped)")
+        json.dump(fams, open(out, "w"), indent=1)
+        print(json.dumps(fams, indent=1))
+        return
     if "--each" in sys.argv:
         print("| # | kernel | grid | us | dram rd MB | dram wr MB | GB/s |")
         print("|---|---|---|---:|---:|---:|---:|")
