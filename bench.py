@@ -314,6 +314,28 @@ def main():
             assert tot.chunks == world * B * n_e2e and comp["p_now"].shape[0] == world * B
             e2e["bulk"] = bulk
         del runner
+        # the same pipeline fed with the int16 PCM a wav file holds (BulkRunner(pcm16=True): half the H2D bytes, scaled
+        # on the device) — reported beside `e2e`, which keeps the reference's float32 waveforms; it matters when
+        # several GPUs share the host's PCIe uplinks
+        host_pcm = (host_wav * 32768.0).clamp_(-32768, 32767).to(torch.int16).pin_memory()
+        runner = BulkRunner(model, B, CHUNK_SAMPLES, precision=precision, keys=ALL_KEYS, stats=True, pcm16=True)
+        runner.run([host_pcm] * 2)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        runner.h2d_bytes = runner.d2h_bytes = 0
+        t0 = time.perf_counter()
+        runner.run((host_pcm for _ in range(n_e2e)), sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e["pcm16_input"] = {"value": total_chunks * CHUNK_SECONDS * n_e2e / dt, "unit": UNIT,
+                              "h2d_bytes_per_step": runner.h2d_bytes // n_e2e,
+                              "d2h_bytes_per_step": runner.d2h_bytes // n_e2e, "steps": n_e2e}
+        del runner, host_pcm
     clocks = sampler.stop() if sampler else None  # sampled over both timed regions (device-timed steps and e2e)
 
     # ---- roofline of the dominant kernel family: profiled pass of the same steps
