@@ -139,6 +139,7 @@ def workload_config(args, precision):
         "batch_per_gpu": args.batch, "precision": precision,
         "l2_policy": "inputs larger than L2 (waveform batch %.0f MB, activations GBs)" % (args.batch * 2.56),
         "weights": "synthetic seed 0 (reference schema, LSTMx1); shipped checkpoints are absent",
+        "audio": getattr(args, "audio", "noise"),
     }
 
 
@@ -196,6 +197,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--audio", default="noise", choices=["noise", "turns"],
+                    help="synthetic input: 0.05*N(0,1), or SURVEY §8d config 2's turn-taking variant (gated noise + tone)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -227,6 +230,8 @@ def main():
     # synthetic audio generated on the device, seeded by global chunk ids
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     wav = torch.randn((B, 2, CHUNK_SAMPLES), generator=gen, device=dev, dtype=torch.float32) * 0.05
+    if args.audio == "turns":
+        wav = synth.make_waveform(B, CHUNK_SAMPLES, 1 + rank, "turns").to(dev)
     if precision == "auto":
         try:
             model.probs(wav[:1], precision="bf16")
