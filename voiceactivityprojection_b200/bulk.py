@@ -156,8 +156,7 @@ class BulkRunner:
                     wav = resample_device(self.din[slot][:b], self.input_rate, self.model.sample_rate, out=self.dwav[:b])
                 elif self.pcm16:
                     wav = self.dwav[:b]
-                    wav.copy_(self.din[slot][:b])
-                    wav.mul_(1.0 / 32768.0)
+                    torch.mul(self.din[slot][:b], 1.0 / 32768.0, out=wav)  # one pass: int16 -> float32, exact scaling
                 else:
                     wav = self.din[slot][:b]
                 self.model.probs(wav, out=o, **kw)
