@@ -204,6 +204,20 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
 int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, int64_t T, int max_fill_frames,
                     int max_omit_frames, float* out);
 
+/* ZeroShot next-speaker / backchannel marginals: replaces ZeroShot.get_probs,
+ * probs_next_speaker, probs_on_silence, probs_on_active and probs_backchannel (vap/zero_shot.py:159-271) with one
+ * kernel. x: device fp32 (batch, T, 256) logits (is_probs 0: softmax applied, as get_probs :264-271) or class
+ * probabilities (is_probs 1). va: device fp32 (batch, va_T, 2) binary voice activity, va_T >= T, frames [0, T) of
+ * every item are used (`va[:, :nmax]`, :268); required only when p is requested. class_sets: HOST uint32 [10][8],
+ * ten 256-bit class sets (bit c%32 of word c/32 = class c): silence pos for next speaker 0 and 1, silence neg 0/1,
+ * active pos 0/1, active neg 0/1, backchannel 0/1 (ZeroShot.subset_silence, subset_silence_hold, subset_active,
+ * subset_active_hold, bc_prediction). Outputs, each device fp32 (batch, T, 2) or NULL: p = next-speaker
+ * probabilities by dialog state (vap/events.py:70-78), p_bc, p_sil = probs_on_silence, p_act = probs_on_active.
+ * A frame whose subsets carry zero probability gives 0/0 = NaN like the reference. `h` may be NULL. */
+int vapb_zero_shot(VapbHandle* h, void* stream, const float* x, int is_probs, int64_t batch, int64_t T,
+                   const float* va, int64_t va_T, const uint32_t* class_sets, float* p, float* p_bc, float* p_sil,
+                   float* p_act);
+
 /* Input path: rational polyphase resampling on the device, the arithmetic of
  * torchaudio.functional.resample (sinc_interp_hann) that vap/audio.py:65-68 applies after decoding a file.
  * orig/new are the two rates divided by their gcd. Input: `items` x `channels` rows of n_in samples, float32

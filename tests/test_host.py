@@ -218,3 +218,25 @@ def test_vap_extractor_stitching_and_minimal_outputs(tmp_path, skip_last):
     lines = open(p).read().strip().splitlines()
     assert lines[0] == "p_now,p_future,model_vad0,model_vad1,H,loss" and len(lines) == 1 + len(mo["p_now"])
     assert lines[-1].endswith(",0")  # loss is shorter than the frame axis: padded with 0 like json_data_to_df
+
+
+def test_zero_shot_mirror_builds_the_reference_subsets():
+    """voiceactivityprojection_b200.zero_shot.ZeroShot: same class subsets (values and order) as the reference's
+    (tests/golden/zero_shot.npz), packed into vapb_zero_shot's ten 256-bit sets; CPU tensors are refused."""
+    from conftest import GOLDEN_DIR
+    from voiceactivityprojection_b200.zero_shot import ZeroShot
+
+    g = np.load(os.path.join(GOLDEN_DIR, "zero_shot.npz"))
+    zs = ZeroShot(bin_times=[0.2, 0.4, 0.6, 0.8], frame_hz=50)
+    names = ["subset_silence", "subset_silence_hold", "subset_active", "subset_active_hold", "bc_prediction"]
+    for k in names:
+        assert np.array_equal(getattr(zs, k).numpy(), g[k]), k
+    for gi, k in enumerate(names):
+        for s in (0, 1):
+            words = [zs._sets[(2 * gi + s) * 8 + w] for w in range(8)]
+            members = [c for c in range(256) if (words[c // 32] >> (c % 32)) & 1]
+            assert members == sorted(g[k][s].tolist())
+    with pytest.raises(RuntimeError):
+        zs.get_probs(torch.zeros(1, 4, 256), torch.zeros(1, 4, 2))
+    with pytest.raises(NotImplementedError):
+        ZeroShot(bin_times=[0.2, 0.4], frame_hz=50)

@@ -158,3 +158,25 @@ def test_vad_filter_oracle_matches_reference_golden():
         fill, omit = g[n + "_par"]
         got = O.vad_filter(torch.from_numpy(g[n + "_in"]), float(fill), float(omit))
         assert torch.equal(got, torch.from_numpy(g[n + "_out"])), n
+
+
+def test_zero_shot_oracle_matches_reference_golden():
+    """oracle/zero_shot_oracle.py against the unmodified reference's ZeroShot (oracle/make_golden_zeroshot.py):
+    class subsets bit-exact, marginals within 1e-6 (float32 sums of <= 56 probabilities in a different order)."""
+    import numpy as np
+
+    from conftest import GOLDEN_DIR
+    from oracle import zero_shot_oracle as Z
+
+    g = np.load(f"{GOLDEN_DIR}/zero_shot.npz")
+    for k, v in Z.subsets().items():
+        assert np.array_equal(v, g[k]), k
+    for name in ("flat", "peaked", "odd"):
+        r = Z.get_probs(g[name + "_logits"], g[name + "_va"])
+        for k in ("p", "p_bc", "p_sil", "p_act"):
+            assert r[k].shape == g[f"{name}_{k}"].shape
+            assert np.abs(r[k] - g[f"{name}_{k}"]).max() <= 1e-6, (name, k)
+        # from probabilities instead of logits: same numbers
+        e = np.exp(g[name + "_logits"] - g[name + "_logits"].max(-1, keepdims=True))
+        r2 = Z.get_probs(e / e.sum(-1, keepdims=True), g[name + "_va"], is_probs=True)
+        assert np.array_equal(r2["p"], r["p"])

@@ -858,6 +858,24 @@ int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, 
   return cudaPeekAtLastError() == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
 }
 
+int vapb_zero_shot(VapbHandle* h, void* stream, const float* x, int is_probs, int64_t batch, int64_t T,
+                   const float* va, int64_t va_T, const uint32_t* class_sets, float* p, float* p_bc, float* p_sil,
+                   float* p_act) {
+  const char* e = nullptr;
+  if (!x || !class_sets) e = "zero_shot: NULL input";
+  else if (batch < 0 || T < 0 || T > 0x3fffffff) e = "zero_shot: invalid shape";
+  else if (p && (!va || va_T < T)) e = "zero_shot: p needs voice activity of at least T frames per item";
+  if (e) {
+    if (h) h->m.err = e; else g_create_err = e;
+    return VAPB_E_INVALID;
+  }
+  if (h) cudaSetDevice(h->m.device);
+  const int n = launch_zero_shot((cudaStream_t)stream, x, is_probs, batch, (int)T, va, va_T, class_sets, p, p_bc,
+                                 p_sil, p_act);
+  if (h) h->m.launches += n;
+  return cudaPeekAtLastError() == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
+}
+
 int vapb_resample(VapbHandle* h, void* stream, const void* x, int x_fmt, int64_t items, int channels, int64_t n_in,
                   int64_t item_stride, int64_t chan_stride, int64_t elem_stride, int orig, int new_rate, int width,
                   const float* bank, float* out, int64_t n_out, int64_t out_row_stride) {

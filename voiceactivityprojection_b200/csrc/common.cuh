@@ -142,6 +142,9 @@ int launch_resample(cudaStream_t st, const void* x, int x_fmt, long long items, 
                     long long item_stride, long long chan_stride, long long elem_stride, int orig, int new_, int width,
                     const float* bank, float* out, long long n_out, long long out_row_stride, std::string* err);
 int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out);
+int launch_zero_shot(cudaStream_t st, const float* x, int is_probs, long long batch, int T, const float* va,
+                     long long va_T, const uint32_t* sets /* host [10][8] */, float* p, float* p_bc, float* p_sil,
+                     float* p_act);
 int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
                  int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse,
                  uint8_t* argmax);

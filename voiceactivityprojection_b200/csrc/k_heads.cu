@@ -274,4 +274,126 @@ int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int
   return 1;
 }
 
+// ZeroShot marginals (vap/zero_shot.py:159-271). Ten class subsets arrive as 256-bit sets
+// (by value, 320 B of kernel parameters): 0-1 silence pos[next speaker 0/1], 2-3 silence neg, 4-5 active pos,
+// 6-7 active neg, 8-9 backchannel. Per frame: probs = softmax(logits) (or the input as is), then
+//   p_sil[s] = sum(pos_sil[s]) / (sum(pos_sil[s]) + sum(neg_sil[s])), p_act[s] likewise   (marginal_probs :159-165)
+//   p_bc[s]  = sum(bc[s])                                                                (probs_backchannel :173-176)
+//   dialog state ds = (long)(2 va1 - va0) + 1 (vap/events.py:70-78): 1 silence -> p = p_sil; 0 only A ->
+//   (1 - p_act[1], p_act[1]); 3 only B -> (p_act[0], 1 - p_act[0]); 2 both -> p_act / (p_act[0] + p_act[1]);
+//   anything else -> 0                                                                 (probs_next_speaker :226-262)
+// Same warp-per-PR-frames shape as probs_kernel: lane owns classes lane*4..+3 and 128+lane*4..+3, so a lane's
+// membership in the ten sets is 80 bits computed once.
+struct ZeroShotSets { uint32_t w[10][8]; };
+
+__global__ void __launch_bounds__(256)
+zero_shot_kernel(const float* __restrict__ x, int is_probs, long long rows, int T, const float* __restrict__ va,
+                 long long va_T, const ZeroShotSets sets, float* __restrict__ p_out, float* __restrict__ p_bc,
+                 float* __restrict__ p_sil, float* __restrict__ p_act) {
+  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PR;
+  const int lane = threadIdx.x & 31;
+  if (row0 >= rows) return;
+  // classes lane*4..+3 are bits (lane&7)*4..+3 of word lane>>3; classes 128+lane*4..+3 the same bits of word 4+(lane>>3)
+  uint32_t member[10];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    const uint32_t lo = (sets.w[q][lane >> 3] >> ((lane & 7) * 4)) & 0xfu;
+    const uint32_t hi = (sets.w[q][4 + (lane >> 3)] >> ((lane & 7) * 4)) & 0xfu;
+    member[q] = lo | (hi << 4);
+  }
+  float v[PR][8];
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;  // tail rows recompute the last row, never stored
+    const float* lr = x + row * kClasses;
+    const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
+    v[r][0] = a0.x; v[r][1] = a0.y; v[r][2] = a0.z; v[r][3] = a0.w;
+    v[r][4] = a1.x; v[r][5] = a1.y; v[r][6] = a1.z; v[r][7] = a1.w;
+  }
+  if (!is_probs) {
+    float mx[PR], s[PR];
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      mx[r] = v[r][0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) mx[r] = fmaxf(mx[r], v[r][j]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int r = 0; r < PR; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], off));
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      s[r] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[r][j] = expf(v[r][j] - mx[r]);
+        s[r] += v[r][j];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int r = 0; r < PR; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const float inv = 1.0f / s[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[r][j] *= inv;
+    }
+  }
+  float acc[PR][10];
+#pragma unroll
+  for (int r = 0; r < PR; ++r)
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a += ((member[q] >> j) & 1u) ? v[r][j] : 0.f;
+      acc[r][q] = a;
+    }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int r = 0; r < PR; ++r)
+#pragma unroll
+      for (int q = 0; q < 10; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], off);
+  if (lane != 0) return;
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    const long long row = row0 + r;
+    if (row >= rows) break;
+    const float sil0 = acc[r][0] / (acc[r][0] + acc[r][2]), sil1 = acc[r][1] / (acc[r][1] + acc[r][3]);
+    const float act0 = acc[r][4] / (acc[r][4] + acc[r][6]), act1 = acc[r][5] / (acc[r][5] + acc[r][7]);
+    if (p_sil) *reinterpret_cast<float2*>(p_sil + row * 2) = make_float2(sil0, sil1);
+    if (p_act) *reinterpret_cast<float2*>(p_act + row * 2) = make_float2(act0, act1);
+    if (p_bc) *reinterpret_cast<float2*>(p_bc + row * 2) = make_float2(acc[r][8], acc[r][9]);
+    if (p_out) {
+      const long long b = row / T, t = row % T;
+      const float2 a = *reinterpret_cast<const float2*>(va + (b * va_T + t) * 2);
+      const long long ds = (long long)(2.0f * a.y - a.x) + 1;
+      float pa = 0.f, pb = 0.f;
+      if (ds == 1) { pa = sil0; pb = sil1; }
+      else if (ds == 0) { pa = 1.0f - act1; pb = act1; }
+      else if (ds == 3) { pa = act0; pb = 1.0f - act0; }
+      else if (ds == 2) { const float sum = act0 + act1; pa = act0 / sum; pb = act1 / sum; }
+      *reinterpret_cast<float2*>(p_out + row * 2) = make_float2(pa, pb);
+    }
+  }
+}
+
+int launch_zero_shot(cudaStream_t st, const float* x, int is_probs, long long batch, int T, const float* va,
+                     long long va_T, const uint32_t* sets /* host [10][8] */, float* p, float* p_bc, float* p_sil,
+                     float* p_act) {
+  const long long rows = batch * T;
+  if (rows <= 0) return 0;
+  ZeroShotSets zs;
+  for (int q = 0; q < 10; ++q)
+    for (int w = 0; w < 8; ++w) zs.w[q][w] = sets[q * 8 + w];
+  zero_shot_kernel<<<(unsigned)((rows + 8 * PR - 1) / (8 * PR)), 256, 0, st>>>(x, is_probs, rows, T, va, va_T, zs, p,
+                                                                               p_bc, p_sil, p_act);
+  return 1;
+}
+
 }  // namespace vapb
