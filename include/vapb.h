@@ -213,7 +213,8 @@ int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, 
  * active pos 0/1, active neg 0/1, backchannel 0/1 (ZeroShot.subset_silence, subset_silence_hold, subset_active,
  * subset_active_hold, bc_prediction). Outputs, each device fp32 (batch, T, 2) or NULL: p = next-speaker
  * probabilities by dialog state (vap/events.py:70-78), p_bc, p_sil = probs_on_silence, p_act = probs_on_active.
- * A frame whose subsets carry zero probability gives 0/0 = NaN like the reference. `h` may be NULL. */
+ * A frame whose subsets carry zero probability gives 0/0 = NaN like the reference. A set may hold at most 64
+ * classes (the reference's largest has 56): VAPB_E_UNSUPPORTED otherwise. `h` may be NULL. */
 int vapb_zero_shot(VapbHandle* h, void* stream, const float* x, int is_probs, int64_t batch, int64_t T,
                    const float* va, int64_t va_T, const uint32_t* class_sets, float* p, float* p_bc, float* p_sil,
                    float* p_act);

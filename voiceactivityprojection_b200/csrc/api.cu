@@ -872,6 +872,11 @@ int vapb_zero_shot(VapbHandle* h, void* stream, const float* x, int is_probs, in
   if (h) cudaSetDevice(h->m.device);
   const int n = launch_zero_shot((cudaStream_t)stream, x, is_probs, batch, (int)T, va, va_T, class_sets, p, p_bc,
                                  p_sil, p_act);
+  if (n < 0) {
+    e = "zero_shot: a class set holds more than 64 classes";
+    if (h) h->m.err = e; else g_create_err = e;
+    return VAPB_E_UNSUPPORTED;
+  }
   if (h) h->m.launches += n;
   return cudaPeekAtLastError() == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
 }

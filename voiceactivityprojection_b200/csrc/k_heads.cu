@@ -274,125 +274,169 @@ int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int
   return 1;
 }
 
-// ZeroShot marginals (vap/zero_shot.py:159-271). Ten class subsets arrive as 256-bit sets
-// (by value, 320 B of kernel parameters): 0-1 silence pos[next speaker 0/1], 2-3 silence neg, 4-5 active pos,
-// 6-7 active neg, 8-9 backchannel. Per frame: probs = softmax(logits) (or the input as is), then
+// ZeroShot marginals (vap/zero_shot.py:159-271). Ten class subsets: 0-1 silence pos[next
+// speaker 0/1], 2-3 silence neg, 4-5 active pos, 6-7 active neg, 8-9 backchannel. Per frame: probs = softmax(logits)
+// (or the input as is), then
 //   p_sil[s] = sum(pos_sil[s]) / (sum(pos_sil[s]) + sum(neg_sil[s])), p_act[s] likewise   (marginal_probs :159-165)
 //   p_bc[s]  = sum(bc[s])                                                                (probs_backchannel :173-176)
 //   dialog state ds = (long)(2 va1 - va0) + 1 (vap/events.py:70-78): 1 silence -> p = p_sil; 0 only A ->
 //   (1 - p_act[1], p_act[1]); 3 only B -> (p_act[0], 1 - p_act[0]); 2 both -> p_act / (p_act[0] + p_act[1]);
 //   anything else -> 0                                                                 (probs_next_speaker :226-262)
-// Same warp-per-PR-frames shape as probs_kernel: lane owns classes lane*4..+3 and 128+lane*4..+3, so a lane's
-// membership in the ten sets is 80 bits computed once.
-struct ZeroShotSets { uint32_t w[10][8]; };
+// HBM-bound (1 KB read, 16-32 B written per frame), so the point is to keep the instruction count per frame low:
+// a warp takes ZR = 8 frames per pass. Phase 1 (lane owns classes lane*4..+3 and 128+lane*4..+3, coalesced float4
+// loads, as probs_kernel): row max, exp, row sum by shuffles; the un-normalised exponentials go to a padded
+// shared-memory tile. Phase 2 (four lanes per frame): every subset is a list of class indices (the subsets are
+// sparse: 4 to 56 of 256 classes, 160 members in all, padded to fours with a zero slot), lane s of a frame's quad
+// adds members s, s+4, ... from the tile; two shuffles per subset finish the sums and the quad's first lane does the divisions and the dialog-state
+// switch. Row stride 260 floats: frame r / class c sits in bank (4r + c) mod 32, so the phase-1 float4 stores and
+// the quad-strided phase-2 reads are conflict-free. (A first version kept class-per-lane ownership for the subset
+// sums too: 80 masked adds and 50 shuffles per frame, 1.3 TB/s; this one is 3x fewer instructions.)
+constexpr int ZR = 8, ZSTRIDE = 260, ZWARPS = 4, ZMAXN = 64;
+struct ZeroShotLists {
+  uint16_t off[10][ZMAXN];  // byte offsets (4 * class) of each subset's members within a tile row, ascending class,
+                            // padded to a multiple of 4 entries with 1024 = the row's zero slot
+  int n4[10];               // entries / 4 = gather iterations per lane
+};
 
-__global__ void __launch_bounds__(256)
+// exp(d), d <= 0, in 6 instructions instead of expf's ~15 (range checks and branches made expf half of this
+// kernel's instruction stream): ex2.approx(d * log2e) with the rounding error of that product and of the constant
+// carried in a first-order correction, so small terms keep ~2 ulp relative accuracy like the reference's exp.
+__device__ __forceinline__ float exp_neg(float d) {
+  const float L_HI = 1.44269502162933349609375f, L_LO = 1.925963033500011e-8f, LN2 = 0.693147182464599609375f;
+  d = fmaxf(d, -120.0f);  // exp underflows to 0 (ftz) long before; keeps a -inf logit from turning t_lo into NaN
+  const float t = d * L_HI;
+  const float t_lo = fmaf(d, L_LO, fmaf(d, L_HI, -t));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e * t_lo, LN2, e);
+}
+
+__global__ void __launch_bounds__(ZWARPS * 32)
 zero_shot_kernel(const float* __restrict__ x, int is_probs, long long rows, int T, const float* __restrict__ va,
-                 long long va_T, const ZeroShotSets sets, float* __restrict__ p_out, float* __restrict__ p_bc,
-                 float* __restrict__ p_sil, float* __restrict__ p_act) {
-  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PR;
-  const int lane = threadIdx.x & 31;
+                 long long va_T, const __grid_constant__ ZeroShotLists lists, float* __restrict__ p_out,
+                 float* __restrict__ p_bc, float* __restrict__ p_sil, float* __restrict__ p_act) {
+  __shared__ __align__(16) float tile[ZWARPS][ZR * ZSTRIDE];
+  __shared__ float inv_sum[ZWARPS][ZR];
+  __shared__ uint16_t members[10][ZMAXN];
+  for (int i = threadIdx.x; i < 10 * ZMAXN; i += ZWARPS * 32) members[i / ZMAXN][i % ZMAXN] = lists.off[i / ZMAXN][i % ZMAXN];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * ZWARPS + warp) * ZR;
   if (row0 >= rows) return;
-  // classes lane*4..+3 are bits (lane&7)*4..+3 of word lane>>3; classes 128+lane*4..+3 the same bits of word 4+(lane>>3)
-  uint32_t member[10];
+  float* const mine = tile[warp];
+  if (lane < ZR) *reinterpret_cast<float4*>(mine + lane * ZSTRIDE + 256) = make_float4(0.f, 0.f, 0.f, 0.f);  // pad slot
+  // ---- phase 1: exponentials of ZR frames into the tile, two batches of four frames (independent shuffle chains)
+#pragma unroll
+  for (int half = 0; half < ZR / 4; ++half) {
+    float v[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long row = row0 + half * 4 + r < rows ? row0 + half * 4 + r : rows - 1;  // tail: recomputed, never stored
+      const float* lr = x + row * kClasses;
+      const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
+      v[r][0] = a0.x; v[r][1] = a0.y; v[r][2] = a0.z; v[r][3] = a0.w;
+      v[r][4] = a1.x; v[r][5] = a1.y; v[r][6] = a1.z; v[r][7] = a1.w;
+    }
+    if (!is_probs) {
+      float mx[4], s[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        mx[r] = v[r][0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) mx[r] = fmaxf(mx[r], v[r][j]);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], off));
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        s[r] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[r][j] = exp_neg(v[r][j] - mx[r]);
+          s[r] += v[r][j];
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) inv_sum[warp][half * 4 + r] = 1.0f / s[r];
+      }
+    } else if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) inv_sum[warp][half * 4 + r] = 1.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float* er = mine + (half * 4 + r) * ZSTRIDE;
+      *reinterpret_cast<float4*>(er + lane * 4) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+      *reinterpret_cast<float4*>(er + 128 + lane * 4) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+    }
+  }
+  __syncwarp();
+  // ---- phase 2: subset sums, four lanes per frame
+  const int r = lane >> 2, s = lane & 3;
+  const char* er = reinterpret_cast<const char*>(mine + r * ZSTRIDE);
+  float a[10];
 #pragma unroll
   for (int q = 0; q < 10; ++q) {
-    const uint32_t lo = (sets.w[q][lane >> 3] >> ((lane & 7) * 4)) & 0xfu;
-    const uint32_t hi = (sets.w[q][4 + (lane >> 3)] >> ((lane & 7) * 4)) & 0xfu;
-    member[q] = lo | (hi << 4);
+    const int n4 = lists.n4[q];  // uniform: no divergence, the lists are padded
+    float acc = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < n4; ++i) acc += *reinterpret_cast<const float*>(er + members[q][i * 4 + s]);
+    a[q] = acc;
   }
-  float v[PR][8];
 #pragma unroll
-  for (int r = 0; r < PR; ++r) {
-    const long long row = row0 + r < rows ? row0 + r : rows - 1;  // tail rows recompute the last row, never stored
-    const float* lr = x + row * kClasses;
-    const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
-    const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
-    v[r][0] = a0.x; v[r][1] = a0.y; v[r][2] = a0.z; v[r][3] = a0.w;
-    v[r][4] = a1.x; v[r][5] = a1.y; v[r][6] = a1.z; v[r][7] = a1.w;
+  for (int q = 0; q < 10; ++q) {
+    a[q] += __shfl_xor_sync(0xffffffffu, a[q], 1);
+    a[q] += __shfl_xor_sync(0xffffffffu, a[q], 2);
   }
-  if (!is_probs) {
-    float mx[PR], s[PR];
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      mx[r] = v[r][0];
-#pragma unroll
-      for (int j = 1; j < 8; ++j) mx[r] = fmaxf(mx[r], v[r][j]);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int r = 0; r < PR; ++r) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], off));
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      s[r] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[r][j] = expf(v[r][j] - mx[r]);
-        s[r] += v[r][j];
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int r = 0; r < PR; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], off);
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      const float inv = 1.0f / s[r];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[r][j] *= inv;
-    }
-  }
-  float acc[PR][10];
-#pragma unroll
-  for (int r = 0; r < PR; ++r)
-#pragma unroll
-    for (int q = 0; q < 10; ++q) {
-      float a = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a += ((member[q] >> j) & 1u) ? v[r][j] : 0.f;
-      acc[r][q] = a;
-    }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-    for (int r = 0; r < PR; ++r)
-#pragma unroll
-      for (int q = 0; q < 10; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], off);
-  if (lane != 0) return;
-#pragma unroll
-  for (int r = 0; r < PR; ++r) {
-    const long long row = row0 + r;
-    if (row >= rows) break;
-    const float sil0 = acc[r][0] / (acc[r][0] + acc[r][2]), sil1 = acc[r][1] / (acc[r][1] + acc[r][3]);
-    const float act0 = acc[r][4] / (acc[r][4] + acc[r][6]), act1 = acc[r][5] / (acc[r][5] + acc[r][7]);
-    if (p_sil) *reinterpret_cast<float2*>(p_sil + row * 2) = make_float2(sil0, sil1);
-    if (p_act) *reinterpret_cast<float2*>(p_act + row * 2) = make_float2(act0, act1);
-    if (p_bc) *reinterpret_cast<float2*>(p_bc + row * 2) = make_float2(acc[r][8], acc[r][9]);
-    if (p_out) {
-      const long long b = row / T, t = row % T;
-      const float2 a = *reinterpret_cast<const float2*>(va + (b * va_T + t) * 2);
-      const long long ds = (long long)(2.0f * a.y - a.x) + 1;
-      float pa = 0.f, pb = 0.f;
-      if (ds == 1) { pa = sil0; pb = sil1; }
-      else if (ds == 0) { pa = 1.0f - act1; pb = act1; }
-      else if (ds == 3) { pa = act0; pb = 1.0f - act0; }
-      else if (ds == 2) { const float sum = act0 + act1; pa = act0 / sum; pb = act1 / sum; }
-      *reinterpret_cast<float2*>(p_out + row * 2) = make_float2(pa, pb);
-    }
+  const long long row = row0 + r;
+  if (s != 0 || row >= rows) return;
+  const float inv = inv_sum[warp][r];
+  const float sil0 = a[0] / (a[0] + a[2]), sil1 = a[1] / (a[1] + a[3]);
+  const float act0 = a[4] / (a[4] + a[6]), act1 = a[5] / (a[5] + a[7]);
+  if (p_sil) *reinterpret_cast<float2*>(p_sil + row * 2) = make_float2(sil0, sil1);
+  if (p_act) *reinterpret_cast<float2*>(p_act + row * 2) = make_float2(act0, act1);
+  if (p_bc) *reinterpret_cast<float2*>(p_bc + row * 2) = make_float2(a[8] * inv, a[9] * inv);
+  if (p_out) {
+    const long long b = row / T, t = row % T;
+    const float2 w = *reinterpret_cast<const float2*>(va + (b * va_T + t) * 2);
+    const long long ds = (long long)(2.0f * w.y - w.x) + 1;
+    float pa = 0.f, pb = 0.f;
+    if (ds == 1) { pa = sil0; pb = sil1; }
+    else if (ds == 0) { pa = 1.0f - act1; pb = act1; }
+    else if (ds == 3) { pa = act0; pb = 1.0f - act0; }
+    else if (ds == 2) { const float sum = act0 + act1; pa = act0 / sum; pb = act1 / sum; }
+    *reinterpret_cast<float2*>(p_out + row * 2) = make_float2(pa, pb);
   }
 }
 
+// sets: host [10][8] uint32, ten 256-bit class sets (bit c%32 of word c/32 = class c). Returns launches or -1
+// (a subset of more than ZMAXN classes).
 int launch_zero_shot(cudaStream_t st, const float* x, int is_probs, long long batch, int T, const float* va,
-                     long long va_T, const uint32_t* sets /* host [10][8] */, float* p, float* p_bc, float* p_sil,
-                     float* p_act) {
+                     long long va_T, const uint32_t* sets, float* p, float* p_bc, float* p_sil, float* p_act) {
   const long long rows = batch * T;
   if (rows <= 0) return 0;
-  ZeroShotSets zs;
-  for (int q = 0; q < 10; ++q)
-    for (int w = 0; w < 8; ++w) zs.w[q][w] = sets[q * 8 + w];
-  zero_shot_kernel<<<(unsigned)((rows + 8 * PR - 1) / (8 * PR)), 256, 0, st>>>(x, is_probs, rows, T, va, va_T, zs, p,
-                                                                               p_bc, p_sil, p_act);
+  ZeroShotLists zl{};
+  for (int q = 0; q < 10; ++q) {
+    int n = 0;
+    for (int c = 0; c < 256; ++c)
+      if ((sets[q * 8 + c / 32] >> (c % 32)) & 1u) {
+        if (n == ZMAXN) return -1;
+        zl.off[q][n++] = (uint16_t)(c * 4);
+      }
+    while (n % 4) zl.off[q][n++] = 1024;
+    zl.n4[q] = n / 4;
+  }
+  const long long tasks = (rows + ZR - 1) / ZR;
+  zero_shot_kernel<<<(unsigned)((tasks + ZWARPS - 1) / ZWARPS), ZWARPS * 32, 0, st>>>(x, is_probs, rows, T, va, va_T,
+                                                                                      zl, p, p_bc, p_sil, p_act);
   return 1;
 }
 
