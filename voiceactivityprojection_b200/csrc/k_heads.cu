@@ -73,6 +73,19 @@ int launch_vad_head(cudaStream_t st, const float* x, const float* w, const float
   return 1;
 }
 
+// exp(d), d <= 0, in 7 instructions instead of expf's ~15 (range checks and branches; it was half of
+// zero_shot_kernel's instruction stream): ex2.approx(d * log2e) with the rounding error of that product and of the constant
+// carried in a first-order correction, so small terms keep ~2 ulp relative accuracy like the reference's exp.
+__device__ __forceinline__ float exp_neg(float d) {
+  const float L_HI = 1.44269502162933349609375f, L_LO = 1.925963033500011e-8f, LN2 = 0.693147182464599609375f;
+  d = fmaxf(d, -120.0f);  // exp underflows to 0 (ftz) long before; keeps a -inf logit from turning t_lo into NaN
+  const float t = d * L_HI;
+  const float t_lo = fmaf(d, L_LO, fmaf(d, L_HI, -t));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e * t_lo, LN2, e);
+}
+
 // One warp handles PR frames at a time (independent shuffle chains interleave); lane owns classes
 // lane*4..+3 and 128+lane*4..+3, whose codebook bit counts are fixed per lane and computed once.
 constexpr int PR = 4;
@@ -128,7 +141,7 @@ probs_kernel(const float* __restrict__ logits, long long rows, int now_lo, int n
     s[r] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v[r][j] = expf(v[r][j] - mx[r]);
+      v[r][j] = expf(v[r][j] - mx[r]);  // exp_neg measured no faster here (heads 0.32 ms either way)
       s[r] += v[r][j];
     }
   }
@@ -282,57 +295,69 @@ int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int
 //   dialog state ds = (long)(2 va1 - va0) + 1 (vap/events.py:70-78): 1 silence -> p = p_sil; 0 only A ->
 //   (1 - p_act[1], p_act[1]); 3 only B -> (p_act[0], 1 - p_act[0]); 2 both -> p_act / (p_act[0] + p_act[1]);
 //   anything else -> 0                                                                 (probs_next_speaker :226-262)
-// HBM-bound (1 KB read, 16-32 B written per frame), so the point is to keep the instruction count per frame low:
-// a warp takes ZR = 8 frames per pass. Phase 1 (lane owns classes lane*4..+3 and 128+lane*4..+3, coalesced float4
-// loads, as probs_kernel): row max, exp, row sum by shuffles; the un-normalised exponentials go to a padded
-// shared-memory tile. Phase 2 (four lanes per frame): every subset is a list of class indices (the subsets are
-// sparse: 4 to 56 of 256 classes, 160 members in all, padded to fours with a zero slot), lane s of a frame's quad
-// adds members s, s+4, ... from the tile; two shuffles per subset finish the sums and the quad's first lane does the divisions and the dialog-state
-// switch. Row stride 260 floats: frame r / class c sits in bank (4r + c) mod 32, so the phase-1 float4 stores and
-// the quad-strided phase-2 reads are conflict-free. (A first version kept class-per-lane ownership for the subset
-// sums too: 80 masked adds and 50 shuffles per frame, 1.3 TB/s; this one is 3x fewer instructions.)
-constexpr int ZR = 8, ZSTRIDE = 260, ZWARPS = 4, ZMAXN = 64;
+// HBM-bound (1 KB read, 16-32 B written per frame), so the point is to keep the instruction count and the exposed
+// latency per frame low: a warp takes ZR = 8 frames per block lifetime.
+// Staging: the eight 1 KB rows go global -> shared memory by cp.async (16 B per lane per copy, all 16 in flight at
+// once, no registers held). Phase 1 (lane owns classes lane*4..+3 and 128+lane*4..+3, as probs_kernel): row max,
+// exp, row sum by shuffles, four frames at a time; the un-normalised exponentials overwrite the tile. Phase 2 (four
+// lanes per frame): every subset is a list of class indices (the subsets are sparse: 4 to 56 of 256 classes, 160
+// members in all, padded to fours with a zero slot), lane s of a frame's quad adds members s, s+4, ... from the
+// tile; two shuffles per subset finish the sums and the quad's first lane does the divisions and the dialog-state
+// switch. Row stride 260 floats: frame r / class c sits in bank (4r + c) mod 32, so the float4 accesses and the
+// quad-strided phase-2 reads are conflict-free.
+// History on a B=256 x T=1000 batch (tools/zero_shot_probe.py): class-per-lane subset sums (80 masked adds + 50
+// shuffles per frame) 205 us; tile + member lists 112; compensated ex2 instead of expf (whose range checks and
+// branches were half the instruction stream) 96; list copy behind the loads instead of in front of them 88;
+// cp.async staging 80 us = 3.3 TB/s. 217 warp instructions per frame put the issue floor at ~49 us, above the 41 us
+// HBM floor; higher occupancy (4 frames per warp) and a 3-instruction exp measured no faster.
+constexpr int ZR = 8, ZLPR = 32 / ZR, ZSTRIDE = 260, ZWARPS = 4, ZMAXN = 64;  // ZLPR lanes per frame in phase 2
 struct ZeroShotLists {
   uint16_t off[10][ZMAXN];  // byte offsets (4 * class) of each subset's members within a tile row, ascending class,
                             // padded to a multiple of 4 entries with 1024 = the row's zero slot
-  int n4[10];               // entries / 4 = gather iterations per lane
+  int n4[10];               // entries / ZLPR = gather iterations per lane
 };
 
-// exp(d), d <= 0, in 6 instructions instead of expf's ~15 (range checks and branches made expf half of this
-// kernel's instruction stream): ex2.approx(d * log2e) with the rounding error of that product and of the constant
-// carried in a first-order correction, so small terms keep ~2 ulp relative accuracy like the reference's exp.
-__device__ __forceinline__ float exp_neg(float d) {
-  const float L_HI = 1.44269502162933349609375f, L_LO = 1.925963033500011e-8f, LN2 = 0.693147182464599609375f;
-  d = fmaxf(d, -120.0f);  // exp underflows to 0 (ftz) long before; keeps a -inf logit from turning t_lo into NaN
-  const float t = d * L_HI;
-  const float t_lo = fmaf(d, L_LO, fmaf(d, L_HI, -t));
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-  return fmaf(e * t_lo, LN2, e);
-}
-
-__global__ void __launch_bounds__(ZWARPS * 32)
+#ifndef ZS_MINBLOCKS
+#define ZS_MINBLOCKS 6  // shared memory allows six blocks per SM; keep registers within that
+#endif
+__global__ void __launch_bounds__(ZWARPS * 32, ZS_MINBLOCKS)
 zero_shot_kernel(const float* __restrict__ x, int is_probs, long long rows, int T, const float* __restrict__ va,
                  long long va_T, const __grid_constant__ ZeroShotLists lists, float* __restrict__ p_out,
                  float* __restrict__ p_bc, float* __restrict__ p_sil, float* __restrict__ p_act) {
   __shared__ __align__(16) float tile[ZWARPS][ZR * ZSTRIDE];
   __shared__ float inv_sum[ZWARPS][ZR];
   __shared__ uint16_t members[10][ZMAXN];
-  for (int i = threadIdx.x; i < 10 * ZMAXN; i += ZWARPS * 32) members[i / ZMAXN][i % ZMAXN] = lists.off[i / ZMAXN][i % ZMAXN];
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * ZWARPS + warp) * ZR;
-  if (row0 >= rows) return;
+  const bool active = row0 < rows;
   float* const mine = tile[warp];
+  const int r = lane / ZLPR, s = lane % ZLPR;  // phase 2: frame and position in the frame's quad
+  float2 w = make_float2(0.f, 0.f);            // the frame's voice activity, fetched now (a load at the point of
+  if (active && p_out && s == 0 && row0 + r < rows) {  // use stalled every warp for a DRAM round trip at its end)
+    const long long row = row0 + r;
+    w = *reinterpret_cast<const float2*>(va + ((row / T) * va_T + row % T) * 2);
+  }
+  if (active) {
   if (lane < ZR) *reinterpret_cast<float4*>(mine + lane * ZSTRIDE + 256) = make_float4(0.f, 0.f, 0.f, 0.f);  // pad slot
   // ---- phase 1: exponentials of ZR frames into the tile, two batches of four frames (independent shuffle chains)
+  // all ZR rows leave for the tile at once (16 B per lane per copy, no registers held while they fly)
+#pragma unroll
+  for (int rr = 0; rr < ZR; ++rr) {
+    const long long row = row0 + rr < rows ? row0 + rr : rows - 1;  // tail: recomputed, never stored
+    const float* lr = x + row * kClasses + lane * 4;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(mine + rr * ZSTRIDE + lane * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(lr) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u), "l"(lr + 128) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 #pragma unroll
   for (int half = 0; half < ZR / 4; ++half) {
     float v[4][8];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const long long row = row0 + half * 4 + r < rows ? row0 + half * 4 + r : rows - 1;  // tail: recomputed, never stored
-      const float* lr = x + row * kClasses;
+      const float* lr = mine + (half * 4 + r) * ZSTRIDE;
       const float4 a0 = *reinterpret_cast<const float4*>(lr + lane * 4);
       const float4 a1 = *reinterpret_cast<const float4*>(lr + 128 + lane * 4);
       v[r][0] = a0.x; v[r][1] = a0.y; v[r][2] = a0.z; v[r][3] = a0.w;
@@ -378,23 +403,32 @@ zero_shot_kernel(const float* __restrict__ x, int is_probs, long long rows, int 
       *reinterpret_cast<float4*>(er + 128 + lane * 4) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
     }
   }
-  __syncwarp();
+  }
+  // the member lists travel as kernel parameters; their copy to shared memory (per-thread constant-bank reads, slow)
+  // sits here, behind the block's global loads, not in front of them
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&lists.off[0][0]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&members[0][0]);
+    for (int i = threadIdx.x; i < 10 * ZMAXN / 2; i += ZWARPS * 32) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (!active) return;
   // ---- phase 2: subset sums, four lanes per frame
-  const int r = lane >> 2, s = lane & 3;
   const char* er = reinterpret_cast<const char*>(mine + r * ZSTRIDE);
   float a[10];
 #pragma unroll
   for (int q = 0; q < 10; ++q) {
-    const int n4 = lists.n4[q];  // uniform: no divergence, the lists are padded
-    float acc = 0.f;
-#pragma unroll 2
-    for (int i = 0; i < n4; ++i) acc += *reinterpret_cast<const float*>(er + members[q][i * 4 + s]);
+    // every list holds at least one group of four (padded), most hold exactly one: straight-line first gather,
+    // then a uniform loop for the rest (no divergence: n4 is the same for every lane)
+    const int n4 = lists.n4[q];
+    float acc = *reinterpret_cast<const float*>(er + members[q][s]);
+    for (int i = 1; i < n4; ++i) acc += *reinterpret_cast<const float*>(er + members[q][i * ZLPR + s]);
     a[q] = acc;
   }
 #pragma unroll
   for (int q = 0; q < 10; ++q) {
-    a[q] += __shfl_xor_sync(0xffffffffu, a[q], 1);
-    a[q] += __shfl_xor_sync(0xffffffffu, a[q], 2);
+#pragma unroll
+    for (int off = 1; off < ZLPR; off <<= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], off);
   }
   const long long row = row0 + r;
   if (s != 0 || row >= rows) return;
@@ -405,8 +439,6 @@ zero_shot_kernel(const float* __restrict__ x, int is_probs, long long rows, int 
   if (p_act) *reinterpret_cast<float2*>(p_act + row * 2) = make_float2(act0, act1);
   if (p_bc) *reinterpret_cast<float2*>(p_bc + row * 2) = make_float2(a[8] * inv, a[9] * inv);
   if (p_out) {
-    const long long b = row / T, t = row % T;
-    const float2 w = *reinterpret_cast<const float2*>(va + (b * va_T + t) * 2);
     const long long ds = (long long)(2.0f * w.y - w.x) + 1;
     float pa = 0.f, pb = 0.f;
     if (ds == 1) { pa = sil0; pb = sil1; }
@@ -431,8 +463,8 @@ int launch_zero_shot(cudaStream_t st, const float* x, int is_probs, long long ba
         if (n == ZMAXN) return -1;
         zl.off[q][n++] = (uint16_t)(c * 4);
       }
-    while (n % 4) zl.off[q][n++] = 1024;
-    zl.n4[q] = n / 4;
+    while (n % ZLPR || n == 0) zl.off[q][n++] = 1024;
+    zl.n4[q] = n / ZLPR;
   }
   const long long tasks = (rows + ZR - 1) / ZR;
   zero_shot_kernel<<<(unsigned)((tasks + ZWARPS - 1) / ZWARPS), ZWARPS * 32, 0, st>>>(x, is_probs, rows, T, va, va_T,
