@@ -91,6 +91,18 @@ int vapb_forward(VapbHandle* h, void* stream, const float* wav, int batch, int64
                  int mode, void* workspace, size_t workspace_bytes, float* logits,
                  float* vad_logits);
 
+/* VapGPT.forward(waveform, attention=True) (vap/model.py:249-268): the forward of vapb_forward in FP32 mode
+ * plus the attention maps the reference returns, softmax(q k^T / 16 + 1 + m_h j) with zeros above the diagonal
+ * (vap/modules.py:82-110, 169-202), as device fp32:
+ *   self_attn       [batch][2][channel_layers][heads][T][T]  (ar_channel; vap/modules.py:342-358)
+ *   cross_attn      [batch][2][cross_layers][heads][T][T]    (stereo layers' cross-attention; :380-408)
+ *   cross_self_attn [batch][2][cross_layers][heads][T][T]    (stereo layers' self-attention)
+ * Index 1 is the speaker channel. The maps are a diagnostic output (4 T^2 floats per head and layer): every
+ * element is written, the caller sizes the batch. Workspace as vapb_workspace_bytes(mode = VAPB_MODE_FP32). */
+int vapb_forward_attention(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples,
+                           void* workspace, size_t workspace_bytes, float* logits, float* vad_logits,
+                           float* self_attn, float* cross_attn, float* cross_self_attn);
+
 /* VapGPT.probs(waveform, now_lims, future_lims) (vap/model.py:180-225), fused
  * with the forward. Outputs, all device fp32:
  *   probs (batch,T,256), vad (batch,T,2) = sigmoid, p_now (batch,T,2),

@@ -162,8 +162,10 @@ def alibi_mask(m: Tensor, T: int) -> Tensor:
     return alibi.unsqueeze(-2) + mask
 
 
-def mha_alibi(sd, prefix: str, Q: Tensor, K: Tensor, V: Tensor, n_heads: int = 4) -> Tensor:
-    """vap/modules.py:82-110 + 189-202. No biases; scale = 1/sqrt(dim) (F7)."""
+def mha_alibi(sd, prefix: str, Q: Tensor, K: Tensor, V: Tensor, n_heads: int = 4,
+              maps: Optional[list] = None) -> Tensor:
+    """vap/modules.py:82-110 + 189-202. No biases; scale = 1/sqrt(dim) (F7). `maps`: list that receives the
+    (B, H, T, T) attention weights the reference returns next to y (:104-110)."""
     B, T, D = Q.shape
     hd = D // n_heads
 
@@ -176,6 +178,8 @@ def mha_alibi(sd, prefix: str, Q: Tensor, K: Tensor, V: Tensor, n_heads: int = 4
     att = torch.einsum("bhid,bhjd->bhij", q, k) * (1.0 / (D ** 0.5))
     att = att + alibi_mask(sd[prefix + "m"].to(att.dtype), T)
     att = F.softmax(att, dim=-1)
+    if maps is not None:
+        maps.append(att)
     y = (att @ v).transpose(1, 2).reshape(B, T, D)
     return F.linear(y, sd[prefix + "proj.weight"])
 
@@ -185,13 +189,14 @@ def _ln(sd, prefix: str, x: Tensor) -> Tensor:
 
 
 def transformer_layer(sd, prefix: str, x: Tensor, src: Optional[Tensor] = None,
-                      n_heads: int = 4) -> Tensor:
+                      n_heads: int = 4, self_maps: Optional[list] = None,
+                      cross_maps: Optional[list] = None) -> Tensor:
     """vap/modules.py:246-275 (pre-LN; cross-attention K/V = un-normalised src)."""
     z = _ln(sd, prefix + "ln_self_attn.", x)
-    x = x + mha_alibi(sd, prefix + "mha.", z, z, z, n_heads)
+    x = x + mha_alibi(sd, prefix + "mha.", z, z, z, n_heads, self_maps)
     if src is not None:
         z = _ln(sd, prefix + "ln_src_attn.", x)
-        x = x + mha_alibi(sd, prefix + "mha_cross.", z, src, src, n_heads)
+        x = x + mha_alibi(sd, prefix + "mha_cross.", z, src, src, n_heads, cross_maps)
     h = F.linear(_ln(sd, prefix + "ln_ffnetwork.", x), sd[prefix + "ffnetwork.0.weight"])
     x = x + F.linear(F.gelu(h), sd[prefix + "ffnetwork.3.weight"])
     return x
@@ -204,20 +209,22 @@ def _count(sd, fmt: str) -> int:
     return n
 
 
-def gpt(sd, x: Tensor, n_heads: int = 4) -> Tensor:
-    """vap/modules.py:342-358 (ar_channel)."""
+def gpt(sd, x: Tensor, n_heads: int = 4, maps: Optional[list] = None) -> Tensor:
+    """vap/modules.py:342-358 (ar_channel); `maps` receives one (B, H, T, T) per layer."""
     for l in range(_count(sd, "ar_channel.layers.{}.ln_self_attn.weight")):
-        x = transformer_layer(sd, f"ar_channel.layers.{l}.", x, None, n_heads)
+        x = transformer_layer(sd, f"ar_channel.layers.{l}.", x, None, n_heads, maps)
     return x
 
 
-def gpt_stereo(sd, x1: Tensor, x2: Tensor, n_heads: int = 4, stages=None):
+def gpt_stereo(sd, x1: Tensor, x2: Tensor, n_heads: int = 4, stages=None, maps: Optional[dict] = None):
     """vap/modules.py:380-408, 287-289 (both directions read the layer INPUT)
-    and Combinator 446-449 (one shared LayerNorm)."""
+    and Combinator 446-449 (one shared LayerNorm). `maps`: dict of four lists
+    (self_a, cross_a, self_b, cross_b; :385-395), one entry per layer."""
+    m = maps if maps is not None else {"self_a": None, "cross_a": None, "self_b": None, "cross_b": None}
     for l in range(_count(sd, "ar.layers.{}.ln_self_attn.weight")):
         p = f"ar.layers.{l}."
-        z1 = transformer_layer(sd, p, x1, x2, n_heads)
-        z2 = transformer_layer(sd, p, x2, x1, n_heads)
+        z1 = transformer_layer(sd, p, x1, x2, n_heads, m["self_a"], m["cross_a"])
+        z2 = transformer_layer(sd, p, x2, x1, n_heads, m["self_b"], m["cross_b"])
         x1, x2 = z1, z2
         if stages is not None:
             stages[f"ar{l}_x1"], stages[f"ar{l}_x2"] = x1, x2
@@ -230,8 +237,9 @@ def gpt_stereo(sd, x1: Tensor, x2: Tensor, n_heads: int = 4, stages=None):
 # model facade                                                                #
 # --------------------------------------------------------------------------- #
 def forward(sd: Dict[str, Tensor], waveform: Tensor, n_heads: int = 4,
-            stages: Optional[dict] = None) -> Dict[str, Tensor]:
-    """vap/model.py:249-268 (attention=False). waveform (B, 2, S)."""
+            stages: Optional[dict] = None, attention: bool = False) -> Dict[str, Tensor]:
+    """vap/model.py:249-268. waveform (B, 2, S). attention=True adds self_attn (B, 2, Lc, H, T, T),
+    cross_attn and cross_self_attn (B, 2, Lx, H, T, T) (:262-266, modules.py:397-406)."""
     assert waveform.shape[1] == 2, f"audio VAP ENCODER: {waveform.shape} != (B, 2, n_samples)"
     s1 = {} if stages is not None else None
     x1 = encoder(sd, waveform[:, :1], s1)
@@ -239,18 +247,26 @@ def forward(sd: Dict[str, Tensor], waveform: Tensor, n_heads: int = 4,
     if stages is not None:
         stages.update({k + "_1": v for k, v in s1.items()})
         stages["enc_2"] = x2
-    o1 = gpt(sd, x1, n_heads)
-    o2 = gpt(sd, x2, n_heads)
+    a1, a2 = ([], []) if attention else (None, None)
+    sm = {"self_a": [], "cross_a": [], "self_b": [], "cross_b": []} if attention else None
+    o1 = gpt(sd, x1, n_heads, a1)
+    o2 = gpt(sd, x2, n_heads, a2)
     if stages is not None:
         stages["ch_1"], stages["ch_2"] = o1, o2
-    x, x1, x2 = gpt_stereo(sd, o1, o2, n_heads, stages)
+    x, x1, x2 = gpt_stereo(sd, o1, o2, n_heads, stages, sm)
     if stages is not None:
         stages["comb"] = x
     v1 = F.linear(x1, sd["va_classifier.weight"], sd["va_classifier.bias"])
     v2 = F.linear(x2, sd["va_classifier.weight"], sd["va_classifier.bias"])
     vad = torch.cat((v1, v2), dim=-1)
     logits = F.linear(x, sd["vap_head.weight"], sd["vap_head.bias"])
-    return {"logits": logits, "vad": vad}
+    ret = {"logits": logits, "vad": vad}
+    if attention:
+        ret["self_attn"] = torch.stack([torch.stack(a1, dim=1), torch.stack(a2, dim=1)], dim=1)
+        ret["cross_attn"] = torch.stack([torch.stack(sm["cross_a"], dim=1), torch.stack(sm["cross_b"], dim=1)], dim=1)
+        ret["cross_self_attn"] = torch.stack([torch.stack(sm["self_a"], dim=1), torch.stack(sm["self_b"], dim=1)],
+                                             dim=1)
+    return ret
 
 
 def code_vectors(total_bins: int = 8) -> Tensor:

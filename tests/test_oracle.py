@@ -180,3 +180,17 @@ def test_zero_shot_oracle_matches_reference_golden():
         e = np.exp(g[name + "_logits"] - g[name + "_logits"].max(-1, keepdims=True))
         r2 = Z.get_probs(e / e.sum(-1, keepdims=True), g[name + "_va"], is_probs=True)
         assert np.array_equal(r2["p"], r["p"])
+
+
+def test_oracle_attention_maps_match_reference_golden():
+    """forward(attention=True): oracle maps bit-identical to the unmodified reference's
+    (oracle/make_golden_attention.py), shapes (B, 2, layers, H, T, T), and unchanged logits."""
+    recipe, arrays = load_golden("attention_maps_T70")
+    sd, wav = golden_inputs(recipe, arrays)
+    with torch.no_grad():
+        out = O.forward(sd, wav, attention=True)
+        plain = O.forward(sd, wav)
+    assert out["self_attn"].shape == (1, 2, 1, 4, 70, 70) and out["cross_attn"].shape == (1, 2, 3, 4, 70, 70)
+    for k in ("logits", "vad", "self_attn", "cross_attn", "cross_self_attn"):
+        assert torch.equal(out[k], arrays[k]), k
+    assert torch.equal(out["logits"], plain["logits"]) and set(plain) == {"logits", "vad"}

@@ -24,6 +24,7 @@ SYMBOLS = {
     "vapb_frames": (_i, [_i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "vapb_workspace_bytes": (_i, [_vp, _i, _i64, _i, C.POINTER(_sz)]),
     "vapb_forward": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _fp, _fp]),
+    "vapb_forward_attention": (_i, [_vp, _vp, _fp, _i, _i64, _vp, _sz] + [_fp] * 5),
     "vapb_probs": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _i, _i, _i, _i] + [_fp] * 9),
     "vapb_probs_from_logits": (_i, [_vp, _vp, _fp, _i64, _i, _i, _i, _i] + [_fp] * 5),
     "vapb_get_stage": (_i, [_vp, _vp, C.c_char_p, _i, _i64, _i, _vp, _sz, _fp, _sz]),

@@ -574,6 +574,27 @@ int vapb_forward(VapbHandle* h, void* stream, const float* wav, int batch, int64
   return VAPB_OK;
 }
 
+int vapb_forward_attention(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples,
+                           void* workspace, size_t workspace_bytes, float* logits, float* vad_logits,
+                           float* self_attn, float* cross_attn, float* cross_self_attn) {
+  if (!h || !wav || !workspace || !logits || !vad_logits || !self_attn || !cross_attn || !cross_self_attn)
+    return VAPB_E_INVALID;
+  Model& m = h->m;
+  if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
+  CallPlan cp;
+  std::string err;
+  int rc = plan_all(m, batch, n_samples, VAPB_MODE_FP32, &cp, &err);
+  if (rc) return fail(m, rc, err);
+  if (workspace_bytes < cp.aux.bytes) return fail(m, VAPB_E_WORKSPACE, "workspace too small");
+  CUDA_OK(m, cudaSetDevice(m.device));
+  const AttnMaps maps{self_attn, cross_attn, cross_self_attn};
+  const float* comb = nullptr;
+  rc = forward_fp32(m, (cudaStream_t)stream, wav, cp.g, (char*)workspace, logits, vad_logits, nullptr, &comb, &maps);
+  if (rc) return rc;
+  CUDA_OK(m, cudaPeekAtLastError());
+  return VAPB_OK;
+}
+
 int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t n_samples, int mode,
                void* workspace, size_t workspace_bytes, int now_lo, int now_hi, int fut_lo, int fut_hi,
                float* logits, float* vad_logits, float* probs, float* vad, float* p_now, float* p_future, float* H,

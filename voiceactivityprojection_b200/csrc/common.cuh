@@ -107,6 +107,9 @@ int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string*
 int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
                      long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence
 
+int launch_attention_map_f32(cudaStream_t st, const float* q, long long q_row_stride, const float* k,
+                             long long kv_row_stride, int nseq, int T, int n_heads, const float* slopes, int cross,
+                             float* maps /*[batch][2][n_layers][H][T][T]*/, int batch, int n_layers, int layer);
 int launch_attention_f32(cudaStream_t st, const float* q, long long q_row_stride, const float* k,
                          const float* v, long long kv_row_stride, float* out, int nseq, int T, int n_heads,
                          const float* slopes, int kv_seq_xor_half /* cross: K/V of seq (s+nseq/2)%nseq */);

@@ -95,7 +95,7 @@ Epilogue epi_plain(float* out, int N) {
 size_t workspace_bytes_fp32(const Model& m, const Geometry& g) { return make_plan(m, g).bytes; }
 
 int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float**) {
+                 float* vad_logits, float* vad_sig, const float**, const AttnMaps* maps) {
   const Plan32 p = make_plan(m, g);
   const Weights& w = m.w32;
   Ctx cx{m, st};
@@ -195,7 +195,13 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     if (cross) cx.gemm(x_in, dense(kDim), lw.wkv_c, MT, MT, 2 * kDim, kDim, epi_plain(F(p.kvc), 2 * kDim));
     { ProfScope ps(m, st, CAT_ATTN);
     m.launches += launch_attention_f32(st, F(p.qkv), 3 * kDim, F(p.qkv) + kDim, F(p.qkv) + 2 * kDim, 3 * kDim,
-                                       F(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0); }
+                                       F(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0);
+    if (maps)
+      m.launches += launch_attention_map_f32(st, F(p.qkv), 3 * kDim, F(p.qkv) + kDim, 3 * kDim, nseq, (int)T,
+                                             m.num_heads, lw.slopes, 0,
+                                             cross ? maps->cross_self_attn : maps->self_attn, g.batch,
+                                             cross ? m.cross_layers : m.channel_layers,
+                                             cross ? li - m.channel_layers : li); }
     const float* x_mid = nullptr;
     {
       Epilogue e{};
@@ -215,7 +221,11 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       cx.gemm(F(p.z), dense(kDim), lw.wq_c, MT, MT, kDim, kDim, epi_plain(F(p.qc), kDim));
       { ProfScope ps(m, st, CAT_ATTN);
       m.launches += launch_attention_f32(st, F(p.qc), kDim, F(p.kvc), F(p.kvc) + kDim, 2 * kDim, F(p.y), nseq,
-                                         (int)T, m.num_heads, lw.slopes_cross, 1); }
+                                         (int)T, m.num_heads, lw.slopes_cross, 1);
+      if (maps)
+        m.launches += launch_attention_map_f32(st, F(p.qc), kDim, F(p.kvc), 2 * kDim, nseq, (int)T, m.num_heads,
+                                               lw.slopes_cross, 1, maps->cross_attn, g.batch, m.cross_layers,
+                                               li - m.channel_layers); }
       Epilogue e{};
       e.resid = x_mid;
       e.resid_map = dense(kDim);

@@ -168,6 +168,120 @@ attention_f32_kernel(const TIO* __restrict__ q, long long q_row_stride, const TI
   }
 }
 
+// Attention MAPS for VapGPT.forward(attention=True) (vap/model.py:262-266; MultiHeadAttentionAlibi returns
+// `(y, att)`, vap/modules.py:82-110): softmax(q k^T / 16 + 1 + m_h j, -inf above the diagonal) written out as
+// fp32 (T, T) per (item, channel, layer, head). A diagnostic output (B x 2 x L x H x T x T floats), so the kernel
+// is the plain three-pass form of the fused one above: row max, row sum with that max, then the normalised
+// weights; same thread mapping, arithmetic order of the scores identical to attention_f32_kernel.
+// maps: [batch][2][n_layers][H][T][T]; sequence seq = c * batch + b goes to item b, channel c.
+__global__ void __launch_bounds__(ATHREADS)
+attention_map_f32_kernel(const float* __restrict__ q, long long q_row_stride, const float* __restrict__ k,
+                         long long kv_row_stride, int nseq, int T, const float* __restrict__ slopes, int cross,
+                         float* __restrict__ maps, int batch, int n_layers, int layer) {
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;           // [AQ][ALD]
+  float* Ks = Qs + AQ * ALD;  // [AK][ALD]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z, H = gridDim.y;
+  const int kvseq = cross ? (seq + nseq / 2) % nseq : seq;
+  const float slope = slopes[head];
+  const float* qb = q + ((long long)seq * T) * q_row_stride + head * AD;
+  const float* kb = k + ((long long)kvseq * T) * kv_row_stride + head * AD;
+  const int q0 = qt * AQ;
+  float* out = maps + ((((long long)(seq % batch) * 2 + seq / batch) * n_layers + layer) * H + head) * T * T;
+  for (int idx = tid; idx < AQ * AD / 4; idx += ATHREADS) {
+    const int r = idx >> 4, d4 = (idx & 15) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) x = load4(qb + (long long)(q0 + r) * q_row_stride + d4);
+    *reinterpret_cast<float4*>(&Qs[r * ALD + d4]) = x;
+  }
+  float mrow[4], lrow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { mrow[i] = -INFINITY; lrow[i] = 0.f; }
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int kt = 0; kt <= qt; ++kt) {
+      const int k0 = kt * AK;
+      __syncthreads();
+      for (int idx = tid; idx < AK * AD / 4; idx += ATHREADS) {
+        const int r = idx >> 4, d4 = (idx & 15) * 4;
+        float4 kx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + r < T) kx = load4(kb + (long long)(k0 + r) * kv_row_stride + d4);
+        *reinterpret_cast<float4*>(&Ks[r * ALD + d4]) = kx;
+      }
+      __syncthreads();
+      float s[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+      for (int d4 = 0; d4 < AD; d4 += 4) {
+        float4 qf[4], kf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qf[i] = *reinterpret_cast<const float4*>(&Qs[(ty * 4 + i) * ALD + d4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) kf[j] = *reinterpret_cast<const float4*>(&Ks[(tx + 16 * j) * ALD + d4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s[i][j] = fmaf(qf[i].x, kf[j].x, s[i][j]);
+            s[i][j] = fmaf(qf[i].y, kf[j].y, s[i][j]);
+            s[i][j] = fmaf(qf[i].z, kf[j].z, s[i][j]);
+            s[i][j] = fmaf(qf[i].w, kf[j].w, s[i][j]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int qi = q0 + ty * 4 + i;
+        float acc = pass == 0 ? -INFINITY : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kj = k0 + tx + 16 * j;
+          const float bias = __fadd_rn(__fmul_rn(slope, (float)kj), 1.0f);  // (m*j) + 1, no FMA contraction
+          float x = s[i][j] * 0.0625f + bias;
+          if (kj > qi || kj >= T) x = -INFINITY;
+          if (pass == 0) {
+            acc = fmaxf(acc, x);
+          } else {
+            const float e = expf(x - mrow[i]);
+            if (pass == 1) acc += e;
+            else if (qi < T && kj < T) out[(long long)qi * T + kj] = e / lrow[i];
+          }
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) acc = fmaxf(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+          mrow[i] = fmaxf(mrow[i], acc);
+        } else if (pass == 1) {
+#pragma unroll
+          for (int off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          lrow[i] += acc;
+        }
+      }
+    }
+  }
+  // keys beyond this query tile's last key tile are all above the diagonal
+  const int kz = (qt + 1) * AK;
+  if (kz < T) {
+    const int w = T - kz;
+    for (int idx = tid; idx < AQ * w; idx += ATHREADS) {
+      const int r = idx / w, c = idx % w;
+      if (q0 + r < T) out[(long long)(q0 + r) * T + kz + c] = 0.f;
+    }
+  }
+}
+
+int launch_attention_map_f32(cudaStream_t st, const float* q, long long q_row_stride, const float* k,
+                             long long kv_row_stride, int nseq, int T, int n_heads, const float* slopes, int cross,
+                             float* maps, int batch, int n_layers, int layer) {
+  const int smem = 2 * AQ * ALD * 4;
+  dim3 grid((unsigned)((T + AQ - 1) / AQ), (unsigned)n_heads, (unsigned)nseq);
+  attention_map_f32_kernel<<<grid, ATHREADS, smem, st>>>(q, q_row_stride, k, kv_row_stride, nseq, T, slopes, cross,
+                                                         maps, batch, n_layers, layer);
+  return 1;
+}
+
 template <typename TIO>
 static int launch_attn(cudaStream_t st, const TIO* q, long long q_row_stride, const TIO* k, const TIO* v,
                        long long kv_row_stride, TIO* out, int nseq, int T, int n_heads, const float* slopes,

@@ -145,8 +145,12 @@ struct StageRef {
 
 // ---- FP32 path (forward_fp32.cu) -------------------------------------------
 size_t workspace_bytes_fp32(const Model& m, const Geometry& g);
+// Optional attention-map outputs of forward(attention=True) (vap/model.py:262-266), fp32 path only:
+// self_attn [B][2][channel_layers][H][T][T] (ar_channel), cross_self_attn / cross_attn [B][2][cross_layers][H][T][T]
+// (the stereo layers' self- and cross-attention). Pointers address item 0 of the call.
+struct AttnMaps { float *self_attn, *cross_attn, *cross_self_attn; };
 int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float** comb_out);
+                 float* vad_logits, float* vad_sig, const float** comb_out, const AttnMaps* maps = nullptr);
 int stage_fp32(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
 // ---- BF16 tensor-core path (forward_bf16.cu) --------------------------------

@@ -10,8 +10,8 @@ ctypes). There is no CPU implementation: CPU tensors raise.
 Differences a caller can see:
   * `VapGPT()` needs no CPC checkpoint; the gAR cell (LSTM/GRU) and depth are
     inferred from the state dict in `load_state_dict`.
-  * `forward(..., attention=True)` raises NotImplementedError (attention maps are
-    never materialised).
+  * `forward(..., attention=True)` returns the reference's attention maps from a
+    separate fp32 map kernel (the fused attention kernels never materialise them).
   * `precision="fp32"` (default; CUDA-core FMA, parity with the reference),
     `"bf16"` or `"fp16"` (tcgen05 tensor cores; same kernels and speed, fp16
     operands give ~8x lower error) — constructor keyword, attribute, or env
@@ -242,13 +242,28 @@ class VapGPT(nn.Module):
 
     @torch.no_grad()
     def forward(self, waveform: Tensor, attention: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
-        """vap/model.py:249-268 -> {"logits": (B,T,256), "vad": (B,T,2)} (vad = logits)."""
-        if attention:
-            raise NotImplementedError("attention=True: the fused attention kernels never materialise (B,H,T,T) maps")
+        """vap/model.py:249-268 -> {"logits": (B,T,256), "vad": (B,T,2)} (vad = logits).
+        attention=True adds the reference's "self_attn" (B,2,channel_layers,H,T,T), "cross_attn" and
+        "cross_self_attn" (B,2,cross_layers,H,T,T): a diagnostic output, computed by the fp32 path with a separate
+        map kernel per attention (vapb_forward_attention); the fused attention kernels never materialise them."""
         wav = self._check_input(waveform)
         B, _, S = wav.shape
         lib, h = _lib.load(), self._ensure_handle()
         _, T = _lib.frames(S)
+        if attention:
+            if precision not in (None, "fp32"):
+                raise ValueError("attention=True runs in fp32 mode")
+            ws = self._workspace(B, S, _lib.MODE_FP32)
+            f = dict(dtype=torch.float32, device=wav.device)
+            H, Lc, Lx = self.conf.num_heads, self.conf.channel_layers, self.conf.cross_layers
+            ret = {"logits": torch.empty((B, T, 256), **f), "vad": torch.empty((B, T, 2), **f),
+                   "self_attn": torch.empty((B, 2, Lc, H, T, T), **f),
+                   "cross_attn": torch.empty((B, 2, Lx, H, T, T), **f),
+                   "cross_self_attn": torch.empty((B, 2, Lx, H, T, T), **f)}
+            st = torch.cuda.current_stream(wav.device).cuda_stream
+            _lib.check(lib, h, lib.vapb_forward_attention(h, st, wav.data_ptr(), B, S, ws.data_ptr(), ws.numel(),
+                                                          *(ret[k].data_ptr() for k in ret)))
+            return ret
         mode = self._mode(precision)
         ws = self._workspace(B, S, mode)
         logits = torch.empty((B, T, 256), dtype=torch.float32, device=wav.device)
