@@ -64,6 +64,8 @@ def test_fp32_matches_reference_golden(name):
 
 
 def test_fp32_stages_match_reference_golden():
+    from oracle import vap_oracle as O
+
     recipe, g = load_golden("lstm1_turns_T125")
     sd, wav = golden_inputs(recipe, g)
     m = _model(sd)
@@ -78,6 +80,13 @@ def test_fp32_stages_match_reference_golden():
                                 ("comb", "stage_comb", 0, 2e-4)]:
         got = m.stage(name, x)[row: row + 1]
         assert _maxerr(got, g[key]) <= tol, (name, key)
+    # encode_audio (vap/model.py:169-175): the same encoder stage as two (B, T, 256) tensors
+    x1, x2 = m.encode_audio(x)
+    assert x1.shape == x2.shape == (B, 125, 256)
+    assert _maxerr(x1[:1], g["stage_enc"]) <= 5e-5
+    with torch.no_grad():
+        ref2 = O.encoder(sd, wav[:, 1:])
+    assert _maxerr(x2, ref2) <= 5e-5
 
 
 def test_fp32_matches_oracle_on_ragged_lengths_and_batch():

@@ -237,8 +237,14 @@ class VapGPT(nn.Module):
         return _lib.MODES[precision or self.precision]
 
     # ------------------------------------------------------------------ hot path
-    def encode_audio(self, audio: Tensor):
-        raise NotImplementedError("encode_audio is fused into forward(); use stage('enc', ...) for diagnostics")
+    @torch.no_grad()
+    def encode_audio(self, audio: Tensor, precision: Optional[str] = None):
+        """vap/model.py:169-175 -> (x1, x2), each (B, T, 256): the encoder output (CPC conv stack, gAR, 100 -> 50 Hz
+        downsample) of the two speaker channels. forward() does not call this (the encoder is the first part of
+        one fused call); it runs that call and reads the encoder stage back."""
+        x = self.stage("enc", audio, precision=precision)
+        B = audio.shape[0]
+        return x[:B], x[B:]
 
     @torch.no_grad()
     def forward(self, waveform: Tensor, attention: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
