@@ -9,7 +9,8 @@ The values come from numpy's PCG64 stream (stable across machines), not from
 torch's RNG, so the authoring container and the GPU box build bit-identical
 weights from a seed without shipping 23 MB files.
 
-Only tests/, __graft_entry__.smoke() and bench.py may import this module.
+An input generator, not an implementation of the path: tests/, tools/ (diagnostic probes), __graft_entry__.smoke()
+and bench.py import it for weights and waveforms; nothing under voiceactivityprojection_b200/ does.
 """
 from __future__ import annotations
 
