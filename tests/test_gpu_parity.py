@@ -521,14 +521,16 @@ def test_forward_attention_maps_match_reference_golden():
         assert (a.sum(-1) - 1).abs().max().item() <= 1e-5, k
 
 
-def test_forward_attention_maps_batch_and_tile_edges_vs_oracle():
-    """B = 3 items, T = 130 (three query tiles, last one ragged): item / channel / layer placement of every map
-    against the oracle. The allocator's free blocks are NaN-filled first, so an element the kernels skip shows."""
+@pytest.mark.parametrize("batch,n_samples", [(3, 41600), (2, 3200), (1, 20480)])
+def test_forward_attention_maps_batch_and_tile_edges_vs_oracle(batch, n_samples):
+    """B = 3 items, T = 130 (three query tiles, last one ragged), T = 10 (one partial tile) and T = 64 (exactly one
+    tile): item / channel / layer placement of every map against the oracle. The allocator's free blocks are
+    NaN-filled first, so an element the kernels skip shows."""
     from oracle import synth
     from oracle import vap_oracle as O
 
     sd = synth.make_state_dict(21, "GRU", 1, 2.0)
-    wav = synth.make_waveform(3, 41600, 9, "turns")
+    wav = synth.make_waveform(batch, n_samples, 9, "turns")
     with torch.no_grad():
         ref = O.forward(sd, wav, attention=True)
     m = _model(sd)
