@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   const uint32_t tmem_slot = bar_base + 8u * 22;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tq);
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer. The Q tile of the NEXT item is requested before the K/V tiles of the current one
@@ -420,7 +422,7 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
     configured = true;
   }
   const int grid = p.n_items < n_sm ? p.n_items : n_sm;
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(p);
+  launch_pdl(attention_tc_kernel, grid, AT_THREADS, AT_SMEM, st, p);
   return 1;
 }
 

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
   float* rs = reinterpret_cast<float*>(smem_gen + CT_OFF_RS);
   float* be = reinterpret_cast<float*>(smem_gen + CT_OFF_BE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tma_out);
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv0_tc_kernel(const __grid_co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();  // above: weights only
 
   const int num_tiles = p.nseq * p.tiles_per_seq;
   auto wav_of = [&](int tile, long long* s0) -> const float* {
@@ -307,7 +309,7 @@ int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_sa
   }
   const long long tiles = (long long)nseq * p.tiles_per_seq;
   const int grid = tiles < n_sm ? (int)tiles : n_sm;
-  conv0_tc_kernel<<<grid, CT_THREADS, CT_SMEM, st>>>(p);
+  launch_pdl(conv0_tc_kernel, grid, CT_THREADS, CT_SMEM, st, p);
   return 1;
 }
 

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   const uint32_t acco_empty = bar_base + 8 * 21; // final epilogue no longer reads ACC_O; 512 arrivals
   const uint32_t tmem_slot = bar_base + 8 * 22;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma_z);
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t t_acch = tmem_base /* 2 x 128 columns */, t_acco = tmem_base + 256;
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer: Z of the tile, then the W k-blocks in the order the MMA thread consumes them:
@@ -426,7 +428,7 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
     configured = true;
   }
   const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
-  ffn_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(p);
+  launch_pdl(ffn_fused_kernel, grid, F_THREADS, F_SMEM, st, p);
   return 1;
 }
 

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
   const uint32_t w_full = bar_base + 8u * 14;
   LinVecs& ev = *reinterpret_cast<LinVecs*>(smem_gen + L_OFF_VEC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma_a);
@@ -179,6 +180,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: everything above read only weights; the producer thread also requests its resident weight slice first
+  if (!(warp == 0 && lane == 0)) pdl_wait();
 
   // Tile walk. Streaming: (mt, nt) pairs strided over the grid. Weight-resident: the CTA's nt is fixed
   // (blockIdx % n_tiles_n) and it strides over M tiles with the CTAs of its group.
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
         mbar_arrive_expect_tx(w_full, 4 * LB_BYTES);
         for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem_base + kb * LB_BYTES, &p.tma_b, w_full, kb * LBK, my_nt * LBN);
       }
+      pdl_wait();
       // The ring holds 3-4 k-blocks (48-64 KB) per SM; at ~1.5 us of DRAM latency that is ~32 GB/s per SM, which is
       // what the K = 256 GEMMs ran at (ncu: the epilogue warps idle on tfull, the tensor pipe 44 % active). The A rows
       // of the tile PF tiles ahead are therefore pulled into L2 while this tile loads.
@@ -577,7 +581,7 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
     }
     v->configured[wres] = true;
   }
-  v->fn[wres]<<<grid, L_THREADS, smem, st>>>(p);
+  launch_pdl(v->fn[wres], grid, L_THREADS, smem, st, p);
   return 1;
 }
 

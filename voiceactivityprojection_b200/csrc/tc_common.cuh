@@ -2,6 +2,7 @@
 // (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / st / fences) and
 // the UMMA shared-memory / instruction descriptors. Inline PTX only.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -276,7 +277,40 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint
   return d;
 }
 
+// Programmatic dependent launch (opt-in, VAPB_PDL=1; see launch_pdl below). launch_dependents lets the next kernel of
+// the stream, if it was launched with the programmatic-serialisation attribute, start its CTAs as this kernel's
+// CTAs leave their SMs; wait blocks until every prerequisite grid has completed and its memory is visible. Both are
+// no-ops for a kernel launched the ordinary way. Every thread of a kernel launched through launch_pdl executes
+// pdl_wait() before its first access to anything another kernel wrote or reads (weights excepted), so completion
+// stays transitive along the stream.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace tc
+
+// Host: ordinary launch, or with cudaLaunchAttributeProgrammaticStreamSerialization when VAPB_PDL=1.
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VAPB_PDL"); return e && atoi(e) != 0; }();
+  return on;
+}
+template <typename P>
+inline void launch_pdl(void (*kern)(P), int grid, int threads, size_t smem, cudaStream_t st, const P& p) {
+  if (!pdl_enabled()) {
+    kern<<<grid, threads, smem, st>>>(p);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, p);
+}
 
 // Host side: the 16-bit format of the launches issued by this thread (set by forward_bf16 for the duration of a call;
 // the unit-test hooks leave it at 0 = bf16). Launchers copy it into their kernel parameters.
