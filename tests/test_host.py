@@ -240,3 +240,44 @@ def test_zero_shot_mirror_builds_the_reference_subsets():
         zs.get_probs(torch.zeros(1, 4, 256), torch.zeros(1, 4, 2))
     with pytest.raises(NotImplementedError):
         ZeroShot(bin_times=[0.2, 0.4], frame_hz=50)
+
+
+def _run_bench(args, env_extra=None, timeout=300):
+    import subprocess
+    import sys
+
+    env = dict(os.environ, **(env_extra or {}))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return subprocess.run([sys.executable, os.path.join(root, "bench.py"), *args], capture_output=True, text=True,
+                          env=env, timeout=timeout, cwd=root)
+
+
+def test_bench_reference_arm_prints_one_contract_line_and_only_on_rank_0():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores): exactly one JSON line on stdout
+    with the contract's keys; under a multi-rank launch only rank 0 works and prints."""
+    r = _run_bench(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-batch", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["higher_is_better"] is True and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "1 chunks of 20 s" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = _run_bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                    {"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_own_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without CUDA the product arm exits non-zero instead of timing something else."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    r = _run_bench(["--steps", "1", "--warmup", "0", "--no-cpu-baseline", "--no-e2e"])
+    assert r.returncode != 0
+    assert r.stdout.strip() == ""
