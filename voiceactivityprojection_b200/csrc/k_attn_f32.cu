@@ -286,7 +286,10 @@ template <typename TIO>
 static int launch_attn(cudaStream_t st, const TIO* q, long long q_row_stride, const TIO* k, const TIO* v,
                        long long kv_row_stride, TIO* out, int nseq, int T, int n_heads, const float* slopes,
                        int cross) {
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     cudaFuncSetAttribute(attention_f32_kernel<TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     configured = true;

@@ -413,7 +413,10 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
   p.dbg = dbg;
   p.fp16 = g_fp16;
   p.pair_major = nseq * p.head_pairs >= 2 * n_sm;
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {
       if (err) *err = "attention_tc: cannot reserve shared memory";

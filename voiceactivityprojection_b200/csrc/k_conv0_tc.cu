@@ -299,7 +299,10 @@ int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_sa
   p.n_samples = n_samples;
   p.L0 = L0;
   p.fp16 = g_fp16;
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM) != cudaSuccess) {
       if (err) *err = "conv0_tc: cannot reserve shared memory";

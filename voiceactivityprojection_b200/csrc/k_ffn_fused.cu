@@ -419,7 +419,10 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
   p.b2 = b2;
   p.dbg = dbg;
   p.fp16 = g_fp16;
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
       if (err) *err = "ffn_fused: cannot reserve shared memory";

@@ -321,7 +321,10 @@ int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string*
   p.norm1 = e.norm1; p.g1 = e.g1; p.b1 = e.b1;
   p.act = e.act;
   p.fp16 = g_fp16;
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM) != cudaSuccess) {
       if (err) *err = "gemm_2sm: cannot reserve shared memory";

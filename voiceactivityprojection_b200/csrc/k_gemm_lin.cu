@@ -551,9 +551,9 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
                    (e.resid ? F_RESID : 0) | (e.accumulate ? F_ACC : 0) | (p.f32_mode == 1 ? F_F32B : 0) |
                    (p.f32_mode == 2 ? F_F32R : 0) | (p.has_o1_bf16 ? F_O1B : 0) | (e.norm2 != NORM_NONE ? F_N2 : 0);
   typedef void (*KFn)(const LinParams);
-  struct Variant { int mask; KFn fn[2]; bool configured[2]; int nst; };
-#define VAPB_LIN_VARIANT(M) {M, {gemm_lin_kernel<false, M, 3>, gemm_lin_kernel<true, M, 3>}, {false, false}, 3}
-#define VAPB_LIN_VARIANT4(M) {M, {gemm_lin_kernel<false, M, 4>, gemm_lin_kernel<true, M, 3>}, {false, false}, 4}
+  struct Variant { int mask; KFn fn[2]; bool configured[2][64]; int nst; };  // configured: per device
+#define VAPB_LIN_VARIANT(M) {M, {gemm_lin_kernel<false, M, 3>, gemm_lin_kernel<true, M, 3>}, {}, 3}
+#define VAPB_LIN_VARIANT4(M) {M, {gemm_lin_kernel<false, M, 4>, gemm_lin_kernel<true, M, 3>}, {}, 4}
   static Variant variants[] = {
       VAPB_LIN_VARIANT(F_O1B),                                        // q/k/v, cross k/v, cross q
       VAPB_LIN_VARIANT(F_O1B | F_ACT),                                // FFN in + GELU
@@ -574,12 +574,15 @@ int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm
   const int grid = tiles < n_sm ? tiles : n_sm;
   const int wres = (a.K == 4 * LBK && grid >= p.n_tiles_n) ? 1 : 0;
   const int smem = wres ? lin_smem_bytes<true, 3>() : (v->nst == 4 ? lin_smem_bytes<false, 4>() : lin_smem_bytes<false, 3>());
-  if (!v->configured[wres]) {
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  cur_dev &= 63;
+  if (!v->configured[wres][cur_dev]) {
     if (cudaFuncSetAttribute(v->fn[wres], cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       if (err) *err = "gemm_lin: cannot reserve shared memory";
       return -1;
     }
-    v->configured[wres] = true;
+    v->configured[wres][cur_dev] = true;
   }
   launch_pdl(v->fn[wres], grid, L_THREADS, smem, st, p);
   return 1;

@@ -403,7 +403,10 @@ int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* 
   p.norm2 = e.norm2; p.g2 = e.g2; p.b2 = e.b2;
   p.out2_bf16 = reinterpret_cast<__nv_bfloat16*>(e.out2);
   p.out2_map = e.out2_map;
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     configured = true;

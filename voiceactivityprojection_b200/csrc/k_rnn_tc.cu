@@ -369,7 +369,10 @@ static int launch_rnn_cfg(cudaStream_t st, RnnParams& p, const void* x, long lon
     if (!make_tmap(&p.tma_out, out, 2, 3, dims, strides, box, 0, err)) return -1;
   }
   auto kern = rnn_tc_kernel<KIND, NG, NB>;
-  static bool configured = false;
+  static bool configured_on[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) {
       if (err) *err = "rnn_tc: cannot reserve shared memory";
