@@ -281,3 +281,30 @@ def test_bench_own_arm_fails_loudly_without_a_gpu():
     r = _run_bench(["--steps", "1", "--warmup", "0", "--no-cpu-baseline", "--no-e2e"])
     assert r.returncode != 0
     assert r.stdout.strip() == ""
+
+
+def test_vad_list_helpers_match_reference_golden():
+    """utils.get_vad_list_subset / vad_list_to_onehot / vad_onehot_to_vad_list / get_dialog_states / add_zero_channel
+    against the unmodified reference's outputs (tests/golden/vad_list.json, oracle/make_golden_vadlist.py):
+    identical JSON (values and int/float types) and identical tensors."""
+    from conftest import GOLDEN_DIR
+    from voiceactivityprojection_b200 import utils as U
+
+    g = json.load(open(os.path.join(GOLDEN_DIR, "vad_list.json")))
+    for c in g["subset"]:
+        assert json.dumps(U.get_vad_list_subset(c["vad_list"], c["start"], c["end"])) == json.dumps(c["out"]), c
+    for c in g["onehot_to_list"]:
+        got = U.vad_onehot_to_vad_list(torch.tensor(c["vad"]).float(), c["frame_hz"], c["ipu_thresh_time"])
+        assert json.dumps(got) == json.dumps(c["out"])
+    for c in g["list_to_onehot"]:
+        got = U.vad_list_to_onehot(c["vad_list"], c["duration"], **c["kw"])
+        assert got.dtype == torch.float32 and torch.equal(got.long(), torch.tensor(c["out"]))
+    d = g["dialog_states"]
+    assert U.get_dialog_states(torch.tensor(d["vad"]).float()).tolist() == d["out"]
+    w = torch.randn(2, 1, 10)
+    z = U.add_zero_channel(w)
+    assert z.shape == (2, 2, 10) and torch.equal(z[:, :1], w) and not z[:, 1].any()
+    with pytest.raises(AssertionError):
+        U.vad_list_to_onehot([[], []], 1.0)
+    with pytest.raises(AssertionError):
+        U.vad_onehot_to_vad_list(torch.zeros(5, 2))
