@@ -308,3 +308,18 @@ def test_vad_list_helpers_match_reference_golden():
         U.vad_list_to_onehot([[], []], 1.0)
     with pytest.raises(AssertionError):
         U.vad_onehot_to_vad_list(torch.zeros(5, 2))
+
+
+def test_audio_header_helpers(tmp_path):
+    """audio.get_audio_info / time_to_frames / sample_to_time (vap/audio.py:14-36) on a 24 kHz stereo int16 file."""
+    import scipy.io.wavfile
+
+    from voiceactivityprojection_b200 import audio as A
+
+    path = str(tmp_path / "x.wav")
+    scipy.io.wavfile.write(path, 24000, np.zeros((36000, 2), dtype=np.int16))
+    info = A.get_audio_info(path)
+    assert info == {"name": path, "duration": 1.5, "sample_rate": 24000, "num_frames": 36000, "bits_per_sample": 16,
+                    "num_channels": 2, "encoding": "PCM_S"}
+    assert A.time_to_frames(0.999, 0.02) == 49 and A.time_to_samples(0.5, 16000) == 8000
+    assert A.sample_to_time(8000, 16000) == 0.5

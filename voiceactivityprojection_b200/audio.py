@@ -9,7 +9,7 @@ resampled with `torchaudio.functional.resample` as the reference does (:65-68).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -35,6 +35,25 @@ def _read_wav(path: str) -> Tuple[Tensor, int]:
 
 def time_to_samples(t: float, sample_rate: int) -> int:
     return int(t * sample_rate)
+
+
+def time_to_frames(t: float, hop_time: float) -> int:
+    return int(t / hop_time)  # vap/audio.py:18-19
+
+
+def sample_to_time(n_samples: int, sample_rate: int) -> float:
+    return n_samples / sample_rate  # vap/audio.py:22-23
+
+
+def get_audio_info(audio_path: str) -> Dict[str, Any]:
+    """vap/audio.py:26-36 for PCM wav files, from the file header (no decode). Same keys; `num_channels` is the
+    channel count (the reference stores `bits_per_sample` under that key, :34)."""
+    import wave
+
+    with wave.open(audio_path, "rb") as f:
+        n, sr, width, ch = f.getnframes(), f.getframerate(), f.getsampwidth(), f.getnchannels()
+    return {"name": audio_path, "duration": sample_to_time(n, sr), "sample_rate": sr, "num_frames": n,
+            "bits_per_sample": 8 * width, "num_channels": ch, "encoding": "PCM_U" if width == 1 else "PCM_S"}
 
 
 def load_waveform(path: str, sample_rate: Optional[int] = None, start_time: Optional[float] = None,
