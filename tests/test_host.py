@@ -323,3 +323,32 @@ def test_audio_header_helpers(tmp_path):
                     "num_channels": 2, "encoding": "PCM_S"}
     assert A.time_to_frames(0.999, 0.02) == 49 and A.time_to_samples(0.5, 16000) == 8000
     assert A.sample_to_time(8000, 16000) == 0.5
+
+
+def test_extraction_cli_writes_minimal_json_and_csv(tmp_path):
+    """`python -m voiceactivityprojection_b200.extraction` (vap/extraction.py:18-56, 340-378): flags, vad-list input,
+    `<audio name>.json` / `.csv` with the minimal keys, on a model double (the real model needs the GPU)."""
+    import scipy.io.wavfile
+
+    from voiceactivityprojection_b200 import extraction as E
+
+    wav_path = str(tmp_path / "dialog.wav")
+    pcm = (np.random.default_rng(0).standard_normal((16000 * 12, 2)) * 3000).astype(np.int16)
+    scipy.io.wavfile.write(wav_path, 16000, pcm)
+    vad_path = str(tmp_path / "dialog_vad_list.json")
+    json.dump([[[0.5, 2.0], [6.0, 7.5]], [[2.5, 5.0]]], open(vad_path, "w"))
+    m = _FakeModel()
+    m.device = "cpu"
+    out = E.main(["-a", wav_path, "-v", vad_path, "--output_dir", str(tmp_path)], model=m)
+    assert out == str(tmp_path / "dialog.json")
+    d = json.load(open(out))
+    assert list(d.keys()) == ["p_now", "p_future", "model_vad0", "model_vad1", "H", "loss", "vad0", "vad1"]
+    assert len(d["p_now"]) == 600 and len(d["loss"]) == 500 and len(d["vad0"]) == 600
+    assert d["vad0"][24] == 0.0 and d["vad0"][25] == 1.0 and d["vad1"][249] == 1.0 and d["vad1"][250] == 0.0
+    out = E.main(["-a", wav_path, "--output_format", "csv", "--output_dir", str(tmp_path)], model=m)
+    lines = open(out).read().strip().splitlines()
+    assert out.endswith("dialog.csv") and lines[0] == "p_now,p_future,model_vad0,model_vad1,H,loss" and len(lines) == 601
+    df = E.json_data_to_df({k: v for k, v in d.items() if not k.startswith("vad")})
+    assert df.shape == (600, 6) and df["loss"].iloc[-1] == 0
+    args, conf = E.get_args(["-a", "x.wav", "--context_time", "10", "--step_time", "2.5"])
+    assert args.context_time == 10 and args.step_time == 2.5 and args.output_format == "json" and conf.frame_hz == 50

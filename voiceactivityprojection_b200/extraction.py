@@ -70,7 +70,7 @@ class VapExtractor:
             model.load_state_dict(torch.load(state_dict_path, map_location="cpu"))
             model = model.to("cuda").eval()
         self.model = model
-        self.device = "cuda"
+        self.device = getattr(model, "device", "cuda")  # VapGPT lives on the GPU; test doubles may say otherwise
         self.precision, self.max_batch, self.compat_skip_last_fold = precision, max_batch, compat_skip_last_fold
         self.context_time, self.step_time = context_time, step_time
         self.chunk_time = context_time + step_time
@@ -122,3 +122,79 @@ class VapExtractor:
         if duration > STEP_EXTRACTION_LIMIT:
             return self.step_extraction(waveform, vad=vad)
         return {k: v.cpu() for k, v in self._probs(waveform.to(self.device)).items()}
+
+
+# --------------------------------------------------------------------------- #
+# command line (vap/extraction.py:18-56, 340-378)                              #
+# --------------------------------------------------------------------------- #
+def get_duration(x: Tensor, sample_rate: int = 16000) -> float:
+    return x.shape[-1] / sample_rate
+
+
+def json_data_to_df(out: Dict[str, list]):
+    """vap/extraction.py:63-79: one DataFrame row per frame, short columns padded with 0."""
+    import pandas as pd
+
+    return pd.DataFrame(minimal_output_rows(out))
+
+
+def get_args(argv=None):
+    from argparse import ArgumentParser
+
+    from .model import VapConfig
+
+    parser = ArgumentParser()
+    parser.add_argument("-a", "--audio", type=str, help="Path to waveform")
+    parser.add_argument("-v", "--vad", type=str, help="Path to vad list", default=None)
+    parser.add_argument("--output_format", type=str, default="json", help="output format: ['json', 'csv']. Default='json'")
+    parser.add_argument("-sd", "--state_dict", type=str,
+                        default="example/VAP_3mmz3t0u_50Hz_ad20s_134-epoch9-val_2.56.pt", help="Path to state_dict")
+    parser, _ = VapConfig.add_argparse_args(parser, [])
+    parser.add_argument("--context_time", type=float, default=20, help="Duration of each chunk processed by model")
+    parser.add_argument("--step_time", type=float, default=5, help="Increment to process in a step")
+    parser.add_argument("--precision", default=None, choices=["fp32", "bf16", "fp16"])
+    parser.add_argument("--output_dir", type=str, default=".", help="where <audio name>.json / .csv is written")
+    args = parser.parse_args(argv)
+    return args, VapConfig.args_to_conf(args)
+
+
+def main(argv=None, model=None) -> str:
+    """`python -m voiceactivityprojection_b200.extraction -a X.wav -sd S.pt [-v X_vad_list.json]`: the reference's
+    `python vap/extraction.py` — minimal JSON (or CSV) next to the audio's base name. Returns the written path.
+    `model`: an already loaded VapGPT (tests / callers that hold one)."""
+    import os
+
+    from .audio import load_waveform
+    from .utils import read_json, vad_list_to_onehot, write_json
+
+    args, _ = get_args(argv)
+    extractor = VapExtractor(context_time=args.context_time, step_time=args.step_time,
+                             state_dict_path=args.state_dict, model=model, precision=args.precision)
+    sr = extractor.model.sample_rate
+    waveform, _ = load_waveform(args.audio, sample_rate=sr)
+    if waveform.shape[0] == 1:  # run.py:219-220: a silent second speaker under a mono file
+        waveform = torch.cat((waveform, torch.zeros_like(waveform)))
+    waveform = waveform.unsqueeze(0)
+    print("waveform: ", tuple(waveform.shape))
+    vad = None
+    if args.vad is not None:
+        vad = vad_list_to_onehot(read_json(args.vad), duration=get_duration(waveform, sr),
+                                 frame_hz=extractor.model.frame_hz).unsqueeze(0)
+        print("vad: ", tuple(vad.shape))
+    min_out = get_minimal_output_json(extractor.extract(waveform), vad)
+    print("Keys:    Frames")
+    for k, v in min_out.items():
+        print(f"{k}:     {len(v)}")
+    base = os.path.join(args.output_dir, os.path.basename(args.audio).replace(".wav", ""))
+    if args.output_format == "json":
+        path = base + ".json"
+        write_json(min_out, path)
+    else:
+        path = base + ".csv"
+        write_minimal_csv(min_out, path)
+    print("Saved -> ", path)
+    return path
+
+
+if __name__ == "__main__":
+    main()
