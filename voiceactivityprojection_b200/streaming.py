@@ -25,8 +25,8 @@ class StreamingVAP:
             raise RuntimeError("StreamingVAP needs the model on a CUDA device (no CPU fallback)")
         self.model, self.precision = model, precision
         self.device = model._device
-        self.n_samples = int(context_time * model.sample_rate)
-        self.tt_frames = int(tt_time * model.frame_hz)
+        self.n_samples = round(context_time * model.sample_rate)  # sds/run_sds.py:173
+        self.tt_frames = round(tt_time * model.frame_hz)          # :182
         self.x = torch.zeros((1, 2, self.n_samples), dtype=torch.float32, device=self.device)
 
     def add_audio_bytes(self, audio_bytes: bytes) -> int:
@@ -49,9 +49,14 @@ class StreamingVAP:
         return n
 
     @torch.no_grad()
-    def step(self) -> Dict[str, object]:
-        """One poll of the reference's loop: full-window probs and the scalar it publishes."""
+    def step(self, levels: bool = False) -> Dict[str, object]:
+        """One poll of the reference's loop: full-window probs and the scalar it publishes (:241-242).
+        levels=True adds the two integers the loop prints next to it (:236-237): 100 x the peak |sample| of each
+        speaker over the newest 4000 samples."""
         kw = {} if self.precision is None else {"precision": self.precision}
         out = self.model.probs(self.x, **kw)
-        p = out["p_now"][0, -self.tt_frames:, 0].mean().item()
-        return {"p_now_mean": p, "out": out}
+        ret = {"p_now_mean": out["p_now"][0, -self.tt_frames:, 0].mean().item(), "out": out}
+        if levels:
+            peak = (self.x[0, :, -4000:].abs().amax(-1) * 100).long().tolist()
+            ret["level_a"], ret["level_b"] = peak
+        return ret
