@@ -47,6 +47,8 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 2, 40000))
     with pytest.raises(NotImplementedError):
         m.train()
+    lg, tgt = torch.tensor([[0.0, 2.0]]), torch.tensor([[1.0, 0.0]])
+    assert torch.allclose(m.vad_loss(lg, tgt), torch.nn.functional.binary_cross_entropy_with_logits(lg, tgt))
 
 
 class _FakeModel:

@@ -246,6 +246,10 @@ class VapGPT(nn.Module):
         B = audio.shape[0]
         return x[:B], x[B:]
 
+    def vad_loss(self, vad_output: Tensor, vad: Tensor) -> Tensor:
+        """vap/model.py:177-178: mean binary cross-entropy of the VAD logits (a metric on outputs; no device kernel)."""
+        return torch.nn.functional.binary_cross_entropy_with_logits(vad_output, vad)
+
     @torch.no_grad()
     def forward(self, waveform: Tensor, attention: bool = False, precision: Optional[str] = None) -> Dict[str, Tensor]:
         """vap/model.py:249-268 -> {"logits": (B,T,256), "vad": (B,T,2)} (vad = logits).
