@@ -354,3 +354,32 @@ def test_extraction_cli_writes_minimal_json_and_csv(tmp_path):
     assert df.shape == (600, 6) and df["loss"].iloc[-1] == 0
     args, conf = E.get_args(["-a", "x.wav", "--context_time", "10", "--step_time", "2.5"])
     assert args.context_time == 10 and args.step_time == 2.5 and args.output_format == "json" and conf.frame_hz == 50
+
+
+def test_objective_helper_classes_match_reference_golden():
+    """objective.ProjectionWindow / Codebook / get_da_labels / loss_vad against the unmodified reference's outputs
+    (tests/golden/objective.npz, oracle/make_golden_objective.py): integer results bit-exact."""
+    from conftest import GOLDEN_DIR
+    from voiceactivityprojection_b200.objective import ObjectiveVAP
+
+    g = np.load(os.path.join(GOLDEN_DIR, "objective.npz"))
+    o = ObjectiveVAP()
+    va = torch.from_numpy(g["va"]).float()
+    idx, ds = o.get_da_labels(va)
+    assert torch.equal(idx, torch.from_numpy(g["labels"])) and torch.equal(ds, torch.from_numpy(g["dialog_states"]))
+    assert torch.equal(o.get_labels(va), idx)
+    wins = o.projection_window_extractor(va)
+    assert wins.dtype == torch.float32 and torch.equal(wins, torch.from_numpy(g["windows"]).float())
+    assert o.projection_window_extractor.projection(va).shape == (3, 160, 2, 100)
+    assert repr(o.projection_window_extractor) == str(g["repr_pw"])
+    cb = o.codebook
+    assert (cb.n_bins, cb.total_bins, cb.n_classes) == (4, 8, 256)
+    assert torch.equal(cb.emb.weight, torch.from_numpy(g["code_vectors"]))
+    assert torch.equal(cb.encode(torch.from_numpy(g["soft"])), torch.from_numpy(g["soft_idx"]))
+    assert torch.equal(cb.decode(torch.from_numpy(g["some_idx"])), torch.from_numpy(g["some_windows"]))
+    assert torch.equal(cb(cb.decode(torch.arange(256))), torch.arange(256))
+    assert torch.equal(cb.single_idx_to_onehot(37), cb.emb.weight[37])
+    lv = o.loss_vad(torch.from_numpy(g["vad_logits"]), torch.from_numpy(g["vad_target"]))
+    assert abs(float(lv) - float(g["loss_vad"])) <= 1e-6
+    with pytest.raises(AssertionError):
+        cb.encode(torch.zeros(3, 2, 5))
