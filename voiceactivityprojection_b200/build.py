@@ -1,6 +1,7 @@
 """Builds libvapb.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
     python -m voiceactivityprojection_b200.build [--force]
+    python -m voiceactivityprojection_b200.build --variant b -D SOME_KNOB=1     # libvapb_b.so for VAPB_LIB A/B runs
 
 nvcc cross-compiles without a GPU. Objects are cached under csrc/build/ keyed on
 the source mtime; the .so is git-ignored but travels to the GPU box with gpurun.
@@ -31,11 +32,19 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant / defines: a second build for same-box A/B runs (`VAPB_LIB=.../libvapb_<variant>.so`): every source is
+    compiled with the extra -D flags into csrc/build_<variant>/ and linked as libvapb_<variant>.so."""
+    if variant:
+        return _build(force, verbose, os.path.join(CSRC, "build_" + variant),
+                      os.path.join(HERE, f"libvapb_{variant}.so"), [f"-D{d}" for d in defines])
+    return _build(force, verbose, os.path.join(CSRC, "build"), OUT, [])
+
+
+def _build(force: bool, verbose: bool, bdir: str, out: str, extra) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))
                   + glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
-    bdir = os.path.join(CSRC, "build")
     os.makedirs(bdir, exist_ok=True)
     objs, jobs = [], []
     for s in srcs:
@@ -46,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        r = subprocess.run([NVCC, *FLAGS, "-c", s, "-o", o], capture_output=True, text=True)
+        r = subprocess.run([NVCC, *FLAGS, *extra, "-c", s, "-o", o], capture_output=True, text=True)
         return s, r
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
@@ -59,13 +68,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed on {s}")
             if verbose:
                 sys.stderr.write(r.stderr)
-    if jobs or force or _stale(OUT, objs):
-        r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-lcudart"], capture_output=True, text=True)
+    if jobs or force or _stale(out, objs):
+        r = subprocess.run([NVCC, "-shared", "-o", out, *objs, "-lcudart"], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("-v", action="store_true")
+    ap.add_argument("--variant", default="", help="build libvapb_<variant>.so next to the main library")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="extra preprocessor define (with --variant)")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.v, variant=a.variant, defines=a.defines))
