@@ -168,6 +168,18 @@ int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64
                         int nseq, int rows_per_seq, int K, const float* bias, int norm1, const float* g1,
                         const float* b1, int act, void* out_bf16, char* err, int err_len);
 
+/* Unit-test hook for the fused conv0 -> conv1 kernel (csrc/k_conv01.cu; vap/encoder_components.py:83-86,99-100).
+ * wav: device fp32 (batch, 2, n_samples); every channel of every item is one sequence (channel-major order
+ * c*batch + item). conv0_w (256,1,10), conv0_b, norm0_g, norm0_b (256): HOST fp32 parameters of conv0 and its
+ * ChannelNorm (folded on the host). w1: device 16-bit [256][8*256] conv1 weight, K index = tap*256 + cin;
+ * bias1 / g1 / b1: device fp32 [256]. out: device 16-bit, row t of sequence s at
+ * out + s*out_seq_stride + (out_pad_rows + t)*256 (elements); whole 128-row tiles are written (zeros past the
+ * L1 = conv1 output length), so a sequence needs out_pad_rows + roundup(L1,128) rows. fp16: 0 = bf16 words. */
+int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
+                      const float* conv0_b, const float* norm0_g, const float* norm0_b, const void* w1,
+                      const float* bias1, const float* g1, const float* b1, void* out, int64_t out_seq_stride,
+                      int out_pad_rows, int fp16, char* err, int err_len);
+
 /* Unit-test hook for the linear-layer GEMM (csrc/k_gemm_lin.cu): same operands as
  * vapb_debug_gemm_tc; outputs are dense (nseq*rows_per_seq, N). f32_mode 1: out1_f32
  * and resid_blocked use the row-blocked fp32 layout [row/128][col/4][row%128][4]

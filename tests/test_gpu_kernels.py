@@ -374,3 +374,57 @@ def test_gemm_2sm_conv_channelnorm_relu(nseq, L, k, s, pad):
     ref = F.relu(_norm(y, 1, g1, b1))
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max().item() <= 4e-2
+
+
+def _conv01_case(B, S, fp16, seed):
+    """Fused conv0 -> conv1 kernel (k_conv01.cu) against torch fp32 on the same 16-bit-rounded hand-off."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dt16 = torch.float16 if fp16 else torch.bfloat16
+    wav = torch.randn((B, 2, S), device="cuda", generator=g) * 0.05
+    w0 = torch.randn((256, 1, 10), device="cuda", generator=g) * 0.3
+    b0 = torch.randn(256, device="cuda", generator=g) * 0.1
+    g0 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    be0 = 0.1 * torch.randn(256, device="cuda", generator=g)
+    w1 = torch.randn((256, 256, 8), device="cuda", generator=g) * 0.03
+    W1p = w1.permute(0, 2, 1).reshape(256, 8 * 256).contiguous().to(dt16)  # [N][tap*256 + cin]
+    b1 = torch.randn(256, device="cuda", generator=g) * 0.1
+    g1 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    be1 = 0.1 * torch.randn(256, device="cuda", generator=g)
+    L0 = (S + 6 - 10) // 5 + 1
+    L1 = (L0 + 4 - 8) // 4 + 1
+    pad, rows = 1, 1 + (L1 + 127) // 128 * 128 + 3
+    out = torch.full((2 * B, rows, 256), float("nan"), device="cuda", dtype=dt16)
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    host = [t.detach().cpu().contiguous() for t in (w0, b0, g0, be0)]
+    rc = lib.vapb_debug_conv01(st, wav.data_ptr(), B, S, host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr(),
+                               host[3].data_ptr(), W1p.data_ptr(), b1.data_ptr(), g1.data_ptr(), be1.data_ptr(),
+                               out.data_ptr(), rows * 256, pad, int(fp16), err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    x = wav.transpose(0, 1).reshape(2 * B, 1, S)  # sequences in channel-major order c * B + item
+    y0 = F.conv1d(x, w0, b0, stride=5, padding=3).transpose(1, 2)  # (2B, L0, 256)
+    y0 = F.relu(_norm(y0, 1, g0, be0)).to(dt16).float()
+    wr = W1p.float().reshape(256, 8, 256).permute(0, 2, 1)
+    y1 = F.conv1d(y0.transpose(1, 2), wr, b1, stride=4, padding=2).transpose(1, 2)  # (2B, L1, 256)
+    ref = F.relu(_norm(y1, 1, g1, be1))
+    assert y1.shape[1] == L1
+    return out, ref, pad, L1
+
+
+@pytest.mark.parametrize("B,S,fp16", [(1, 2000, 0), (1, 40000, 0), (2, 37392, 1), (3, 320000, 1), (2, 81920 * 5 + 7, 0)])
+def test_conv01_fused_matches_torch(B, S, fp16):
+    out, ref, pad, L1 = _conv01_case(B, S, fp16, seed=B * 1000 + S % 997)
+    got = out[:, pad:pad + L1].float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    tol = 8e-3 if fp16 else 5e-2
+    assert err.max().item() <= tol, f"max-abs {err.max().item()} at {divmod(int(err.argmax()), 256)}"
+    assert err.mean().item() <= tol / 10
+    tail = out[:, pad + L1:pad + (L1 + 127) // 128 * 128].float()
+    assert (tail == 0).all()                      # rows past the sequence end are the next layer's zero padding
+    assert torch.isnan(out[:, :pad].float()).all()  # rows before the sequence are not touched
+    assert torch.isnan(out[:, pad + (L1 + 127) // 128 * 128:].float()).all()

@@ -11,6 +11,8 @@
 
 using namespace vapb;
 
+namespace vapb { extern thread_local int g_fp16; }  // 16-bit format of this thread's launches (tc_common.cuh)
+
 struct VapbHandle {
   Model m;
 };
@@ -136,6 +138,7 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_CONV_2SM")) h->m.conv_2sm = atoi(v);
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
+  if (const char* v = getenv("VAPB_CONV01")) h->m.conv01 = atoi(v);
   if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
   if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
   if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
@@ -752,6 +755,48 @@ int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
   }
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
+int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
+                      const float* conv0_b, const float* norm0_g, const float* norm0_b, const void* w1,
+                      const float* bias1, const float* g1, const float* b1, void* out, int64_t out_seq_stride,
+                      int out_pad_rows, int fp16, char* err, int err_len) {
+  Geometry g;
+  std::string msg;
+  int rc = -1;
+  float* dev_tab = nullptr;
+  if (!wav || !conv0_w || !conv0_b || !norm0_g || !norm0_b || !w1 || !bias1 || !g1 || !b1 || !out || batch < 1 ||
+      make_geometry(batch, n_samples, &g) != 0) {
+    msg = "conv01: invalid argument";
+  } else {
+    std::vector<float> tab(12 * kDim);
+    Conv0Stats cs;
+    conv0_v2_fold(conv0_w, conv0_b, norm0_g, tab.data(), tab.data() + 10 * kDim, &cs);
+    memcpy(tab.data() + 11 * kDim, norm0_b, kDim * sizeof(float));
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaMalloc(&dev_tab, tab.size() * 4) != cudaSuccess ||
+        cudaMemcpy(dev_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      msg = "conv01: cannot stage the conv0 table";
+    } else {
+      const int prev = g_fp16;
+      g_fp16 = fp16 ? 1 : 0;
+      rc = launch_conv01((cudaStream_t)stream, wav, batch, n_samples, 0, 2 * batch, g.L[0], g.L[1], tab.data(), dev_tab,
+                         cs, w1, bias1, g1, b1, out, out_seq_stride, out_pad_rows, n_sm, &msg);
+      g_fp16 = prev;
+      if (rc >= 0) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+      }
+    }
+  }
+  if (dev_tab) cudaFree(dev_tab);
   if (rc < 0) {
     if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
     return VAPB_E_CUDA;

@@ -38,6 +38,8 @@ struct State16 {
   const bf16 *comb_a, *comb_b, *head_w;
   const float *c0_u, *c0_d;  // folded conv0 + ChannelNorm parameters (k_conv0_v2.cu)
   Conv0Stats c0_stats;
+  const float* c0_tab;             // [12][256] = u | d | beta on the device, and the same on the host: the fused
+  std::vector<float> c0_tab_host;  // conv0 -> conv1 kernel takes the table as kernel parameters (k_conv01.cu)
 };
 
 struct Plan16 {
@@ -49,7 +51,9 @@ struct Plan16 {
 
 Plan16 make_plan(const Model& m, const Geometry& g) {
   Plan16 p{};
-  const long long per_seq0 = (g.L[0] + 16) * kDim * 2;
+  const bool fused01 = m.conv01 != 0;  // conv0 lives inside conv1's producer: no act[0], act[1] holds whole 128-row tiles
+  const long long l1_tiles = (g.L[1] + 127) / 128 * 128;
+  const long long per_seq0 = (fused01 ? l1_tiles + 16 : g.L[0] + 16) * kDim * 2;
   long long mb = (m.conv_mb_bytes > 0 ? m.conv_mb_bytes : (4LL << 30)) / per_seq0;
   if (mb < 1) mb = 1;
   if (mb > g.nseq) mb = g.nseq;
@@ -60,10 +64,11 @@ Plan16 make_plan(const Model& m, const Geometry& g) {
     p.lo[i] = nx.p;
     const long long need = (long long)nx.s * (g.L[i + 1] - 1) + nx.k;
     long long lp = need > nx.p + g.L[i] ? need : nx.p + g.L[i];
+    if (fused01 && i == 1 && lp < nx.p + l1_tiles) lp = nx.p + l1_tiles;
     lp = (lp + nx.s - 1) / nx.s * nx.s;
     p.lpad[i] = lp;
     p.act[i] = off;
-    off = align_up(off + (size_t)mb * lp * kDim * 2);
+    if (!(fused01 && i == 0)) off = align_up(off + (size_t)mb * lp * kDim * 2);
   }
   p.act4 = off;  off = align_up(off + (size_t)g.nseq * g.L[4] * kDim * 2);
   p.rnn_lpad = 4 + g.L[4] + (g.L[4] & 1);  // even, so the stride-2 tensor map strides nest
@@ -229,6 +234,11 @@ static int prepare_fmt(Model& m, State16* s, int fp16) {
                   T(GE + "batchNorm0.weight").data.data(), u.data(), d.data(), &s->c0_stats);
     put_f32(&s->c0_u, u);
     put_f32(&s->c0_d, d);
+    s->c0_tab_host = u;
+    s->c0_tab_host.insert(s->c0_tab_host.end(), d.begin(), d.end());
+    const auto& be = T(GE + "batchNorm0.bias").data;
+    s->c0_tab_host.insert(s->c0_tab_host.end(), be.begin(), be.end());
+    put_f32(&s->c0_tab, s->c0_tab_host);
   }
   if (cudaMalloc(&s->arena, host.size()) != cudaSuccess ||
       cudaMemcpy(s->arena, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -265,7 +275,7 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
 
   {
     ProfScope ps(m, st, CAT_OTHER);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = m.conv01 ? 1 : 0; i < 4; ++i) {
       m.launches += launch_zero_rows(st, H(p.act[i]), 2, p.mb, p.lpad[i] * kDim, 0, p.lo[i]);
       m.launches += launch_zero_rows(st, H(p.act[i]), 2, p.mb, p.lpad[i] * kDim, p.lo[i] + g.L[i],
                                      p.lpad[i] - p.lo[i] - g.L[i]);
@@ -281,7 +291,16 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
   m.trace(st, "g" + std::to_string(m.trace_group) + " conv_begin");
   for (int s0 = 0; s0 < nseq; s0 += p.mb) {
     const int n = (nseq - s0 < p.mb) ? nseq - s0 : p.mb;
-    {
+    if (m.conv01) {
+      // conv0 + conv1 in one kernel (k_conv01.cu): the first layer's 512 B per frame never reach HBM
+      ProfScope ps(m, st, CAT_CONV_GEMM);
+      std::string err;
+      const int k = launch_conv01(st, wav, g.batch, g.S, s0, n, g.L[0], g.L[1], s.c0_tab_host.data(), s.c0_tab, s.c0_stats,
+                                  s.conv_w[1], w.conv_b[1], w.conv_g[1], w.conv_be[1], H(p.act[1]), p.lpad[1] * kDim,
+                                  (int)p.lo[1], m.n_sm, &err);
+      if (k < 0) { m.err = err; return -3; }
+      m.launches += k;
+    } else {
       ProfScope ps(m, st, CAT_CONV0);
       if (m.conv0_tc) {
         std::string err;
@@ -295,7 +314,7 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
                                       H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0]);
       }
     }
-    for (int i = 1; i <= 4; ++i) {
+    for (int i = m.conv01 ? 2 : 1; i <= 4; ++i) {
       const Conv& c = kConv[i];
       Epilogue e{};
       e.bias = w.conv_b[i];
