@@ -178,7 +178,8 @@ int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64
 int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
                       const float* conv0_b, const float* norm0_g, const float* norm0_b, const void* w1,
                       const float* bias1, const float* g1, const float* b1, void* out, int64_t out_seq_stride,
-                      int out_pad_rows, int fp16, char* err, int err_len);
+                      int out_pad_rows, int fp16, char* err, int err_len,
+                      long long* dbg_clocks /* device [4][4][16] SM-clock samples of CTA 0, or NULL */);
 
 /* Unit-test hook for the linear-layer GEMM (csrc/k_gemm_lin.cu): same operands as
  * vapb_debug_gemm_tc; outputs are dense (nseq*rows_per_seq, N). f32_mode 1: out1_f32

@@ -376,7 +376,7 @@ def test_gemm_2sm_conv_channelnorm_relu(nseq, L, k, s, pad):
     assert (out.float() - ref).abs().max().item() <= 4e-2
 
 
-def _conv01_case(B, S, fp16, seed):
+def _conv01_case(B, S, fp16, seed, dbg=None):
     """Fused conv0 -> conv1 kernel (k_conv01.cu) against torch fp32 on the same 16-bit-rounded hand-off."""
     from voiceactivityprojection_b200 import _lib
 
@@ -402,7 +402,8 @@ def _conv01_case(B, S, fp16, seed):
     host = [t.detach().cpu().contiguous() for t in (w0, b0, g0, be0)]
     rc = lib.vapb_debug_conv01(st, wav.data_ptr(), B, S, host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr(),
                                host[3].data_ptr(), W1p.data_ptr(), b1.data_ptr(), g1.data_ptr(), be1.data_ptr(),
-                               out.data_ptr(), rows * 256, pad, int(fp16), err, 512)
+                               out.data_ptr(), rows * 256, pad, int(fp16), err, 512,
+                               None if dbg is None else dbg.data_ptr())
     assert rc == 0, err.value.decode()
     torch.cuda.synchronize()
     x = wav.transpose(0, 1).reshape(2 * B, 1, S)  # sequences in channel-major order c * B + item

@@ -32,3 +32,24 @@ for B, S, fp16 in [(1, 2000, 0), (1, 40000, 1), (3, 320000, 1)]:
         print("  max err per output channel block:", [round(v, 4) for v in per_cb.tolist()])
         per_seq = err.amax(dim=(1, 2))
         print("  max err per sequence:", [round(v, 4) for v in per_seq.tolist()])
+
+# timeline of the first tiles (SM clocks of cluster 0 / CTA 0): producer warp 12 and the MMA thread
+if os.environ.get("CONV01_TIMELINE", "1") != "0":
+    dbg = torch.zeros(4 * 4 * 16 + 16, dtype=torch.int64, device="cuda")
+    _conv01_case(64, 320000, 1, seed=5, dbg=dbg)
+    tm = dbg[256:264].cpu().tolist()
+    d = dbg[:256].reshape(4, 4, 16).cpu()
+    t00 = int(d[d > 0].min())
+    pn = ["(unused)", "next tap's X (+ window barrier at tile end)", "wait d0_full", "load_pack (TMEM -> regs)",
+          "wait stage empty", "STS", "fence.proxy.async", "syncwarp + arrive"]
+    tot = sum(tm)
+    print("producer warp 12 of CTA 0, cycles per phase over the whole kernel:")
+    for n, v in zip(pn, tm):
+        print(f"  {n:40s} {v:12d}  {100.0 * v / max(tot, 1):5.1f} %")
+    names = ["X.begin", "xa.arrive", "d0_full", "ld3", "st0", "st1", "d0_free", "st2", "st3", "Z.enter", "Z.xa_full",
+             "Z.issued", "C0", "C1", "C2", "C3"]
+    print("event clocks relative to the first stamp (tile iteration, tap):")
+    for it in range(4):
+        for j in range(4):
+            row = d[it, j]
+            print(f"  it{it} j{j}: " + "  ".join(f"{n}={int(v) - t00 if v > 0 else -1}" for n, v in zip(names, row.tolist())))

@@ -765,7 +765,7 @@ int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64
 int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
                       const float* conv0_b, const float* norm0_g, const float* norm0_b, const void* w1,
                       const float* bias1, const float* g1, const float* b1, void* out, int64_t out_seq_stride,
-                      int out_pad_rows, int fp16, char* err, int err_len) {
+                      int out_pad_rows, int fp16, char* err, int err_len, long long* dbg_clocks) {
   Geometry g;
   std::string msg;
   int rc = -1;
@@ -788,7 +788,7 @@ int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_sampl
       const int prev = g_fp16;
       g_fp16 = fp16 ? 1 : 0;
       rc = launch_conv01((cudaStream_t)stream, wav, batch, n_samples, 0, 2 * batch, g.L[0], g.L[1], tab.data(), dev_tab,
-                         cs, w1, bias1, g1, b1, out, out_seq_stride, out_pad_rows, n_sm, &msg);
+                         cs, w1, bias1, g1, b1, out, out_seq_stride, out_pad_rows, n_sm, &msg, dbg_clocks);
       g_fp16 = prev;
       if (rc >= 0) {
         cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);

@@ -109,7 +109,7 @@ int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string*
 int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq, long long L0,
                   long long L1, const float* host_tab, const float* dev_tab, const Conv0Stats& cs, const void* w1,
                   const float* bias1, const float* g1, const float* b1, void* out, long long out_seq_stride,
-                  int out_pad_rows, int n_sm, std::string* err);
+                  int out_pad_rows, int n_sm, std::string* err, long long* dbg = nullptr);
 
 int launch_zero_rows(cudaStream_t st, void* buf, int elem_bytes, int nseq, long long seq_stride_elems,
                      long long row0, long long nrows);  // zero rows [row0,row0+nrows) of every sequence

@@ -13,16 +13,23 @@
 // frame of row t0+128) and the MMA thread issues both k-blocks from it: every conv0 output is computed 1.06 times
 // instead of twice.
 //
-// conv0 on CUDA cores, one lane per output row: the lane scales its frame's 10 samples by the frame's
-// 1/sqrt(var+eps) (closed form x'Gx + 2h.x + s, as k_conv0_tc.cu) and runs 12 packed FMAs per channel pair
-// (10 taps, the folded bias d_c * rstd, the norm bias beta_c) whose weight operands come straight from the kernel
-// parameter bank as uniform registers (FFMA2 R, R.F32, UR.F32x2, R): no shared-memory operand traffic at all;
-// cvt.rn.relu packs two channels. Zero padding frames (f < 0, f >= L0) come out as exact zeros (rstd = 0, flag = 0).
+// conv0 itself is a second, tiny tensor-core GEMM per tap j: D0[256 rows][256 ch] = X'_j[256][32] U[256][32]^T, fp16
+// operands whatever the mode (the products are internal), K = 32 = (x' hi | x' lo): a producer lane scales its frame's
+// 10 samples by the frame's 1/sqrt(var+eps) (closed form x'Gx + 2h.x + s, as k_conv0_tc.cu), splits them into fp16
+// hi + lo parts and writes one 64-byte operand row (10 taps, rstd for the folded bias d_c, a validity flag for the norm
+// bias beta_c; lo parts in the second half); U holds fp16(u | d | beta) twice. D0 lives in the 256 TMEM columns of the
+// conv1 accumulator that is idle at that moment (tap 0: the tile's own accumulator before its main loop starts, taps
+// 1-3: the other one after its epilogue has drained it), so conv1 keeps both accumulators. The producers then only move
+// D0: tcgen05.ld -> cvt.rn.relu pack -> swizzled A block (the fourth channel block is read early into registers so the
+// TMEM columns are released before a ring stage is free). Zero padding frames (f < 0, f >= L0) have x' = 0, flag = 0:
+// exact zeros. A first version computed conv0 on CUDA cores with weights streamed from the parameter bank (LDCU +
+// FFMA2): correct, but 3-5x too slow (the 12 KB table thrashes the constant cache; profiles/r2_conv01_history.md).
 //
 // Roles per CTA (512 threads): warp 0 = TMA producer of W1 (both k-blocks of the stage, own 128 output channels),
-// warp 1 = MMA issuer (leader CTA), warp 2 = TMEM allocation, warp 3 = the extra row t0+128 (lane = 8 channels),
-// warps 4-11 = epilogue (bias -> ChannelNorm -> ReLU -> 16-bit -> swizzled staging -> TMA store that undoes the
-// row permutation), warps 12-15 = conv0 producers. The stage's full barrier (leader CTA) counts the W bytes plus one
+// warp 1 = MMA issuer (leader CTA: conv1 stages and the conv0 GEMMs, interleaved C C Z C C per tap so neither waits on
+// the other), warp 2 = TMEM allocation, warp 3 = the extra row t0+128 (CUDA cores, lane = 8 channels), warps 4-11 =
+// epilogue (bias -> ChannelNorm -> ReLU -> 16-bit -> swizzled staging -> TMA store that undoes the row permutation),
+// warps 12-15 = conv0 producers (lane = MMA row). The stage's full barrier (leader CTA) counts the W bytes plus one
 // arrival per producing warp of both CTAs.
 #include <string>
 
@@ -39,7 +46,7 @@ constexpr int F_STAGES = 3;
 constexpr int F_A_BYTES = 17 * 1024;              // 17 row groups x (8 rows x 128 B)
 constexpr int F_WK_BYTES = 128 * 64 * 2;          // one k-block of this CTA's half of W1
 constexpr int F_STAGE_BYTES = F_A_BYTES + 2 * F_WK_BYTES;  // 49 KB
-constexpr int F_OFF_STG = F_STAGES * F_STAGE_BYTES;        // [half][2] x 8 KB (128 rows x 64 B, SW64)
+constexpr int F_OFF_STG = F_STAGES * F_STAGE_BYTES;        // [epilogue warp][2] x 2 KB (32 rows x 64 B, SW64)
 constexpr int F_OFF_BAR = F_OFF_STG + 4 * 8192;
 constexpr int F_OFF_VEC = F_OFF_BAR + 256;
 constexpr int F_WIN = 2585;                        // samples of one tile's window (rows t0 .. t0+128, taps 0..3)
@@ -57,23 +64,24 @@ struct F01Vecs {
   float s, pad_[3];
 };
 constexpr int F_OFF_XSB = F_OFF_VEC + (int)sizeof(F01Vecs);
-constexpr int F_OFF_XP = F_OFF_XSB + 2 * F_XS * 4;       // float [2][128][12]: scaled frames of the current tap
-constexpr int F_SMEM = F_OFF_XP + 2 * 128 * 12 * 4 + 1024;
+constexpr int F_OFF_XA = F_OFF_XSB + 2 * F_XS * 4;       // conv0 A operand: fp16 [4 k-chunks][128 rows][8] (no swizzle)
+constexpr int F_OFF_U = F_OFF_XA + 4 * 128 * 16;         // conv0 B operand: fp16 [4 k-chunks][128 own channels][8]
+constexpr int F_SMEM = F_OFF_U + 4 * 128 * 16 + 1024;
 static_assert(F_STAGE_BYTES % 1024 == 0 && F_OFF_STG % 1024 == 0, "SW128 operands need 1024-byte aligned bases");
 static_assert(F_SMEM <= 232448, "shared memory budget");
 
 struct alignas(64) F01Params {
   CUtensorMap tma_w;   // (2048, 256) 16-bit, box (64, 128), SW128
-  CUtensorMap tma_o;   // store_mode 0: (256, 8, 16, tiles, nseq) box (32, 8, 16, 1, 1); 1: (256, 16, rows/16, nseq) box (32, 1, 8, 1); SW64
-  float4 wq[12][64];   // [k][c/4]: k < 10 folded taps u_k, k = 10 folded bias d, k = 11 ChannelNorm bias beta
+  CUtensorMap tma_o;   // store_mode 0: (256, 8, 16, tiles, nseq) box (32, 8, 4, 1, 1); 1: (256, 16, rows/16, nseq) box (32, 1, 8, 1); SW64
   Conv0Stats cs;
   const float* wav;
-  const float* wg;     // the same 12 x 256 table in global memory (extra-row warp)
+  const float* wg;     // folded conv0 table [12][256] in global memory: k < 10 taps u_k, k = 10 bias d, k = 11 norm bias beta
   const float *bias, *g1, *b1;
   long long n_samples;
   int batch, seq0, nseq, pair_tiles_per_seq;
   int L0, L1;
   int store_mode;
+  long long* dbg;  // diagnostics (tools/conv01_probe.py): SM-clock stamps of cluster 0 / CTA 0, [tile iteration < 4][tap][16 events], or null
 };
 
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_leader, int c0, int c1) {
@@ -99,6 +107,26 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// Arrival with the default (.release.cta) semantics on a barrier of this or the peer CTA, as CUTLASS's ClusterBarrier::
+// arrive: the data it publishes was written by this warp to its OWN shared memory and made visible to the async proxy
+// with fence.proxy.async; the .release.cluster form above costs ~1000 cycles per arrival (measured: 38 % of the
+// producers' time) and sits on their critical path four times per tap.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_cluster(uint32_t bar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquires writes of the peer CTA too
   asm volatile(
@@ -157,61 +185,7 @@ __device__ __forceinline__ float frame_rstd(const V& cs, const float (&xv)[10]) 
   return rsqrtf(fmaxf(ss, 0.f) * (1.0f / (kDim - 1)) + kEps);
 }
 
-// 16 channels (quarter V of channel block cb; wq0 = 16 cb + 4 V indexes the float4 weight table) of FOUR conv0 output
-// rows (MMA rows lane + 32 m) -> the SW128 A block. One uniform weight load feeds four rows: per channel pair and tap
-// one FFMA2 per row and a quarter of an LDCU. xp[m] = the row's 10 samples * rstd, rstd, valid flag.
-template <int FP16, int V>
-__device__ __forceinline__ void produce_q(const F01Params& p, const float (&xp)[4][12], int cb, int lane, uint8_t* ablk) {
-  constexpr int v = V;
-  const int wq0 = cb * 16 + V * 4;  // cb is a loop counter and V a constant: the weight loads stay on the uniform datapath
-  const uint32_t sw = (uint32_t)(lane & 7);
-  uint8_t* arow = ablk + (lane >> 3) * 1024 + (lane & 7) * 128;  // row lane + 32 m is 4 m row groups further
-  const bool dup = lane >= 1 && lane < 8;                         // rows 1..7 of group 0 are rows 0..6 of group 16
-  uint8_t* drow = ablk + 16 * 1024 + ((lane - 1) & 7) * 128;
-  const uint32_t dsw = (uint32_t)((lane - 1) & 7);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {  // 16-byte chunk = 8 channels
-    uint32_t pk[4][4];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int c4 = wq0 + h * 2 + q;
-      float2 a[4], b[4];
-      {
-        const float4 w = p.wq[11][c4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const float2 x = make_float2(xp[m][11], xp[m][11]);
-          a[m] = __fmul2_rn(x, make_float2(w.x, w.y));
-          b[m] = __fmul2_rn(x, make_float2(w.z, w.w));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        const float4 w = p.wq[k][c4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const float2 x = make_float2(xp[m][k], xp[m][k]);
-          a[m] = __ffma2_rn(x, make_float2(w.x, w.y), a[m]);
-          b[m] = __ffma2_rn(x, make_float2(w.z, w.w), b[m]);
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        pk[m][2 * q] = pack_relu<FP16>(a[m].x, a[m].y);
-        pk[m][2 * q + 1] = pack_relu<FP16>(b[m].x, b[m].y);
-      }
-    }
-    const uint32_t chunk = (uint32_t)(2 * v + h);
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-      *reinterpret_cast<uint4*>(arow + m * 4096 + ((chunk ^ sw) << 4)) = make_uint4(pk[m][0], pk[m][1], pk[m][2], pk[m][3]);
-    if (dup) *reinterpret_cast<uint4*>(drow + ((chunk ^ dsw) << 4)) = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
-  }
-}
-
-// Epilogue of one CTA (warps 4-11) as its own function: the kernel body then holds only the producers' code, which
-// lets ptxas keep a rotating set of uniform registers for their parameter-bank weight loads (inlined, the epilogue's
-// register pressure collapsed that schedule to one load in flight).
+// Epilogue of one CTA (warps 4-11) as its own function (its register allocation stays separate from the producers').
 struct F01EpiArgs {
   uint32_t smem_base, tmem_base, rank;
   uint8_t* smem_gen;
@@ -232,20 +206,20 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
     *t0 = (pt % p.pair_tiles_per_seq) * 256 + (int)rank * 128;
   };
   {
-  // ===== epilogue (both CTAs, own 128 rows): thread = (accumulator row, column half)
+  // ===== epilogue (both CTAs, own 128 rows): thread = (accumulator row, column half). Every warp stages and stores its
+  // own 32 rows (2 KB per 32-channel chunk, two buffers): no block-level barrier on the path that releases the
+  // accumulator - the next tile's conv0 GEMMs for taps 1-3 are waiting for it.
   const int quad = warp & 3, half = (warp - 4) >> 2;
   const int row_in_tile = quad * 32 + lane;                     // MMA row r = 8g + i
   const int dt = 16 * (lane & 7) + quad * 4 + (lane >> 3);      // t - t0 of that row
-  const bool leader = (threadIdx.x - 128 - half * 128) == 0;
-  const bool lead_warp = ((warp - 4) & 3) == 0;
   const int cbase = half * 128;
-  const uint32_t stg_addr = smem_base + F_OFF_STG + half * 16384;
-  uint8_t* stg_gen = smem_gen + F_OFF_STG + half * 16384;
-  const uint32_t sw64 = (uint32_t)((row_in_tile >> 1) & 3);
+  const uint32_t stg_addr = smem_base + F_OFF_STG + (uint32_t)(warp - 4) * 4096u;
+  uint8_t* stg_gen = smem_gen + F_OFF_STG + (warp - 4) * 4096;
+  const uint32_t sw64 = (uint32_t)((lane >> 1) & 3);
   uint32_t stg_cnt = 0;
-  auto bar_half = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); };
   auto bar_epi = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
   const uint32_t tempty_leader0 = mapa(tempty_bar(0), 0), tempty_leader1 = mapa(tempty_bar(1), 0);
+  const bool storer = p.store_mode == 0 ? lane == 0 : lane < 4;  // lanes that issue this warp's TMA stores
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters) {
@@ -265,10 +239,12 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
         tmem_ld_wait();
         if (c < 3) tmem_ld32(taddr + (c + 1) * 32, rr[(c + 1) & 1]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = __uint_as_float(rr[c & 1][i]) + ev.bias[cbase + c * 32 + i];
-          s += v;
-          ss = fmaf(v, v, ss);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bi = *reinterpret_cast<const float4*>(&ev.bias[cbase + c * 32 + i]);
+          const float v0 = __uint_as_float(rr[c & 1][i]) + bi.x, v1 = __uint_as_float(rr[c & 1][i + 1]) + bi.y;
+          const float v2 = __uint_as_float(rr[c & 1][i + 2]) + bi.z, v3 = __uint_as_float(rr[c & 1][i + 3]) + bi.w;
+          s += (v0 + v1) + (v2 + v3);
+          ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
         }
       }
       ev.part[half][row_in_tile][0] = s;
@@ -287,62 +263,54 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         tmem_ld_wait();
-        if (c < 3) tmem_ld32(taddr + (c + 1) * 32, rr[(c + 1) & 1]);
-        float v[32];
+        if (c < 3) {
+          tmem_ld32(taddr + (c + 1) * 32, rr[(c + 1) & 1]);
+        } else {
+          // the accumulator has been read for the last time: release it before the last chunk's arithmetic and store
+          tc_fence_before();
+          mbar_arrive_remote(acc == 0 ? tempty_leader0 : tempty_leader1);
+        }
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 bi = *reinterpret_cast<const float4*>(&ev.bias[cbase + c * 32 + i]);
           const float4 g = *reinterpret_cast<const float4*>(&ev.g1[cbase + c * 32 + i]);
           const float4 b = *reinterpret_cast<const float4*>(&ev.b1[cbase + c * 32 + i]);
           const float bb[4] = {bi.x, bi.y, bi.z, bi.w}, gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {b.x, b.y, b.z, b.w};
+          float v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float x = fmaf((__uint_as_float(rr[c & 1][i + j]) + bb[j] - mean1) * rstd1, gg[j], be[j]);
-            v[i + j] = row_ok ? fmaxf(x, 0.f) : 0.f;  // rows past the sequence end are the next layer's zero padding
+            v[j] = row_ok ? fmaxf(x, 0.f) : 0.f;  // rows past the sequence end are the next layer's zero padding
           }
+          pk[i >> 1] = pack16(v[0], v[1], FP16);
+          pk[(i >> 1) + 1] = pack16(v[2], v[3], FP16);
         }
-        if (p.store_mode == 0) {
-          if (leader) bulk_wait_read<1>();
-        } else if (lead_warp && lane < 16) {
-          bulk_wait_read<1>();
-        }
-        bar_half();
-        const uint32_t boff = (stg_cnt & 1u) * 8192u;
-        uint8_t* rowp = stg_gen + boff + (uint32_t)row_in_tile * 64u;
+        if (storer) bulk_wait_read<1>();  // the store that read this buffer two chunks ago has drained it
+        __syncwarp();
+        const uint32_t boff = (stg_cnt & 1u) * 2048u;
+        uint8_t* rowp = stg_gen + boff + (uint32_t)lane * 64u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack16(v[8 * j], v[8 * j + 1], FP16);
-          u.y = pack16(v[8 * j + 2], v[8 * j + 3], FP16);
-          u.z = pack16(v[8 * j + 4], v[8 * j + 5], FP16);
-          u.w = pack16(v[8 * j + 6], v[8 * j + 7], FP16);
-          *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) = u;
-        }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async();
-        bar_half();
-        // the staging tile is in MMA row order (8g + i); the store's box walks (channel, i, g) so row 8g + i lands on
-        // output row t0 + 16 i + g
-        if (p.store_mode == 0) {
-          if (leader) {
-            if (tile_ok) tma_store_5d(&p.tma_o, stg_addr + boff, cbase + c * 32, 0, 0, t0 >> 7, lseq);
-            bulk_commit();
+        __syncwarp();
+        // the warp's staging tile is in MMA row order (lane = 8 (g - 4 quad) + i); the store's box walks (channel, i, g)
+        // so that row lands on output row t0 + 16 i + g
+        if (storer) {
+          if (tile_ok) {
+            if (p.store_mode == 0) tma_store_5d(&p.tma_o, stg_addr + boff, cbase + c * 32, 0, 4 * quad, t0 >> 7, lseq);
+            else tma_store_4d(&p.tma_o, stg_addr + boff + (uint32_t)lane * 512u, cbase + c * 32, 4 * quad + lane, t0 >> 4, lseq);
           }
-        } else if (lead_warp && lane < 16) {
-          if (tile_ok) tma_store_4d(&p.tma_o, stg_addr + boff + (uint32_t)lane * 512u, cbase + c * 32, lane, t0 >> 4, lseq);
           bulk_commit();
         }
         ++stg_cnt;
       }
     }
-    tc_fence_before();
-    mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
-  if (p.store_mode == 0) {
-    if (leader) bulk_wait<0>();
-  } else if (lead_warp && lane < 16) {
-    bulk_wait<0>();
-  }
+  if (storer) bulk_wait<0>();
   }
 }
 
@@ -356,14 +324,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (8 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (10 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * 12;
+  const uint32_t xa_full_bar = bar_base + 8u * 12;  // leader: x' operand rows of both CTAs written (8 warps)
+  const uint32_t d0_full_bar = bar_base + 8u * 13;  // both: the conv0 GEMM of the current tap has completed
+  const uint32_t d0_free_bar = bar_base + 8u * 14;  // leader: both CTAs' producers have read D0 out of TMEM (8 warps)
+  const uint32_t win_full_bar = bar_base + 8u * 15;  // local: the waveform window of tile n is complete (producers -> extra-row warp)
+  const uint32_t win_free_bar = bar_base + 8u * 16;  // local: the extra-row warp has read the window of tile n
+  const uint32_t tmem_slot = bar_base + 8u * 20;
   F01Vecs& ev = *reinterpret_cast<F01Vecs*>(smem_gen + F_OFF_VEC);
   float* xs = reinterpret_cast<float*>(smem_gen + F_OFF_XSB);
-  float* xps = reinterpret_cast<float*>(smem_gen + F_OFF_XP);
-  // warp index through a shuffle: the compiler then knows the role branches are warp-uniform (uniform registers for
-  // the producers' parameter-bank weight loads)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs, owns the full barriers)
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs, owns the cross-CTA barriers)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tma_w);
@@ -376,6 +346,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
       mbar_init(tfull_bar(a), 1);     // multicast MMA commit
       mbar_init(tempty_bar(a), 512);  // the epilogue threads of both CTAs (leader's copy is the one used)
     }
+    mbar_init(xa_full_bar, 2 * F_PROD_WARPS);
+    mbar_init(d0_full_bar, 1);  // multicast MMA commit
+    mbar_init(d0_free_bar, 2 * F_PROD_WARPS);
+    mbar_init(win_full_bar, 1);
+    mbar_init(win_free_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
@@ -395,9 +370,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
     ev.h2[10] = ev.h2[11] = 0.f;
     ev.s = p.cs.s;
   }
+  // conv0 B operand of this CTA's 128 channels: fp16 [k chunk of 8][channel][8], K = (u0..9, d, beta, 0 x4 | u0..9, d, 0 x5)
+  for (int i = threadIdx.x; i < 128 * 32; i += F_THREADS) {
+    const int n = i >> 5, k = i & 31, kk = k & 15;
+    const float v = (kk < 11 || k == 11) ? __ldg(p.wg + kk * kDim + (int)rank * 128 + n) : 0.f;
+    *reinterpret_cast<__half*>(smem_gen + F_OFF_U + (k >> 3) * 2048 + n * 16 + (k & 7) * 2) = __float2half_rn(v);
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();  // both CTAs' barriers and TMEM allocations exist before anyone signals across the pair
+  cluster_sync_all();  // both CTAs' barriers, operands and TMEM allocations exist before anyone signals across the pair
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -407,6 +389,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
   auto tile_of = [&](int pt, int* lseq, int* t0) {
     *lseq = pt / p.pair_tiles_per_seq;
     *t0 = (pt % p.pair_tiles_per_seq) * 256 + (int)rank * 128;
+  };
+  // TMEM columns of the conv0 result of (tile iteration it, tap j): tap 0 sits in the tile's own conv1 accumulator
+  // (it & 1) before that tile's main loop starts, taps 1-3 in the other one
+  auto d0_acc = [&](int it, int j) { return j == 0 ? (it & 1) : ((it + 1) & 1); };
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+  auto stamp = [&](int it, int j, int e) {
+    if (dbg_on && it < 4) p.dbg[(it * 4 + j) * 16 + e] = clock64();
   };
 
   if (warp == 0) {
@@ -428,41 +417,143 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA only): per stage, taps j and j+4 from the same A block one row group apart
+    // ===== MMA issuer (leader CTA only). Per tap: C C Z C C, where C = one ring stage of conv1 (taps j and j+4 from the
+    // same A block one row group apart) and Z = the conv0 GEMM of the NEXT tap, issued while two stages are still queued
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = make_idesc_16(256, 256, 0, 0, FP16);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      const uint32_t idesc1 = make_idesc_16(256, 256, 0, 0, FP16);
+      const uint32_t idesc0 = make_idesc_16(256, 256, 0, 0, 1);  // conv0: fp16 operands in either mode
+      int stage = 0;
+      uint32_t phase = 0, z = 0;  // z = conv0 GEMMs issued so far
+      // true when the next conv0 GEMM could be issued without blocking (same conditions as issue_z waits for)
+      auto z_ready = [&](int it, int j) {
+        if (j == 1 && !mbar_test_cluster(tempty_bar(d0_acc(it, j)), (uint32_t)((((it + 1) >> 1) - 1) & 1))) return false;
+        return mbar_test_cluster(xa_full_bar, z & 1u) && mbar_test_cluster(d0_free_bar, (z - 1u) & 1u);
+      };
+      auto issue_z = [&](int it, int j) {
+        const int a = d0_acc(it, j);
+        stamp(it, j, 9);
+        // taps 1-3 go to the other accumulator: the epilogues of tile it-1 (both CTAs) must have drained it. It is the
+        // k-th release of that barrier, k = (it+1)/2 (k = 0: nothing to wait for, the parity trick passes)
+        if (j == 1) mbar_wait(tempty_bar(a), (uint32_t)((((it + 1) >> 1) - 1) & 1));
+        mbar_wait_cluster(xa_full_bar, z & 1u);
+        stamp(it, j, 10);
+        mbar_wait_cluster(d0_free_bar, (z - 1u) & 1u);  // the previous conv0 result has left TMEM (z = 0 passes)
+        stamp(it, j, 11);
+        tc_fence_after();
+        const uint32_t xa = smem_base + F_OFF_XA, ub = smem_base + F_OFF_U;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+          umma_16_2sm(tmem_base + a * 256, make_smem_desc_nosw(xa + s2 * 4096, 2048, 128),
+                      make_smem_desc_nosw(ub + s2 * 4096, 2048, 128), idesc0, s2 != 0);
+        umma_commit_2sm(d0_full_bar);
+        ++z;
+      };
+      auto issue_c = [&](uint32_t d_tmem, int ss, int it) {
+        mbar_wait_cluster(full_bar(stage), phase);
+        stamp(it, ss >> 2, 12 + (ss & 3));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + stage * F_STAGE_BYTES, w_addr = a_addr + F_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_16_2sm(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(w_addr + k * 32, 0, 1024),
+                      idesc1, (ss | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_16_2sm(d_tmem, make_smem_desc_sw128(a_addr + 1024 + k * 32, 0, 1024),
+                      make_smem_desc_sw128(w_addr + F_WK_BYTES + k * 32, 0, 1024), idesc1, 1);
+        umma_commit_2sm(empty_bar(stage));
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      };
+      int it = 0;
+      if (cluster_id < num_pair_tiles) issue_z(0, 0);
+      for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));  // epilogues of tile it-2 have drained it
+        mbar_wait_cluster(d0_free_bar, 0u);  // conv0 result 4 it (tap 0 of this tile, in this accumulator) has been read out
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int ss = 0; ss < 16; ++ss) {
-          mbar_wait_cluster(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * F_STAGE_BYTES, w_addr = a_addr + F_A_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_16_2sm(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(w_addr + k * 32, 0, 1024),
-                        idesc, (ss | k) != 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_16_2sm(d_tmem, make_smem_desc_sw128(a_addr + 1024 + k * 32, 0, 1024),
-                        make_smem_desc_sw128(w_addr + F_WK_BYTES + k * 32, 0, 1024), idesc, 1);
-          umma_commit_2sm(empty_bar(stage));
-          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        const bool more = pt + n_clusters < num_pair_tiles;
+        for (int j = 0; j < 4; ++j) {
+          // C C Z C C, but a conv0 GEMM that is not ready yet (tap 1 waits for the previous tile's epilogue) lets the
+          // remaining stages of this tap go first instead of idling the tensor pipe behind a blocked issuer
+          const bool has_z = j < 3 || more;
+          const int zi = j < 3 ? it : it + 1, zj = j < 3 ? j + 1 : 0;
+          issue_c(d_tmem, 4 * j, it);
+          issue_c(d_tmem, 4 * j + 1, it);
+          int c_next = 2;
+          while (has_z && c_next < 4 && !z_ready(zi, zj)) issue_c(d_tmem, 4 * j + c_next++, it);
+          if (has_z) issue_z(zi, zj);
+          while (c_next < 4) issue_c(d_tmem, 4 * j + c_next++, it);
         }
         umma_commit_2sm(tfull_bar(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp == 3 || warp >= F_PROD_WARP0) {
-    // ===== conv0 producers (warps 12-15) and the extra row t0 + 128 (warp 3)
-    const bool extra = warp == 3;
-    const int pw = warp - F_PROD_WARP0;
-    const int ptid = pw * 32 + lane;                                    // producers: MMA row r = 8g + i of the x' pass
-    const int dt = extra ? 128 : 16 * (ptid & 7) + (ptid >> 3);         // t - t0 of that row
-    auto bar_all = [&]() { asm volatile("bar.sync 4, %0;" ::"n"((F_PROD_WARPS + 1) * 32) : "memory"); };
+  } else if (warp == 3) {
+    // ===== the extra row t0 + 128 (group 16, row 7 of every A block): CUDA cores, lane = channels 8 lane .. 8 lane + 7,
+    // fp32 weights from global memory (L1-resident)
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters, ++it) {
+      int lseq, t0;
+      tile_of(pt, &lseq, &t0);
+      // The tile's window xs[it & 1]: wait for the producers, take the 25 samples of the four taps at once and hand the
+      // buffer back (mbarriers, not a block barrier: this warp runs up to three ring stages behind the producers, which
+      // must not wait for it - they would be waiting for stages that only they can fill).
+      mbar_wait(win_full_bar, (uint32_t)(it & 1));
+      float xall[25];
+      {
+        const float* xw = xs + (it & 1) * F_XS;
+#pragma unroll
+        for (int k = 0; k < 25; ++k) xall[k] = xw[(2560 + k) + (2560 + k) / 320];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(win_free_bar);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = 4 * (t0 + 128) - 2 + j;
+        const bool valid = f >= 0 && f < p.L0;
+        float xv[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) xv[k] = xall[5 * j + k];
+        const float rstd = valid ? frame_rstd(ev, xv) : 0.f;
+        float acc[8];
+        {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.wg + 11 * kDim + lane * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.wg + 11 * kDim + lane * 8 + 4));
+          const float fl = valid ? 1.f : 0.f;
+          acc[0] = fl * b0.x; acc[1] = fl * b0.y; acc[2] = fl * b0.z; acc[3] = fl * b0.w;
+          acc[4] = fl * b1.x; acc[5] = fl * b1.y; acc[6] = fl * b1.z; acc[7] = fl * b1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const float xk = (k < 10 ? xv[k % 10] : 1.f) * rstd;
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wg + k * kDim + lane * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wg + k * kDim + lane * 8 + 4));
+          acc[0] = fmaf(xk, w0.x, acc[0]); acc[1] = fmaf(xk, w0.y, acc[1]);
+          acc[2] = fmaf(xk, w0.z, acc[2]); acc[3] = fmaf(xk, w0.w, acc[3]);
+          acc[4] = fmaf(xk, w1.x, acc[4]); acc[5] = fmaf(xk, w1.y, acc[5]);
+          acc[6] = fmaf(xk, w1.z, acc[6]); acc[7] = fmaf(xk, w1.w, acc[7]);
+        }
+        const uint4 u = make_uint4(pack_relu<FP16>(acc[0], acc[1]), pack_relu<FP16>(acc[2], acc[3]),
+                                   pack_relu<FP16>(acc[4], acc[5]), pack_relu<FP16>(acc[6], acc[7]));
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if ((lane >> 3) == cb)
+            *reinterpret_cast<uint4*>(smem_gen + stage * F_STAGE_BYTES + 16 * 1024 + 7 * 128 +
+                                      ((((uint32_t)lane & 7u) ^ 7u) << 4)) = u;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa(full_bar(stage), 0));
+          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= F_PROD_WARP0) {
+    // ===== conv0 producers (warps 12-15): lane = MMA row r = 8g + i  <->  t = t0 + 16 i + g
+    const int pw = warp - F_PROD_WARP0;  // = TMEM lane quadrant of the warp (12 % 4 == 0)
+    const int r = pw * 32 + lane;
+    const int dt = 16 * (r & 7) + (r >> 3);  // t - t0 of the row
     auto bar_prod = [&]() { asm volatile("bar.sync 5, %0;" ::"n"(F_PROD_WARPS * 32) : "memory"); };
     auto prefetch = [&](int pt, int buf) {  // the tile's waveform window -> xs[buf] (zero outside the signal)
       int lseq, t0;
@@ -471,101 +562,145 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
       const float* x = p.wav + ((long long)(seq % p.batch) * 2 + seq / p.batch) * p.n_samples;
       const long long sbase = 20LL * t0 - 13;
       const uint32_t dst = smem_base + F_OFF_XSB + (uint32_t)buf * (F_XS * 4);
-      for (int i = ptid; i < F_WIN; i += F_PROD_WARPS * 32) {
+      for (int i = r; i < F_WIN; i += F_PROD_WARPS * 32) {
         const long long s = sbase + i;
         const bool ok = s >= 0 && s < p.n_samples;
         cp_async4(dst + 4u * (uint32_t)(i + i / 320), ok ? x + s : x, ok ? 4u : 0u);
       }
       cp_async_commit();
     };
+    const uint32_t xa_full_leader = mapa(xa_full_bar, 0), d0_free_leader = mapa(d0_free_bar, 0);
+    // diagnostics: cycles this warp spent per phase, summed over the kernel (registers; written once at the end)
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0;
+    const bool tm_on = p.dbg != nullptr && blockIdx.x == 0 && pw == 0;
+    auto tick = [&]() { if (tm_on) tc0 = clock64(); };
+    auto tock = [&](int k) { if (tm_on) { const long long t1 = clock64(); tm[k] += t1 - tc0; tc0 = t1; } };
+    // X: operand row of the conv0 GEMM of tap j of the tile starting at t0 (window buffer buf): this thread's frame
+    // scaled by its 1 / sqrt(var + eps), as fp16 hi parts (10 taps, rstd, validity flag) in k 0..15 and lo parts in
+    // k 16..31. Zero padding frames of conv1 (f < 0, f >= L0) give an all-zero row. The caller has seen the previous
+    // conv0 GEMM complete (d0_full), so the single operand buffer is free.
+    auto make_x = [&](int t0, int buf, int j) {
+      const float* xw = xs + buf * F_XS;
+      const int f = 4 * (t0 + dt) - 2 + j;
+      const bool valid = f >= 0 && f < p.L0;
+      const int i0 = 20 * dt + 5 * j;
+      float xv[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) xv[k] = xw[(i0 + k) + (i0 + k) / 320];
+      const float rstd = valid ? frame_rstd(ev, xv) : 0.f;
+      uint32_t hi[6], lo[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float v0 = q < 5 ? xv[2 * q < 10 ? 2 * q : 0] * rstd : rstd;
+        const float v1 = q < 5 ? xv[2 * q + 1 < 10 ? 2 * q + 1 : 0] * rstd : (valid ? 1.f : 0.f);
+        const __half2 h = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v0 - hf.x, q < 5 ? v1 - hf.y : 0.f);
+        hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[q] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      uint8_t* xrow = smem_gen + F_OFF_XA + r * 16;
+      *reinterpret_cast<uint4*>(xrow) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(xrow + 2048) = make_uint4(hi[4], hi[5], 0u, 0u);
+      *reinterpret_cast<uint4*>(xrow + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(xrow + 6144) = make_uint4(lo[4], lo[5], 0u, 0u);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(xa_full_leader);
+    };
     int stage = 0, it = 0;
-    uint32_t phase = 0;
-    if (!extra && cluster_id < num_pair_tiles) prefetch(cluster_id, 0);
+    uint32_t phase = 0, z = 0;
+    if (cluster_id < num_pair_tiles) {
+      int lseq, t0;
+      tile_of(cluster_id, &lseq, &t0);
+      prefetch(cluster_id, 0);
+      cp_async_wait_all();
+      bar_prod();
+      if (r == 0) mbar_arrive(win_full_bar);
+      if (cluster_id + n_clusters < num_pair_tiles) prefetch(cluster_id + n_clusters, 1);
+      make_x(t0, 0, 0);
+    }
     for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters, ++it) {
-      const int buf = it & 1;
       int lseq, t0;
       tile_of(pt, &lseq, &t0);
-      if (!extra) cp_async_wait_all();
-      bar_all();  // xs[buf] is complete; everyone is done with xs[buf ^ 1] (read during the previous tile)
-      if (!extra && pt + n_clusters < num_pair_tiles) prefetch(pt + n_clusters, buf ^ 1);
-      const float* xw = xs + buf * F_XS;
-      for (int j = 0; j < 4; ++j) {
-        // this thread's frame: samples, 1 / sqrt(var + eps), validity (zero padding frames of conv1 give zeros)
-        const int f = 4 * (t0 + dt) - 2 + j;
-        const bool valid = f >= 0 && f < p.L0;
-        const int i0 = 20 * dt + 5 * j;
-        float xv[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) xv[k] = xw[(i0 + k) + (i0 + k) / 320];
-        const float rstd = valid ? frame_rstd(ev, xv) : 0.f;
-        if (!extra) {
-          // share the scaled frames: every producer warp needs all 128 rows (it owns 16 channels of each)
-          float* xrow = xps + ((j & 1) * 128 + ptid) * 12;
-          *reinterpret_cast<float4*>(xrow) = make_float4(xv[0] * rstd, xv[1] * rstd, xv[2] * rstd, xv[3] * rstd);
-          *reinterpret_cast<float4*>(xrow + 4) = make_float4(xv[4] * rstd, xv[5] * rstd, xv[6] * rstd, xv[7] * rstd);
-          *reinterpret_cast<float4*>(xrow + 8) = make_float4(xv[8] * rstd, xv[9] * rstd, rstd, valid ? 1.f : 0.f);
-          bar_prod();  // (double-buffered on j: the reads of j - 1 finished before their owners arrived here)
-          float xp[4][12];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const float* src = xps + ((j & 1) * 128 + lane + 32 * m) * 12;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const float4 t4 = *reinterpret_cast<const float4*>(src + 4 * q);
-              xp[m][4 * q] = t4.x; xp[m][4 * q + 1] = t4.y; xp[m][4 * q + 2] = t4.z; xp[m][4 * q + 3] = t4.w;
-            }
+      for (int j = 0; j < 4; ++j, ++z) {
+        tick();
+        mbar_wait(d0_full_bar, z & 1u);  // the conv0 GEMM of this tap is in TMEM (and has released the operand buffer)
+        tock(2);
+        // the NEXT tap's operand first: it is off the critical path here (its GEMM is issued two ring stages later)
+        if (j < 3) {
+          make_x(t0, it & 1, j + 1);
+        } else if (pt + n_clusters < num_pair_tiles) {
+          int lseq1, t1;
+          tile_of(pt + n_clusters, &lseq1, &t1);
+          cp_async_wait_all();
+          bar_prod();  // the next tile's window is complete; every producer has left this tile's window
+          if (r == 0) mbar_arrive(win_full_bar);
+          if (pt + 2 * n_clusters < num_pair_tiles) {
+            mbar_wait(win_free_bar, (uint32_t)(it & 1));  // ... and so has the extra-row warp (it read it at its tile start)
+            prefetch(pt + 2 * n_clusters, it & 1);
           }
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            uint8_t* ablk = smem_gen + stage * F_STAGE_BYTES;
-            switch (pw) {  // one instantiation per channel quarter (a warp-dependent index would leave the uniform path)
-              case 0: produce_q<FP16, 0>(p, xp, cb, lane, ablk); break;
-              case 1: produce_q<FP16, 1>(p, xp, cb, lane, ablk); break;
-              case 2: produce_q<FP16, 2>(p, xp, cb, lane, ablk); break;
-              default: produce_q<FP16, 3>(p, xp, cb, lane, ablk); break;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa(full_bar(stage), 0));
-            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
-          }
-        } else {
-          // row t0 + 128 (group 16, row 7): lane = channels 8 lane .. 8 lane + 7, weights from global memory (L1)
-          float acc[8];
-          {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.wg + 11 * kDim + lane * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.wg + 11 * kDim + lane * 8 + 4));
-            const float fl = valid ? 1.f : 0.f;
-            acc[0] = fl * b0.x; acc[1] = fl * b0.y; acc[2] = fl * b0.z; acc[3] = fl * b0.w;
-            acc[4] = fl * b1.x; acc[5] = fl * b1.y; acc[6] = fl * b1.z; acc[7] = fl * b1.w;
-          }
-#pragma unroll
-          for (int k = 0; k < 11; ++k) {
-            const float xk = (k < 10 ? xv[k % 10] : 1.f) * rstd;
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.wg + k * kDim + lane * 8));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.wg + k * kDim + lane * 8 + 4));
-            acc[0] = fmaf(xk, w0.x, acc[0]); acc[1] = fmaf(xk, w0.y, acc[1]);
-            acc[2] = fmaf(xk, w0.z, acc[2]); acc[3] = fmaf(xk, w0.w, acc[3]);
-            acc[4] = fmaf(xk, w1.x, acc[4]); acc[5] = fmaf(xk, w1.y, acc[5]);
-            acc[6] = fmaf(xk, w1.z, acc[6]); acc[7] = fmaf(xk, w1.w, acc[7]);
-          }
-          const uint4 u = make_uint4(pack_relu<FP16>(acc[0], acc[1]), pack_relu<FP16>(acc[2], acc[3]),
-                                     pack_relu<FP16>(acc[4], acc[5]), pack_relu<FP16>(acc[6], acc[7]));
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            if ((lane >> 3) == cb)
-              *reinterpret_cast<uint4*>(smem_gen + stage * F_STAGE_BYTES + 16 * 1024 + 7 * 128 +
-                                        ((((uint32_t)lane & 7u) ^ 7u) << 4)) = u;
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa(full_bar(stage), 0));
-            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
-          }
+          make_x(t1, (it + 1) & 1, 0);
         }
+        tock(1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(pw * 32) << 16) + d0_acc(it, j) * 256;
+        const bool dup = r >= 1 && r < 8;  // rows 1..7 of group 0 are rows 0..6 of group 16
+        const uint32_t sw = (uint32_t)(r & 7), dsw = (uint32_t)((r - 1) & 7);
+        // 64 channels of this row: TMEM -> ReLU -> 16-bit, two 32-column loads (register budget)
+        auto load_pack = [&](int cb, uint32_t (&pk)[32]) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t raw[32];
+            tmem_ld32(taddr + cb * 64 + h * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              pk[h * 16 + i] = pack_relu<FP16>(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
+          }
+        };
+        auto store_blk = [&](const uint32_t (&pk)[32]) {
+          tock(3);
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          tock(4);
+          uint8_t* ablk = smem_gen + stage * F_STAGE_BYTES;
+          uint8_t* arow = ablk + (r >> 3) * 1024 + (r & 7) * 128;
+          uint8_t* drow = ablk + 16 * 1024 + ((r - 1) & 7) * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(arow + (((uint32_t)c ^ sw) << 4)) = u;
+            if (dup) *reinterpret_cast<uint4*>(drow + (((uint32_t)c ^ dsw) << 4)) = u;
+          }
+          tock(5);
+          fence_proxy_async();
+          tock(6);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa(full_bar(stage), 0));
+          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+          tock(7);
+        };
+        // The last channel block is read FIRST and held in registers: D0 has then left TMEM as soon as block 2 is
+        // loaded (after block 1's stage came free), one stage time before the ring could take block 3 - the next
+        // conv0 GEMM and, for tap 0, the tile's conv1 main loop are waiting for exactly that.
+        uint32_t held[32];
+        load_pack(3, held);
+#pragma unroll 1
+        for (int cb = 0; cb < 3; ++cb) {
+          uint32_t pk[32];
+          load_pack(cb, pk);
+          if (cb == 2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(d0_free_leader);
+          }
+          store_blk(pk);
+        }
+        store_blk(held);
       }
     }
+    if (tm_on && lane == 0)
+      for (int k = 0; k < 8; ++k) p.dbg[256 + k] = tm[k];
   } else if (warp >= 4 && warp < 12) {
     const F01EpiArgs ea{smem_base, tmem_base, rank, smem_gen, warp, lane, num_pair_tiles, n_clusters, cluster_id};
     conv01_epilogue<FP16>(p, ea);
@@ -582,16 +717,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
 }  // namespace
 
 // wav: (batch, 2, n_samples) fp32; sequences [seq0, seq0 + nseq) of the channel-major order c * batch + item.
-// u / d / beta: folded conv0 parameters (conv0_v2_fold) on the HOST (they travel as kernel parameters) and the same
-// table [12][256] = u | d | beta in device memory (wg). w1: conv1 weight [256][8 * 256] (16-bit, tap-major K), bias1 /
+// dev_tab: folded conv0 parameters (conv0_v2_fold) [12][256] = u (10 taps) | d | beta in device memory (host_tab, the
+// same table on the host, is not used any more: the first version passed it as kernel parameters). w1: conv1 weight [256][8 * 256] (16-bit, tap-major K), bias1 /
 // g1 / b1: conv1 bias and ChannelNorm affine (device). out: row t of sequence s at out + s * out_seq_stride +
 // (out_pad_rows + t) * 256; the kernel writes whole 128-row tiles (zeros past L1), so every sequence needs
 // out_pad_rows + roundup(L1, 128) rows.
 int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq, long long L0,
                   long long L1, const float* host_tab /*[12][256]*/, const float* dev_tab, const Conv0Stats& cs,
                   const void* w1, const float* bias1, const float* g1, const float* b1, void* out,
-                  long long out_seq_stride, int out_pad_rows, int n_sm, std::string* err) {
+                  long long out_seq_stride, int out_pad_rows, int n_sm, std::string* err, long long* dbg) {
   F01Params p{};
+  p.dbg = dbg;
   {
     const uint64_t dims[2] = {(uint64_t)(8 * kDim), (uint64_t)kDim};
     const uint64_t strides[1] = {(uint64_t)(8 * kDim)};
@@ -605,7 +741,7 @@ int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samp
   if (p.store_mode == 0) {
     const uint64_t dims[5] = {(uint64_t)kDim, 8, 16, (uint64_t)tiles128, (uint64_t)nseq};
     const uint64_t strides[4] = {16ull * kDim, (uint64_t)kDim, 128ull * kDim, (uint64_t)out_seq_stride};
-    const uint32_t box[5] = {32, 8, 16, 1, 1};
+    const uint32_t box[5] = {32, 8, 4, 1, 1};  // one epilogue warp's 32 rows: 4 row groups g, 8 rows i each
     std::string e0;
     if (!make_tmap(&p.tma_o, obase, 2, 5, dims, strides, box, 64, &e0)) {
       if (force_mode == 0) { if (err) *err = e0; return -1; }
@@ -618,10 +754,6 @@ int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samp
     const uint32_t box[4] = {32, 1, 8, 1};
     if (!make_tmap(&p.tma_o, obase, 2, 4, dims, strides, box, 64, err)) return -1;
   }
-  for (int k = 0; k < 12; ++k)
-    for (int c4 = 0; c4 < 64; ++c4)
-      p.wq[k][c4] = make_float4(host_tab[k * kDim + 4 * c4], host_tab[k * kDim + 4 * c4 + 1], host_tab[k * kDim + 4 * c4 + 2],
-                                host_tab[k * kDim + 4 * c4 + 3]);
   p.cs = cs;
   p.wav = wav;
   p.wg = dev_tab;
