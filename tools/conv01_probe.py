@@ -35,12 +35,16 @@ for B, S, fp16 in [(1, 2000, 0), (1, 40000, 1), (3, 320000, 1)]:
 
 # timeline of the first tiles (SM clocks of cluster 0 / CTA 0): producer warp 12 and the MMA thread
 if os.environ.get("CONV01_TIMELINE", "1") != "0":
-    dbg = torch.zeros(4 * 4 * 16 + 16, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(4 * 4 * 16 + 32, dtype=torch.int64, device="cuda")
     _conv01_case(64, 320000, 1, seed=5, dbg=dbg)
     tm = dbg[256:264].cpu().tolist()
     d = dbg[:256].reshape(4, 4, 16).cpu()
+    et = dbg[264:268].cpu().tolist()
+    if et[3]:
+        print(f"epilogue warp 4 of CTA 0, cycles per tile: accumulator ready -> statistics {et[0] / et[3]:.0f}, -> released "
+              f"{et[1] / et[3]:.0f}, -> tile done {et[2] / et[3]:.0f}  ({et[3]} tiles)")
     t00 = int(d[d > 0].min())
-    pn = ["(unused)", "next tap's X (+ window barrier at tile end)", "wait d0_full", "load_pack (TMEM -> regs)",
+    pn = ["first block (ld + st) before X", "next tap's X (+ window barrier at tile end)", "wait d0_full", "load_pack (TMEM -> regs)",
           "wait stage empty", "STS", "fence.proxy.async", "syncwarp + arrive"]
     tot = sum(tm)
     print("producer warp 12 of CTA 0, cycles per phase over the whole kernel:")

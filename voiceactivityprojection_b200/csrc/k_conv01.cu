@@ -42,6 +42,13 @@ using namespace tc;
 
 namespace {
 
+// diagnostics (tools/conv01_probe.py): SM-clock timers, compiled only into the probe build (-DF01_TIMERS)
+#ifdef F01_TIMERS
+#define F01_T(...) __VA_ARGS__
+#else
+#define F01_T(...)
+#endif
+
 constexpr int F_STAGES = 3;
 constexpr int F_A_BYTES = 17 * 1024;              // 17 row groups x (8 rows x 128 B)
 constexpr int F_WK_BYTES = 128 * 64 * 2;          // one k-block of this CTA's half of W1
@@ -169,17 +176,23 @@ __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {  // max(., 0
 }
 
 // 1 / sqrt(var + eps) over the 256 conv0 channels of a frame from its 10 samples (vap/encoder_components.py:62-70)
+// cs.G holds the symmetric matrix folded to its upper triangle (off-diagonal entries doubled, lower triangle zero):
+// 55 multiply-adds instead of 100, and only the float4 groups that hold non-zeros are read.
 template <typename V>
 __device__ __forceinline__ float frame_rstd(const V& cs, const float (&xv)[10]) {
   float ss = cs.s;
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
-    const float4 g0 = *reinterpret_cast<const float4*>(&cs.G[k][0]), g1 = *reinterpret_cast<const float4*>(&cs.G[k][4]),
-                 g2 = *reinterpret_cast<const float4*>(&cs.G[k][8]);
     float y = cs.h2[k];
-    y = fmaf(g0.x, xv[0], y); y = fmaf(g0.y, xv[1], y); y = fmaf(g0.z, xv[2], y); y = fmaf(g0.w, xv[3], y);
-    y = fmaf(g1.x, xv[4], y); y = fmaf(g1.y, xv[5], y); y = fmaf(g1.z, xv[6], y); y = fmaf(g1.w, xv[7], y);
-    y = fmaf(g2.x, xv[8], y); y = fmaf(g2.y, xv[9], y);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (4 * q + 3 < k) continue;  // this group lies below the diagonal
+      const float4 g = *reinterpret_cast<const float4*>(&cs.G[k][4 * q]);
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (4 * q + e >= k && 4 * q + e < 10) y = fmaf(gv[e], xv[4 * q + e], y);
+    }
     ss = fmaf(xv[k], y, ss);
   }
   return rsqrtf(fmaxf(ss, 0.f) * (1.0f / (kDim - 1)) + kEps);
@@ -220,6 +233,8 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
   auto bar_epi = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
   const uint32_t tempty_leader0 = mapa(tempty_bar(0), 0), tempty_leader1 = mapa(tempty_bar(1), 0);
   const bool storer = p.store_mode == 0 ? lane == 0 : lane < 4;  // lanes that issue this warp's TMA stores
+  // diagnostics: cycles from accumulator-ready to statistics, to release, to tile end; tiles
+  F01_T(long long etm[4] = {0, 0, 0, 0}; const bool etm_on = p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;)
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters) {
@@ -227,11 +242,15 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
     tile_of(pt, &lseq, &t0);
     const bool row_ok = t0 + dt < p.L1, tile_ok = t0 < p.L1;
     mbar_wait(tfull_bar(acc), acc_phase);
+    F01_T(long long te0 = 0, te1 = 0; if (etm_on) te0 = clock64();)
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + cbase;
+    // Pass 1: mean / variance of (acc + bias) over the row's 256 channels (this thread's 128, then the other half's
+    // partial sums through shared memory). Packed fp32 arithmetic throughout: the epilogue sits on the path that
+    // releases the accumulator for the next tile's conv0 GEMMs.
     float mean1, rstd1;
     {
-      float s = 0.f, ss = 0.f;
+      float2 s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, q2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       uint32_t rr[2][32];
       tmem_ld32(taddr, rr[0]);
 #pragma unroll
@@ -241,12 +260,17 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 bi = *reinterpret_cast<const float4*>(&ev.bias[cbase + c * 32 + i]);
-          const float v0 = __uint_as_float(rr[c & 1][i]) + bi.x, v1 = __uint_as_float(rr[c & 1][i + 1]) + bi.y;
-          const float v2 = __uint_as_float(rr[c & 1][i + 2]) + bi.z, v3 = __uint_as_float(rr[c & 1][i + 3]) + bi.w;
-          s += (v0 + v1) + (v2 + v3);
-          ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+          const float2 v0 = __fadd2_rn(make_float2(__uint_as_float(rr[c & 1][i]), __uint_as_float(rr[c & 1][i + 1])),
+                                       make_float2(bi.x, bi.y));
+          const float2 v1 = __fadd2_rn(make_float2(__uint_as_float(rr[c & 1][i + 2]), __uint_as_float(rr[c & 1][i + 3])),
+                                       make_float2(bi.z, bi.w));
+          s2[0] = __fadd2_rn(s2[0], v0);
+          s2[1] = __fadd2_rn(s2[1], v1);
+          q2[0] = __ffma2_rn(v0, v0, q2[0]);
+          q2[1] = __ffma2_rn(v1, v1, q2[1]);
         }
       }
+      float s = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y), ss = (q2[0].x + q2[0].y) + (q2[1].x + q2[1].y);
       ev.part[half][row_in_tile][0] = s;
       ev.part[half][row_in_tile][1] = ss;
       bar_epi();
@@ -256,60 +280,75 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
       const float var = fmaxf(ss - s * mean1, 0.f) * (1.0f / (kDim - 1));
       rstd1 = rsqrtf(var + kEps);
       bar_epi();
+      F01_T(if (etm_on) { te1 = clock64(); etm[0] += te1 - te0; })
     }
+    // Pass 2: out = relu(((acc + bias) - mean) * rstd * g + b) as three packed FMAs and a cvt.relu pack per channel
+    // pair. All four 32-channel chunks are computed into registers first, so the accumulator is released after the
+    // last TMEM load and the staging / TMA stores happen off that path.
+    uint32_t pk[4][16];
     {
-      uint32_t rr[2][32];
-      tmem_ld32(taddr, rr[0]);
+      const float2 r2 = make_float2(rstd1, rstd1), m2 = make_float2(-mean1 * rstd1, -mean1 * rstd1);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c8 = 0; c8 < 8; ++c8) {  // 16 columns at a time (register budget: the 64 packed outputs stay live)
+        const int c = c8 >> 1, i0 = (c8 & 1) * 16;
+        uint32_t rr[16];
+        tmem_ld16(taddr + c8 * 16, rr);
         tmem_ld_wait();
-        if (c < 3) {
-          tmem_ld32(taddr + (c + 1) * 32, rr[(c + 1) & 1]);
-        } else {
-          // the accumulator has been read for the last time: release it before the last chunk's arithmetic and store
+        if (c8 == 7) {
           tc_fence_before();
           mbar_arrive_remote(acc == 0 ? tempty_leader0 : tempty_leader1);
+          F01_T(if (etm_on) { const long long t2 = clock64(); etm[1] += t2 - te1; te1 = t2; })
         }
-        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int ii = 0; ii < 16; ii += 4) {
+          const int i = i0 + ii;
           const float4 bi = *reinterpret_cast<const float4*>(&ev.bias[cbase + c * 32 + i]);
           const float4 g = *reinterpret_cast<const float4*>(&ev.g1[cbase + c * 32 + i]);
           const float4 b = *reinterpret_cast<const float4*>(&ev.b1[cbase + c * 32 + i]);
-          const float bb[4] = {bi.x, bi.y, bi.z, bi.w}, gg[4] = {g.x, g.y, g.z, g.w}, be[4] = {b.x, b.y, b.z, b.w};
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = fmaf((__uint_as_float(rr[c & 1][i + j]) + bb[j] - mean1) * rstd1, gg[j], be[j]);
-            v[j] = row_ok ? fmaxf(x, 0.f) : 0.f;  // rows past the sequence end are the next layer's zero padding
-          }
-          pk[i >> 1] = pack16(v[0], v[1], FP16);
-          pk[(i >> 1) + 1] = pack16(v[2], v[3], FP16);
+          float2 t0v = __ffma2_rn(make_float2(__uint_as_float(rr[ii]), __uint_as_float(rr[ii + 1])), r2, m2);
+          float2 t1v = __ffma2_rn(make_float2(__uint_as_float(rr[ii + 2]), __uint_as_float(rr[ii + 3])), r2, m2);
+          t0v = __ffma2_rn(make_float2(bi.x, bi.y), r2, t0v);
+          t1v = __ffma2_rn(make_float2(bi.z, bi.w), r2, t1v);
+          t0v = __ffma2_rn(t0v, make_float2(g.x, g.y), make_float2(b.x, b.y));
+          t1v = __ffma2_rn(t1v, make_float2(g.z, g.w), make_float2(b.z, b.w));
+          pk[c][i >> 1] = pack_relu<FP16>(t0v.x, t0v.y);
+          pk[c][(i >> 1) + 1] = pack_relu<FP16>(t1v.x, t1v.y);
         }
-        if (storer) bulk_wait_read<1>();  // the store that read this buffer two chunks ago has drained it
-        __syncwarp();
-        const uint32_t boff = (stg_cnt & 1u) * 2048u;
-        uint8_t* rowp = stg_gen + boff + (uint32_t)lane * 64u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) =
-              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        // the warp's staging tile is in MMA row order (lane = 8 (g - 4 quad) + i); the store's box walks (channel, i, g)
-        // so that row lands on output row t0 + 16 i + g
-        if (storer) {
-          if (tile_ok) {
-            if (p.store_mode == 0) tma_store_5d(&p.tma_o, stg_addr + boff, cbase + c * 32, 0, 4 * quad, t0 >> 7, lseq);
-            else tma_store_4d(&p.tma_o, stg_addr + boff + (uint32_t)lane * 512u, cbase + c * 32, 4 * quad + lane, t0 >> 4, lseq);
-          }
-          bulk_commit();
-        }
-        ++stg_cnt;
       }
     }
+    if (!row_ok) {  // rows past the sequence end are the next layer's zero padding (last tile of a sequence only)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[c][i] = 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (storer) bulk_wait_read<1>();  // the store that read this buffer two chunks ago has drained it
+      __syncwarp();
+      const uint32_t boff = (stg_cnt & 1u) * 2048u;
+      uint8_t* rowp = stg_gen + boff + (uint32_t)lane * 64u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ sw64) << 4)) =
+            make_uint4(pk[c][4 * j], pk[c][4 * j + 1], pk[c][4 * j + 2], pk[c][4 * j + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      // the warp's staging tile is in MMA row order (lane = 8 (g - 4 quad) + i); the store's box walks (channel, i, g)
+      // so that row lands on output row t0 + 16 i + g
+      if (storer) {
+        if (tile_ok) {
+          if (p.store_mode == 0) tma_store_5d(&p.tma_o, stg_addr + boff, cbase + c * 32, 0, 4 * quad, t0 >> 7, lseq);
+          else tma_store_4d(&p.tma_o, stg_addr + boff + (uint32_t)lane * 512u, cbase + c * 32, 4 * quad + lane, t0 >> 4, lseq);
+        }
+        bulk_commit();
+      }
+      ++stg_cnt;
+    }
+    F01_T(if (etm_on) { etm[2] += clock64() - te1; etm[3] += 1; })
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
+  F01_T(if (etm_on) for (int k = 0; k < 4; ++k) p.dbg[264 + k] = etm[k];)
   if (storer) bulk_wait<0>();
   }
 }
@@ -364,7 +403,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
 #pragma unroll
-      for (int l = 0; l < 12; ++l) ev.G[k][l] = l < 10 ? p.cs.G[k][l < 10 ? l : 0] : 0.f;
+      for (int l = 0; l < 12; ++l)  // upper triangle, off-diagonal entries doubled (G is symmetric)
+        ev.G[k][l] = (l < 10 && l >= k) ? (l == k ? 1.f : 2.f) * p.cs.G[k][l < 10 ? l : 0] : 0.f;
       ev.h2[k] = p.cs.h2[k];
     }
     ev.h2[10] = ev.h2[11] = 0.f;
@@ -393,10 +433,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
   // TMEM columns of the conv0 result of (tile iteration it, tap j): tap 0 sits in the tile's own conv1 accumulator
   // (it & 1) before that tile's main loop starts, taps 1-3 in the other one
   auto d0_acc = [&](int it, int j) { return j == 0 ? (it & 1) : ((it + 1) & 1); };
+#ifdef F01_TIMERS
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
   auto stamp = [&](int it, int j, int e) {
     if (dbg_on && it < 4) p.dbg[(it * 4 + j) * 16 + e] = clock64();
   };
+#else
+  auto stamp = [&](int, int, int) {};
+#endif
 
   if (warp == 0) {
     // ===== TMA producer of W1 (both CTAs): k-blocks (j, cb) and (j+4, cb), own 128 output channels
@@ -571,10 +615,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
     };
     const uint32_t xa_full_leader = mapa(xa_full_bar, 0), d0_free_leader = mapa(d0_free_bar, 0);
     // diagnostics: cycles this warp spent per phase, summed over the kernel (registers; written once at the end)
+#ifdef F01_TIMERS
     long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc0 = 0;
     const bool tm_on = p.dbg != nullptr && blockIdx.x == 0 && pw == 0;
     auto tick = [&]() { if (tm_on) tc0 = clock64(); };
     auto tock = [&](int k) { if (tm_on) { const long long t1 = clock64(); tm[k] += t1 - tc0; tc0 = t1; } };
+#else
+    auto tick = [&]() {};
+    auto tock = [&](int) {};
+#endif
     // X: operand row of the conv0 GEMM of tap j of the tile starting at t0 (window buffer buf): this thread's frame
     // scaled by its 1 / sqrt(var + eps), as fp16 hi parts (10 taps, rstd, validity flag) in k 0..15 and lo parts in
     // k 16..31. Zero padding frames of conv1 (f < 0, f >= L0) give an all-zero row. The caller has seen the previous
@@ -627,36 +676,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
         tick();
         mbar_wait(d0_full_bar, z & 1u);  // the conv0 GEMM of this tap is in TMEM (and has released the operand buffer)
         tock(2);
-        // the NEXT tap's operand first: it is off the critical path here (its GEMM is issued two ring stages later)
-        if (j < 3) {
-          make_x(t0, it & 1, j + 1);
-        } else if (pt + n_clusters < num_pair_tiles) {
-          int lseq1, t1;
-          tile_of(pt + n_clusters, &lseq1, &t1);
-          cp_async_wait_all();
-          bar_prod();  // the next tile's window is complete; every producer has left this tile's window
-          if (r == 0) mbar_arrive(win_full_bar);
-          if (pt + 2 * n_clusters < num_pair_tiles) {
-            mbar_wait(win_free_bar, (uint32_t)(it & 1));  // ... and so has the extra-row warp (it read it at its tile start)
-            prefetch(pt + 2 * n_clusters, it & 1);
-          }
-          make_x(t1, (it + 1) & 1, 0);
-        }
-        tock(1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(pw * 32) << 16) + d0_acc(it, j) * 256;
         const bool dup = r >= 1 && r < 8;  // rows 1..7 of group 0 are rows 0..6 of group 16
         const uint32_t sw = (uint32_t)(r & 7), dsw = (uint32_t)((r - 1) & 7);
-        // 64 channels of this row: TMEM -> ReLU -> 16-bit, two 32-column loads (register budget)
+        // 64 channels of this row: TMEM -> ReLU -> 16-bit, four 16-column loads (register budget)
         auto load_pack = [&](int cb, uint32_t (&pk)[32]) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t raw[32];
-            tmem_ld32(taddr + cb * 64 + h * 32, raw);
+          for (int h = 0; h < 4; ++h) {
+            uint32_t raw[16];
+            tmem_ld16(taddr + cb * 64 + h * 16, raw);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              pk[h * 16 + i] = pack_relu<FP16>(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
+            for (int i = 0; i < 8; ++i)
+              pk[h * 8 + i] = pack_relu<FP16>(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
           }
         };
         auto store_blk = [&](const uint32_t (&pk)[32]) {
@@ -695,12 +728,31 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
             if (lane == 0) mbar_arrive_remote(d0_free_leader);
           }
           store_blk(pk);
+          if (cb == 0) {
+            // the NEXT tap's operand, after this tap's first block is on its way (the stages this tap still owes are
+            // not due before one, two and three stage times from now; its own GEMM is issued two stages from now)
+            tock(0);
+            if (j < 3) {
+              make_x(t0, it & 1, j + 1);
+            } else if (pt + n_clusters < num_pair_tiles) {
+              int lseq1, t1;
+              tile_of(pt + n_clusters, &lseq1, &t1);
+              cp_async_wait_all();
+              bar_prod();  // the next tile's window is complete; every producer has left this tile's window
+              if (r == 0) mbar_arrive(win_full_bar);
+              if (pt + 2 * n_clusters < num_pair_tiles) {
+                mbar_wait(win_free_bar, (uint32_t)(it & 1));  // ... and so has the extra-row warp (it read it at its tile start)
+                prefetch(pt + 2 * n_clusters, it & 1);
+              }
+              make_x(t1, (it + 1) & 1, 0);
+            }
+            tock(1);
+          }
         }
         store_blk(held);
       }
     }
-    if (tm_on && lane == 0)
-      for (int k = 0; k < 8; ++k) p.dbg[256 + k] = tm[k];
+    F01_T(if (tm_on && lane == 0) for (int k = 0; k < 8; ++k) p.dbg[256 + k] = tm[k];)
   } else if (warp >= 4 && warp < 12) {
     const F01EpiArgs ea{smem_base, tmem_base, rank, smem_gen, warp, lane, num_pair_tiles, n_clusters, cluster_id};
     conv01_epilogue<FP16>(p, ea);
