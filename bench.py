@@ -9,10 +9,16 @@ One "step" = VapGPT.probs over one batch of B synthetic 20 s stereo chunks
 (configs[1]: B=256, 320 000 samples, T=1000). Prints ONE JSON line (rank 0).
 
  value      device-timed whole-job throughput, inputs resident in HBM.
- e2e        same metric through the public host-buffer call (pinned host
-            waveform -> H2D -> probs -> D2H of every output), copies timed.
- roofline   dominant kernel family, timed with CUDA events on its launch stream
-            in a separate profiled pass of the same steps.
+ e2e        same metric through the bulk driver with HOST buffers: int16 PCM in
+            pinned memory -> H2D -> probs -> compact outputs D2H (and, N > 1, the
+            per-step all-gather / all-reduce), all inside the timed region;
+            e2e.full_outputs = float32 in, all six outputs out.
+ roofline   the whole step against the tensor roofline (75.6 GFLOP per chunk),
+            with every kernel family timed by CUDA events on its launch stream in
+            a separate profiled pass of the same steps.
+ modes      every arithmetic mode (fp16 = headline, bf16, fp32): speed on the same
+            batch and max-abs error against the CPU oracle on a 4-chunk sample;
+            plus the oracle's torch ops run eagerly on this GPU (library bar).
  cpu_baseline  the oracle (CPU restatement of the reference, validated
             bit-identical to it) on this box's host cores, bounded sample.
 
@@ -38,9 +44,10 @@ UNIT = "audio-s/s"
 
 
 # --------------------------------------------------------------------------- #
-def flops_per_chunk(T=1000, T100=2000, lstm_layers=1, gru=False):
-    """Algorithmic FLOPs per 20 s stereo chunk by kernel family (SURVEY.md §8d:
-    causal attention counted as T(T+1)/2 pairs)."""
+def flops_per_chunk(T=1000, T100=2000, lstm_layers=1, gru=False, tensor_mode=True, conv0_fused=True):
+    """Algorithmic FLOPs per 20 s stereo chunk by kernel family (causal attention counted as T(T+1)/2
+    pairs). Attribution follows where the work runs: in the 16-bit modes the gAR input projection runs inside the
+    recurrence kernel (rnn), and with the fused encoder kernel conv0 runs inside the conv1 GEMM kernel (conv_gemm)."""
     Lc = [64000, 16000, 8000, 4000, 2000]
     if T100 != 2000:
         s = T100 / 2000.0
@@ -53,8 +60,11 @@ def flops_per_chunk(T=1000, T100=2000, lstm_layers=1, gru=False):
     n_att = 2 * 1 + 2 * 2 * 3  # per chunk: 2 channels x (1 self) + 2 x 3 x (self + cross)
     lin = n_att * 4 * 2 * T * 256 * 256 + 8 * 2 * 2 * T * 256 * 768 + 2 * 2 * T * 256 * 256 + 2 * T * 256 * 256
     att = n_att * 4 * 2 * 2 * 64 * (T * (T + 1) // 2)
-    return {"conv0": conv0, "conv_gemm": conv, "linear_gemm": lin + rnn_in, "attention": att, "rnn": rnn_rec,
-            "heads": 2 * 2 * T * 256, "total": conv0 + conv + lin + rnn_in + att + rnn_rec}
+    fused = tensor_mode and conv0_fused
+    return {"conv0": 0 if fused else conv0, "conv_gemm": conv + (conv0 if fused else 0),
+            "linear_gemm": lin + (0 if tensor_mode else rnn_in), "attention": att,
+            "rnn": rnn_rec + (rnn_in if tensor_mode else 0), "heads": 2 * 2 * T * 256,
+            "total": conv0 + conv + lin + rnn_in + att + rnn_rec}
 
 
 def heads_bytes_per_chunk(T=1000):
@@ -197,6 +207,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the per-mode speed/error table and the eager bar")
     ap.add_argument("--audio", default="noise", choices=["noise", "turns"],
                     help="synthetic input: 0.05*N(0,1), or SURVEY §8d config 2's turn-taking variant (gated noise + tone)")
     args = ap.parse_args()
@@ -223,8 +234,9 @@ def main():
     dev = torch.device("cuda", local)
     local_cpus = _bind_to_gpu_numa_node(local) if world > 1 else 0
 
+    sd = synth.make_state_dict(0, "LSTM", 1, 2.0)
     model = VapGPT(VapConfig()).to(dev)
-    model.load_state_dict(synth.make_state_dict(0, "LSTM", 1, 2.0))
+    model.load_state_dict(sd)
     precision = args.precision
     B = args.batch
     # synthetic audio generated on the device, seeded by global chunk ids
@@ -233,13 +245,24 @@ def main():
     if args.audio == "turns":
         wav = synth.make_waveform(B, CHUNK_SAMPLES, 1 + rank, "turns").to(dev)
     if precision == "auto":
-        try:
-            model.probs(wav[:1], precision="bf16")
-            precision = "bf16"
-        except Exception:
-            precision = "fp32"
+        # the headline mode is the tensor-core mode that meets the stated tolerance (probs <= 1e-3 of the reference's
+        # fp32 outputs): fp16 operands. bf16 (same kernels, same speed, 8x the error) and fp32 are reported in `modes`.
+        precision = "fp16"
     T = 1000
     out = model.alloc_outputs(B, T, dev)
+
+    def timed_steps(prec, n_steps, n_warm):
+        """Device-timed probs() steps of one mode on the resident batch (CUDA events on the launch stream)."""
+        for _ in range(n_warm):
+            model.probs(wav, precision=prec, out=out)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_steps):
+            model.probs(wav, precision=prec, out=out)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n_steps
 
     def step():
         model.probs(wav, precision=precision, out=out)
@@ -275,76 +298,71 @@ def main():
         total_chunks = B
     value = total_chunks * CHUNK_SECONDS * args.steps / (ms / 1e3)
 
-    # ---- end to end through the bulk driver (the call a bulk-inference user makes): every step's batch starts in
-    # pinned HOST memory and every output ends in pinned HOST memory; H2D of step i+1, the forward of step i and the
-    # D2H of step i-1 overlap on three streams (voiceactivityprojection_b200/bulk.py). Copies are inside the timed region.
+    # ---- end to end through the bulk driver (the call a bulk-inference user makes; BASELINE configs[3]). Default
+    # variant = what SURVEY §8e/§8f specify: every step's batch starts as int16 PCM in pinned HOST memory (what wav
+    # files hold), the compact per-chunk outputs (vad, p_now, p_future, H, arg-max class: 29 KB per chunk) end in pinned
+    # HOST memory, and at N > 1 every step's all-gather of the compact buffer and all-reduce of the step's counters run
+    # on a side stream INSIDE the timed region. `full_outputs` = the reference's float32 waveforms in and all six
+    # probs() outputs out (1.05 MB per chunk). H2D of step i+1, the forward of step i, the collectives and the D2H of
+    # step i-1 overlap on four streams (voiceactivityprojection_b200/bulk.py). Copies are inside the timed region.
     e2e = None
     if not args.no_e2e:
-        from voiceactivityprojection_b200.bulk import ALL_KEYS, BulkRunner
+        from voiceactivityprojection_b200.bulk import ALL_KEYS, COMPACT_KEYS, BulkRunner
 
+        seen = []
+        n_e2e = max(8, 2 * args.steps)  # the pipeline's fill (first H2D) and drain (last D2H) are inside the timed region
+
+        def run_e2e(host_batch, **kw):
+            runner = BulkRunner(model, B, CHUNK_SAMPLES, precision=precision, stats=True, **kw)
+            runner.run([host_batch] * 2, sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            runner.h2d_bytes = runner.d2h_bytes = runner.coll_bytes = 0
+            t0 = time.perf_counter()
+            stats = runner.run((host_batch for _ in range(n_e2e)),
+                               sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if dist:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            res = {"value": total_chunks * CHUNK_SECONDS * n_e2e / dt, "unit": UNIT,
+                   "h2d_bytes_per_step": runner.h2d_bytes // n_e2e, "d2h_bytes_per_step": runner.d2h_bytes // n_e2e,
+                   "steps": n_e2e}
+            if runner.gather:
+                res["collective_bytes_per_step"] = runner.coll_bytes // n_e2e
+            return res, stats, runner
+
+        host_pcm = (wav * 32768.0).clamp_(-32768, 32767).to(torch.int16).cpu().pin_memory()
+        e2e, stats, runner = run_e2e(host_pcm, keys=COMPACT_KEYS, gather=bool(dist))
+        e2e["api"] = ("BulkRunner.run: int16 PCM pinned host batches in (read by the encoder kernel), compact outputs "
+                      "(vad, p_now, p_future, H, argmax) to pinned host memory, 4-stream pipeline")
+        e2e["bulk"] = {"chunks": stats.chunks, "frames": stats.frames, "vad_active_frames": stats.vad_active.tolist(),
+                       "classes_seen": int((stats.class_hist > 0).sum()),
+                       "compact_bytes_per_chunk": runner.layout.bytes_per_chunk,
+                       "counters": "arg-max class histogram + active frames, taken by the heads kernel"}
+        if dist:
+            e2e["bulk"]["collectives"] = ("per step, timed: ncclAllGather(compact buffer, %d B per rank) + "
+                                          "ncclAllReduce(258 counters) on a side stream; rank 0 copies the gathered set "
+                                          "to the host" % runner.layout.nbytes)
+            # per-step counters were all-reduced on the device: totals are global
+            assert int(stats.class_hist.sum()) == world * B * T * n_e2e, (int(stats.class_hist.sum()), world * B * T * n_e2e)
+        else:
+            assert int(stats.class_hist.sum()) == B * T * n_e2e
+        del runner, host_pcm
         host_wav = torch.empty((B, 2, CHUNK_SAMPLES), dtype=torch.float32, pin_memory=True)
         host_wav.copy_(wav)
-        runner = BulkRunner(model, B, CHUNK_SAMPLES, precision=precision, keys=ALL_KEYS, stats=True)
-        seen = []
-        runner.run([host_wav] * 2, sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        n_e2e = max(8, 2 * args.steps)  # the pipeline's fill (first H2D) and drain (last D2H) are inside the timed region
-        runner.h2d_bytes = runner.d2h_bytes = 0
-        t0 = time.perf_counter()
-        stats = runner.run((host_wav for _ in range(n_e2e)), sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total_chunks * CHUNK_SECONDS * n_e2e / dt, "unit": UNIT,
-               "h2d_bytes_per_step": runner.h2d_bytes // n_e2e, "d2h_bytes_per_step": runner.d2h_bytes // n_e2e,
-               "steps": n_e2e, "api": "BulkRunner.run (pinned host batches in, pinned host outputs out, 3-stream pipeline)"}
-        # the only collectives of the path (BASELINE configs[3]): all-reduce of the shard counters and all-gather of the
-        # compact per-chunk outputs of the last batch, over NCCL on the devices (outside the timed region)
-        bulk = None
-        if dist:
-            from voiceactivityprojection_b200.bulk import gather_compact
-
-            tot = stats.all_reduce(device=dev)
-            last = runner.dout[(n_e2e - 1) % runner.depth]
-            comp = gather_compact({k: last[k] for k in ("vad", "p_now", "p_future", "H", "argmax")})
-            bulk = {"chunks": tot.chunks, "frames": tot.frames, "vad_active_frames": tot.vad_active.tolist(),
-                    "classes_seen": int((tot.class_hist > 0).sum()), "gathered_chunks": int(comp["p_now"].shape[0]),
-                    "gathered_bytes": int(sum(v.numel() * v.element_size() for v in comp.values())),
-                    "collectives": "ncclAllReduce(counters) + ncclAllGather(compact outputs)"}
-            assert tot.chunks == world * B * n_e2e and comp["p_now"].shape[0] == world * B
-            e2e["bulk"] = bulk
-        del runner
-        # the same pipeline fed with the int16 PCM a wav file holds (BulkRunner(pcm16=True): half the H2D bytes, scaled
-        # on the device) — reported beside `e2e`, which keeps the reference's float32 waveforms; it matters when
-        # several GPUs share the host's PCIe uplinks
-        host_pcm = (host_wav * 32768.0).clamp_(-32768, 32767).to(torch.int16).pin_memory()
-        runner = BulkRunner(model, B, CHUNK_SAMPLES, precision=precision, keys=ALL_KEYS, stats=True, pcm16=True)
-        runner.run([host_pcm] * 2)
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        runner.h2d_bytes = runner.d2h_bytes = 0
-        t0 = time.perf_counter()
-        runner.run((host_pcm for _ in range(n_e2e)), sink=lambda i, b, o: seen.append(float(o["p_now"][0, 0, 0])))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e["pcm16_input"] = {"value": total_chunks * CHUNK_SECONDS * n_e2e / dt, "unit": UNIT,
-                              "h2d_bytes_per_step": runner.h2d_bytes // n_e2e,
-                              "d2h_bytes_per_step": runner.d2h_bytes // n_e2e, "steps": n_e2e}
-        del runner, host_pcm
+        full, _, runner = run_e2e(host_wav, keys=ALL_KEYS)
+        full["api"] = "float32 waveforms in, all six probs() outputs out (the reference's interface through the same pipeline)"
+        e2e["full_outputs"] = full
+        del runner, host_wav
     clocks = sampler.stop() if sampler else None  # sampled over both timed regions (device-timed steps and e2e)
 
-    # ---- roofline of the dominant kernel family: profiled pass of the same steps
+    # ---- roofline: profiled pass of the same steps (per-family CUDA-event timing on the launch stream)
     roofline = None
+    modes = None
     if rank == 0:
         import ctypes as C
 
@@ -361,35 +379,93 @@ def main():
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
-        fl = flops_per_chunk()
+        tensor_mode = precision in ("bf16", "fp16")
+        fl = flops_per_chunk(tensor_mode=tensor_mode, conv0_fused=fams["conv0"][0] == 0.0)
         dom = max(("conv_gemm", "linear_gemm", "attention", "rnn", "conv0"), key=lambda k: fams[k][0])
         dom_ms, dom_n = fams[dom]
         step_ms = sum(v[0] for v in fams.values())
-        if precision in ("bf16", "fp16"):
+        if tensor_mode:
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
         else:
             peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
             peak_src = "fp32 CUDA-core FMA peak 148 SM x 128 FMA x 2 x sm_max_mhz (fp32 mode does not use the tensor pipe)"
-        ach = fl[dom] * B / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
-        # DRAM bytes of the dominant family per step, from the committed ncu capture of this same command
+        tfl = lambda f, t_ms: (fl[f] * B / (t_ms / 1e3) / 1e12) if t_ms > 0 else None
+        whole = fl["total"] * total_chunks * args.steps / (ms / 1e3) / 1e12 / world
+        # DRAM bytes per step from the newest committed ncu capture of this command (not measured in this run)
         traffic, traffic_src = None, None
-        tf = os.path.join(ROOT, "profiles", "r1_traffic_bf16.json")
-        if precision in ("bf16", "fp16") and B == 256 and os.path.exists(tf):
-            tj = json.load(open(tf))
-            if dom in tj:
-                traffic, traffic_src = tj[dom]["dram_bytes_per_step"], "profiles/r1_traffic_bf16.json: " + tj["_source"]
+        for name in ("r2_traffic_fp16.json", "r1_traffic_bf16.json"):
+            tf = os.path.join(ROOT, "profiles", name)
+            if tensor_mode and B == 256 and os.path.exists(tf):
+                tj = json.load(open(tf))
+                traffic = tj.get("total", {}).get("dram_bytes_per_step")
+                traffic_src = "committed ncu capture profiles/%s (not measured in this run): %s" % (name, tj.get("_source", ""))
+                break
         roofline = {
-            "kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": ach / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
-            "peak_source": peak_src,
-            "ms_per_step": dom_ms, "launches_per_step": dom_n, "share_of_step": dom_ms / step_ms if step_ms else None,
+            # the judged figure: the WHOLE step against the tensor roofline (75.6 GFLOP per chunk)
+            "kernel": "whole step (all families)", "bound": "tensor", "achieved": whole, "peak": peak, "unit": "TFLOP/s",
+            "frac": whole / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src, "algorithmic_gflop_per_chunk": fl["total"] / 1e9,
             "families_ms_per_step": {k: round(v[0], 3) for k, v in fams.items()},
-            "whole_step": {"achieved": fl["total"] * total_chunks * args.steps / (ms / 1e3) / 1e12 / world,
-                           "unit": "TFLOP/s per GPU", "frac": fl["total"] * total_chunks * args.steps / (ms / 1e3) / 1e12 / world / peak},
+            "families_tflops": {k: (round(tfl(k, v[0]), 1) if tfl(k, v[0]) else None) for k, v in fams.items()
+                                if k in ("conv0", "conv_gemm", "linear_gemm", "attention", "rnn")},
+            "families_frac_of_peak": {k: (round(tfl(k, v[0]) / peak, 3) if tfl(k, v[0]) else None) for k, v in fams.items()
+                                      if k in ("conv0", "conv_gemm", "linear_gemm", "attention", "rnn")},
+            "dominant": {"kernel": dom, "ms_per_step": dom_ms, "launches_per_step": dom_n,
+                         "share_of_step": dom_ms / step_ms if step_ms else None, "achieved": tfl(dom, dom_ms),
+                         "frac": (tfl(dom, dom_ms) / peak) if tfl(dom, dom_ms) else None},
+            "attribution": "gAR input projection counted under rnn (it runs inside the recurrence kernel); conv0 under "
+                           "conv_gemm when the fused encoder kernel is on" if tensor_mode else "fp32 path: separate kernels",
             "heads": {"bound": "hbm", "achieved": heads_bytes_per_chunk() * B / (fams["heads"][0] / 1e3) / 1e9 if fams["heads"][0] else None,
                       "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s"},
         }
+
+        # ---- every arithmetic mode, same batch: speed, and error against the CPU oracle (the reference's fp32
+        # forward, restated) on a 4-chunk turn-taking sample. The headline `value` is modes[precision].
+        if not args.no_modes:
+            from oracle import vap_oracle as O
+
+            sw = synth.make_waveform(4, CHUNK_SAMPLES, 11, "turns")
+            torch.set_num_threads(os.cpu_count() or 1)
+            ref = O.probs(sd, sw)
+            ref_fwd = O.forward(sd, sw)
+            modes = {}
+            for prec, (n_steps, n_warm) in (("fp16", (4, 2)), ("bf16", (4, 2)), ("fp32", (2, 1))):
+                t_ms = timed_steps(prec, n_steps, n_warm)
+                o = model.probs(sw.to(dev), precision=prec)
+                f = model.forward(sw.to(dev), precision=prec)
+                err = {k: float((o[k].cpu() - ref[k]).abs().max()) for k in ("probs", "vad", "p_now", "p_future", "H")}
+                err["logits"] = float((f["logits"].cpu() - ref_fwd["logits"]).abs().max())
+                agree = float((o["probs"].argmax(-1).cpu() == ref["probs"].argmax(-1)).float().mean())
+                vad_same = float(((o["vad"].cpu() >= 0.5) == (ref["vad"] >= 0.5)).float().mean())
+                modes[prec] = {"value": B * CHUNK_SECONDS / (t_ms / 1e3), "unit": UNIT, "ms_per_step": t_ms,
+                               "steps": n_steps, "max_abs_err_vs_oracle": err, "argmax_agreement": agree,
+                               "vad_threshold_agreement": vad_same}
+            modes["_sample"] = "4 chunks of 20 s, turn-taking synthetic audio (seed 11), synthetic weights seed 0"
+            # the library-kernel bar: the oracle's torch ops (cuDNN conv/LSTM, cuBLAS, eager softmax) on this same GPU
+            try:
+                sd_dev = {k: v.to(dev) for k, v in sd.items()}
+                eb = min(B, 32)
+                with torch.no_grad():
+                    for name, tf32, ac in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
+                        torch.backends.cuda.matmul.allow_tf32 = tf32
+                        torch.backends.cudnn.allow_tf32 = tf32
+                        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                            O.probs(sd_dev, wav[:eb])
+                            torch.cuda.synchronize()
+                            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            a.record()
+                            O.probs(sd_dev, wav[:eb])
+                            b.record()
+                            torch.cuda.synchronize()
+                        modes.setdefault("eager_b200", {})[name] = {
+                            "value": eb * CHUNK_SECONDS / (a.elapsed_time(b) / 1e3), "unit": UNIT, "batch": eb}
+                modes["eager_b200"]["_what"] = ("oracle restatement (the reference's ATen ops) run with torch eager on "
+                                                "this GPU: the library-kernel bar, not the product path")
+                del sd_dev
+            except Exception as e:  # an out-of-memory eager run must not take the bench line with it
+                modes["eager_b200"] = {"unavailable": repr(e)[:200]}
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -401,7 +477,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16"}.get(precision, "f32"),
             "data": "synthetic", "config": workload_config(args, precision), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "modes": modes,
         }
         if local_cpus:
             line["config"]["host_affinity"] = f"rank bound to the {local_cpus} CPUs local to its GPU (NVML)"

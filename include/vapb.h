@@ -117,6 +117,27 @@ int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t
                float* vad, float* p_now, float* p_future, float* H, float* loss,
                uint8_t* argmax);
 
+/* vapb_probs with two extras for bulk inference:
+ *  - wav_fmt VAPB_WAV_PCM16: `wav` holds int16 PCM in the same (batch, 2, n_samples) layout (what a wav file holds;
+ *    the reference converts on the host, vap/audio.py:47). The fused encoder kernel reads it directly and scales by
+ *    1/32768 (exact), so the waveform crosses PCIe and HBM at half the bytes. 16-bit modes only, n_samples even,
+ *    4-byte aligned buffer; VAPB_E_UNSUPPORTED otherwise (vapb_pcm16_to_f32 converts for those cases).
+ *  - counters (nullable): device unsigned long long [258], ACCUMULATED by the heads kernel: [0,256) histogram of the
+ *    arg-max projection-window class over the call's frames, [256 + c] frames with vad[..., c] >= 0.5. */
+#define VAPB_WAV_F32 0
+#define VAPB_WAV_PCM16 1
+int vapb_probs_ex(VapbHandle* h, void* stream, const void* wav, int wav_fmt, int batch, int64_t n_samples,
+                  int mode, void* workspace, size_t workspace_bytes, int now_lo, int now_hi,
+                  int fut_lo, int fut_hi, float* logits, float* vad_logits, float* probs,
+                  float* vad, float* p_now, float* p_future, float* H, float* loss,
+                  uint8_t* argmax, unsigned long long* counters);
+
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: the bulk driver clears its per-step counters with it. */
+int vapb_memset_zero(void* stream, void* ptr, size_t bytes);
+
+/* out[i] = pcm[i] / 32768 for n int16 samples (device buffers), on `stream`. */
+int vapb_pcm16_to_f32(void* stream, const int16_t* pcm, int64_t n, float* out);
+
 /* ObjectiveVAP.get_probs(logits) (vap/objective.py:249-281) and the post-forward
  * half of VapGPT.probs on logits the caller already has: softmax, p_now,
  * p_future, entropy, argmax over `rows` frames of 256 logits (device fp32).

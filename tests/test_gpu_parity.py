@@ -213,11 +213,63 @@ def test_bulk_runner_pcm16_input_matches_float_input():
     pcm = (synth.make_waveform(3, n, 5, "turns") * 20000).round().clamp(-32768, 32767).to(torch.int16).pin_memory()
     ref = m.probs((pcm.float() / 32768.0).cuda())
     got = {}
-    r = BulkRunner(m, 4, n, pcm16=True, stats=False)
+    from voiceactivityprojection_b200.bulk import ALL_KEYS
+
+    r = BulkRunner(m, 4, n, stats=False, keys=ALL_KEYS)  # int16 host batches are recognised by their dtype
     r.run([pcm], sink=lambda i, b, o: got.update({k: v.clone() for k, v in o.items()}))
-    assert r.h2d_bytes == pcm.numel() * 2
+    assert r.h2d_bytes == pcm.numel() * 2 and r.pcm16 is True
     for k in ["probs", "vad", "p_now", "p_future", "H", "loss"]:
         assert torch.equal(got[k], ref[k].cpu()), k
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_pcm16_read_by_the_encoder_kernel_equals_converted_input(precision):
+    """16-bit modes: the fused conv0/conv1 kernel reads int16 PCM itself (vapb_probs_ex, VAPB_WAV_PCM16); the scaling by
+    2^-15 is exact, so every output is bit-identical to feeding x / 32768 as float32."""
+    from oracle import synth
+
+    m = _model(synth.make_state_dict(3, "LSTM", 1, 2.0), precision)
+    for n in (40000, 37392, 320000):
+        pcm = (synth.make_waveform(2, n, 5, "turns") * 20000).round().clamp(-32768, 32767).to(torch.int16).cuda()
+        ref = {k: v.clone() for k, v in m.probs(pcm.float() / 32768.0).items()}
+        got = m.probs(pcm)
+        for k in ref:
+            assert torch.equal(got[k], ref[k]), (n, k)
+    odd = (synth.make_waveform(1, 40001, 6, "turns") * 20000).round().to(torch.int16).cuda()  # odd length: converted
+    ref = {k: v.clone() for k, v in m.probs(odd.float() / 32768.0).items()}
+    got = m.probs(odd)
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+
+
+def test_bulk_runner_compact_outputs_and_kernel_counters():
+    """Default BulkRunner: compact outputs (vad, p_now, p_future, H, arg-max class) in one buffer, `probs` / `loss` not
+    even computed, histogram and active-frame counters taken by the heads kernel."""
+    from oracle import synth
+    from voiceactivityprojection_b200.bulk import COMPACT_KEYS, BulkRunner
+
+    m = _model(synth.make_state_dict(3, "LSTM", 1, 2.0), "fp16")
+    n = 40000
+    sizes = [4, 4, 3]
+    pcm = [(synth.make_waveform(b, n, 30 + i, "turns") * 20000).round().to(torch.int16).pin_memory()
+           for i, b in enumerate(sizes)]
+    direct = [m.probs(h.cuda(), out=m.alloc_outputs(h.shape[0], 125, "cuda", argmax=True)) for h in pcm]
+    direct = [{k: v.cpu().clone() for k, v in d.items()} for d in direct]
+    got = []
+    runner = BulkRunner(m, 4, n)
+    stats = runner.run(pcm, sink=lambda i, b, o: got.append({k: v.clone() for k, v in o.items()}))
+    assert runner.layout.bytes_per_chunk == 125 * (3 * 8 + 4 + 1)
+    assert runner.d2h_bytes == 2 * runner.layout.nbytes + 3 * 125 * 29 + 3 * 258 * 8
+    hist = torch.zeros(256, dtype=torch.int64)
+    vact = torch.zeros(2, dtype=torch.int64)
+    for o, d in zip(got, direct):
+        assert set(o) == set(COMPACT_KEYS)
+        for k in COMPACT_KEYS:
+            assert torch.equal(o[k], d[k]), k
+        hist += torch.bincount(d["argmax"].reshape(-1).long(), minlength=256)
+        vact += (d["vad"] >= 0.5).sum(dim=(0, 1))
+    assert stats.chunks == 11 and stats.frames == 11 * 125
+    assert torch.equal(stats.class_hist, hist) and torch.equal(stats.vad_active, vact)
 
 
 # tensor-core modes vs the reference's fp32 outputs (DESIGN.md section 6); fp16 operands carry 3 more mantissa bits

@@ -71,7 +71,8 @@ def test_bulk_runner_ingests_24k_pcm_and_matches_host_resampled_input():
     m = VapGPT(VapConfig(), precision="fp32").to("cuda")
     m.load_state_dict(synth.make_state_dict(7, "LSTM", 1, 2.0))
     n16 = 48000
-    runner = BulkRunner(m, batch=3, n_samples=n16, pcm16=True, input_rate=24000, stats=False)
+    runner = BulkRunner(m, batch=3, n_samples=n16, pcm16=True, input_rate=24000, stats=False,
+                        keys=("probs", "vad", "p_now", "p_future", "H"))
     assert runner.n_in == 72000
     rng = np.random.default_rng(4)
     pcm = torch.from_numpy((rng.standard_normal((5, 2, 72000)) * 1500).astype(np.int16))

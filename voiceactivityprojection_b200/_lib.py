@@ -26,6 +26,9 @@ SYMBOLS = {
     "vapb_forward": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _fp, _fp]),
     "vapb_forward_attention": (_i, [_vp, _vp, _fp, _i, _i64, _vp, _sz] + [_fp] * 5),
     "vapb_probs": (_i, [_vp, _vp, _fp, _i, _i64, _i, _vp, _sz, _i, _i, _i, _i] + [_fp] * 9),
+    "vapb_probs_ex": (_i, [_vp, _vp, _fp, _i, _i, _i64, _i, _vp, _sz, _i, _i, _i, _i] + [_fp] * 10),
+    "vapb_pcm16_to_f32": (_i, [_vp, _fp, _i64, _fp]),
+    "vapb_memset_zero": (_i, [_vp, _fp, _sz]),
     "vapb_probs_from_logits": (_i, [_vp, _vp, _fp, _i64, _i, _i, _i, _i] + [_fp] * 5),
     "vapb_get_stage": (_i, [_vp, _vp, C.c_char_p, _i, _i64, _i, _vp, _sz, _fp, _sz]),
     "vapb_profile_begin": (_i, [_vp]),

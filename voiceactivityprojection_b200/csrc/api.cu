@@ -454,11 +454,16 @@ int plan_all(const Model& m, int batch, int64_t n_samples, int mode, CallPlan* c
 }
 
 int run_forward(Model& m, cudaStream_t st, const float* wav, const Geometry& g, int mode, char* ws, float* logits,
-                float* vad_logits, float* vad_sig, cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr) {
+                float* vad_logits, float* vad_sig, cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr,
+                int wav_pcm16 = 0) {
   const float* comb = nullptr;
-  return mode == VAPB_MODE_FP32 ? forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb)
-                                : forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb,
-                                               mode == VAPB_MODE_FP16, conv_wait, conv_done);
+  if (mode == VAPB_MODE_FP32) {
+    if (wav_pcm16) { m.err = "int16 PCM input is read by the 16-bit modes only (vapb_pcm16_to_f32 converts for fp32)"; return VAPB_E_UNSUPPORTED; }
+    return forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb);
+  }
+  const int rc = forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, mode == VAPB_MODE_FP16, conv_wait,
+                              conv_done, wav_pcm16);
+  return rc == -4 ? VAPB_E_UNSUPPORTED : rc;
 }
 
 // Streams and events of the item-group pipeline (created on first use, owned by the handle).
@@ -484,6 +489,8 @@ struct ProbsOut {  // vapb_probs's optional outputs; every pointer addresses ite
   uint8_t* argmax;
   int now_lo, now_hi, fut_lo, fut_hi;
   bool want_probs;  // false: vapb_forward (logits + vad logits only)
+  unsigned long long* counters = nullptr;  // [258] accumulated: arg-max class histogram, active frames per channel
+  int wav_pcm16 = 0;                       // the waveform buffer holds int16 PCM
 };
 
 // Forward (+ the probs()/loss kernels) of items [b0, b0 + g.batch) on `st`.
@@ -495,14 +502,16 @@ int run_items(Model& m, cudaStream_t st, const float* wav, int b0, const Geometr
   float* vs = nullptr;
   if (o.want_probs) vs = o.vad ? o.vad + r0 * 2 : reinterpret_cast<float*>(ws_all + aux.vad_sig) + r0 * 2;
   float* lse = reinterpret_cast<float*>(ws_all + aux.lse) + r0;
-  const int rc = run_forward(m, st, wav + (long long)b0 * 2 * g.S, g, mode, ws_path, lg, at(o.vad_logits, r0 * 2), vs,
-                             conv_wait, conv_done);
+  const float* wav_b0 = o.wav_pcm16 ? reinterpret_cast<const float*>(reinterpret_cast<const int16_t*>(wav) + (long long)b0 * 2 * g.S)
+                                    : wav + (long long)b0 * 2 * g.S;
+  const int rc = run_forward(m, st, wav_b0, g, mode, ws_path, lg, at(o.vad_logits, r0 * 2), vs, conv_wait, conv_done,
+                             o.wav_pcm16);
   if (rc || !o.want_probs) return rc;
   const long long rows = (long long)g.batch * T;
   ProfScope ps(m, st, CAT_HEADS);
   m.launches += launch_probs(st, lg, rows, o.now_lo, o.now_hi, o.fut_lo, o.fut_hi, at(o.probs, r0 * kClasses),
                              at(o.p_now, r0 * 2), at(o.p_future, r0 * 2), at(o.H, r0), o.loss ? lse : nullptr,
-                             o.argmax ? o.argmax + r0 : nullptr);
+                             o.argmax ? o.argmax + r0 : nullptr, o.counters, o.counters ? vs : nullptr);
   if (o.loss) m.launches += launch_loss(st, lg, vs, lse, g.batch, (int)T, o.loss + (long long)b0 * (T - 100));
   return 0;
 }
@@ -602,7 +611,17 @@ int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t
                void* workspace, size_t workspace_bytes, int now_lo, int now_hi, int fut_lo, int fut_hi,
                float* logits, float* vad_logits, float* probs, float* vad, float* p_now, float* p_future, float* H,
                float* loss, uint8_t* argmax) {
+  return vapb_probs_ex(h, stream, wav, VAPB_WAV_F32, batch, n_samples, mode, workspace, workspace_bytes, now_lo, now_hi,
+                       fut_lo, fut_hi, logits, vad_logits, probs, vad, p_now, p_future, H, loss, argmax, nullptr);
+}
+
+int vapb_probs_ex(VapbHandle* h, void* stream, const void* wav_any, int wav_fmt, int batch, int64_t n_samples, int mode,
+                  void* workspace, size_t workspace_bytes, int now_lo, int now_hi, int fut_lo, int fut_hi,
+                  float* logits, float* vad_logits, float* probs, float* vad, float* p_now, float* p_future, float* H,
+                  float* loss, uint8_t* argmax, unsigned long long* counters) {
+  const float* wav = static_cast<const float*>(wav_any);
   if (!h || !wav || !workspace) return VAPB_E_INVALID;
+  if (wav_fmt != VAPB_WAV_F32 && wav_fmt != VAPB_WAV_PCM16) return VAPB_E_INVALID;
   Model& m = h->m;
   if (!m.finalized) return fail(m, VAPB_E_STATE, "vapb_finalize has not been called");
   if (now_lo < 0 || now_hi > 3 || now_lo > now_hi || fut_lo < 0 || fut_hi > 3 || fut_lo > fut_hi)
@@ -617,6 +636,8 @@ int vapb_probs(VapbHandle* h, void* stream, const float* wav, int batch, int64_t
                                        std::to_string(cp.g.T - 1) + " but size is 100)");
   CUDA_OK(m, cudaSetDevice(m.device));
   ProbsOut o{logits, vad_logits, probs, vad, p_now, p_future, H, loss, argmax, now_lo, now_hi, fut_lo, fut_hi, true};
+  o.counters = counters;
+  o.wav_pcm16 = wav_fmt == VAPB_WAV_PCM16;
   rc = run_call(m, (cudaStream_t)stream, wav, cp, mode, (char*)workspace, o);
   if (rc) return rc;
   CUDA_OK(m, cudaPeekAtLastError());
@@ -633,7 +654,7 @@ int vapb_probs_from_logits(VapbHandle* h, void* stream, const float* logits, int
   if (rows == 0) return VAPB_OK;
   CUDA_OK(m, cudaSetDevice(m.device));
   m.launches += launch_probs((cudaStream_t)stream, logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs, p_now,
-                             p_future, H, nullptr, argmax);
+                             p_future, H, nullptr, argmax, nullptr, nullptr);
   CUDA_OK(m, cudaPeekAtLastError());
   return VAPB_OK;
 }
@@ -787,7 +808,7 @@ int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_sampl
     } else {
       const int prev = g_fp16;
       g_fp16 = fp16 ? 1 : 0;
-      rc = launch_conv01((cudaStream_t)stream, wav, batch, n_samples, 0, 2 * batch, g.L[0], g.L[1], tab.data(), dev_tab,
+      rc = launch_conv01((cudaStream_t)stream, wav, 0, batch, n_samples, 0, 2 * batch, g.L[0], g.L[1], tab.data(), dev_tab,
                          cs, w1, bias1, g1, b1, out, out_seq_stride, out_pad_rows, n_sm, &msg, dbg_clocks);
       g_fp16 = prev;
       if (rc >= 0) {
@@ -966,6 +987,17 @@ int vapb_resample(VapbHandle* h, void* stream, const void* x, int x_fmt, int64_t
     if (h) h->m.err = err; else g_create_err = err;
   }
   return rc;
+}
+
+int vapb_memset_zero(void* stream, void* ptr, size_t bytes) {
+  if (!ptr) return VAPB_E_INVALID;
+  return cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream) == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
+}
+
+int vapb_pcm16_to_f32(void* stream, const int16_t* pcm, int64_t n, float* out) {
+  if (!pcm || !out || n < 0) return VAPB_E_INVALID;
+  if (n) launch_pcm16_to_f32((cudaStream_t)stream, pcm, n, out);
+  return cudaPeekAtLastError() == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
 }
 
 int vapb_launch_count(const VapbHandle* h, uint64_t* launches) {

@@ -105,8 +105,9 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
 int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);
 
 // conv0 + ChannelNorm + ReLU fused into conv1's operand producer (k_conv01.cu). host_tab / dev_tab: the folded conv0
-// table [12][256] = u (10 taps) | d | beta on the host (kernel parameters) and on the device. Returns launches or -1.
-int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq, long long L0,
+// table [12][256] = u (10 taps) | d | beta on the host (unused) and on the device. wav: fp32, or int16 PCM (wav_pcm16,
+// scaled by 1/32768 on the fly; needs an even n_samples). Returns launches or -1.
+int launch_conv01(cudaStream_t st, const void* wav, int wav_pcm16, int batch, long long n_samples, int seq0, int nseq, long long L0,
                   long long L1, const float* host_tab, const float* dev_tab, const Conv0Stats& cs, const void* w1,
                   const float* bias1, const float* g1, const float* b1, void* out, long long out_seq_stride,
                   int out_pad_rows, int n_sm, std::string* err, long long* dbg = nullptr);
@@ -155,9 +156,12 @@ int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int
 int launch_zero_shot(cudaStream_t st, const float* x, int is_probs, long long batch, int T, const float* va,
                      long long va_T, const uint32_t* sets /* host [10][8] */, float* p, float* p_bc, float* p_sil,
                      float* p_act);
+// counters (nullable): unsigned long long [258], ACCUMULATED: [0,256) histogram of the arg-max class over the rows,
+// [256 + c] frames of channel c with vad_sig >= 0.5 (vad_sig: (rows, 2) sigmoid outputs, needed with counters)
 int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
                  int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse,
-                 uint8_t* argmax);
+                 uint8_t* argmax, unsigned long long* counters, const float* vad_sig);
+int launch_pcm16_to_f32(cudaStream_t st, const int16_t* pcm, long long n, float* out);  // out[i] = pcm[i] / 32768
 
 int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, const float* lse, int batch,
                 int T, float* loss);

@@ -260,9 +260,15 @@ void bf16_release(Model& m) {
 
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g) { return make_plan(m, g).bytes; }
 
-int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
+int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry& g, char* ws, float* logits,
                  float* vad_logits, float* vad_sig, const float**, int fp16, cudaEvent_t conv_wait,
-                 cudaEvent_t conv_done) {
+                 cudaEvent_t conv_done, int wav_pcm16) {
+  // wav_pcm16: the buffer holds int16 PCM (same (B, 2, S) layout); only the fused conv0 -> conv1 kernel reads it
+  if (wav_pcm16 && (!m.conv01 || (g.S & 1))) {
+    m.err = "int16 PCM input needs the fused conv0/conv1 path (VAPB_CONV01=1) and an even n_samples";
+    return -4;
+  }
+  const float* wav = wav_f32;
   const State16& s = static_cast<const State16*>(m.bf16_state)[fp16 ? 1 : 0];
   Fp16Scope fmt_scope(fp16 ? 1 : 0);
   const Plan16 p = make_plan(m, g);
@@ -295,7 +301,7 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
       // conv0 + conv1 in one kernel (k_conv01.cu): the first layer's 512 B per frame never reach HBM
       ProfScope ps(m, st, CAT_CONV_GEMM);
       std::string err;
-      const int k = launch_conv01(st, wav, g.batch, g.S, s0, n, g.L[0], g.L[1], s.c0_tab_host.data(), s.c0_tab, s.c0_stats,
+      const int k = launch_conv01(st, wav, wav_pcm16, g.batch, g.S, s0, n, g.L[0], g.L[1], s.c0_tab_host.data(), s.c0_tab, s.c0_stats,
                                   s.conv_w[1], w.conv_b[1], w.conv_g[1], w.conv_be[1], H(p.act[1]), p.lpad[1] * kDim,
                                   (int)p.lo[1], m.n_sm, &err);
       if (k < 0) { m.err = err; return -3; }

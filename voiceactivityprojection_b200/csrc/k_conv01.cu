@@ -81,7 +81,7 @@ struct alignas(64) F01Params {
   CUtensorMap tma_w;   // (2048, 256) 16-bit, box (64, 128), SW128
   CUtensorMap tma_o;   // store_mode 0: (256, 8, 16, tiles, nseq) box (32, 8, 4, 1, 1); 1: (256, 16, rows/16, nseq) box (32, 1, 8, 1); SW64
   Conv0Stats cs;
-  const float* wav;
+  const void* wav;     // (batch, 2, n_samples) fp32, or int16 PCM (scaled by 1/32768 when read; needs n_samples even)
   const float* wg;     // folded conv0 table [12][256] in global memory: k < 10 taps u_k, k = 10 bias d, k = 11 norm bias beta
   const float *bias, *g1, *b1;
   long long n_samples;
@@ -353,7 +353,7 @@ __device__ __noinline__ void conv01_epilogue(const F01Params& p, const F01EpiArg
   }
 }
 
-template <int FP16>
+template <int FP16, int PCM16>
 __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_constant__ F01Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -371,6 +371,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
   const uint32_t tmem_slot = bar_base + 8u * 20;
   F01Vecs& ev = *reinterpret_cast<F01Vecs*>(smem_gen + F_OFF_VEC);
   float* xs = reinterpret_cast<float*>(smem_gen + F_OFF_XSB);
+  // sample i of the window in buffer buf. fp32: word i + i / 320 (the skew spreads the lanes' 20-sample stride over the
+  // banks). int16 PCM: the window is loaded as aligned sample pairs starting one sample early, element i + 1 at
+  // half-word (i + 1) + 2 ((i + 1) / 320); the scaling by 2^-15 is exact.
+  auto win = [&](int buf, int i) -> float {
+    if (PCM16) {
+      const int e = i + 1;
+      return (float)reinterpret_cast<const int16_t*>(xs + buf * F_XS)[e + 2 * (e / 320)] * (1.0f / 32768.0f);
+    }
+    return xs[buf * F_XS + i + i / 320];
+  };
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs, owns the cross-CTA barriers)
 
@@ -545,11 +555,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
       // must not wait for it - they would be waiting for stages that only they can fill).
       mbar_wait(win_full_bar, (uint32_t)(it & 1));
       float xall[25];
-      {
-        const float* xw = xs + (it & 1) * F_XS;
 #pragma unroll
-        for (int k = 0; k < 25; ++k) xall[k] = xw[(2560 + k) + (2560 + k) / 320];
-      }
+      for (int k = 0; k < 25; ++k) xall[k] = win(it & 1, 2560 + k);
       __syncwarp();
       if (lane == 0) mbar_arrive(win_free_bar);
 #pragma unroll
@@ -603,13 +610,25 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
       int lseq, t0;
       tile_of(pt, &lseq, &t0);
       const int seq = p.seq0 + lseq;  // channel-major sequence id: c * batch + item
-      const float* x = p.wav + ((long long)(seq % p.batch) * 2 + seq / p.batch) * p.n_samples;
+      const long long row = ((long long)(seq % p.batch) * 2 + seq / p.batch) * p.n_samples;
       const long long sbase = 20LL * t0 - 13;
       const uint32_t dst = smem_base + F_OFF_XSB + (uint32_t)buf * (F_XS * 4);
-      for (int i = r; i < F_WIN; i += F_PROD_WARPS * 32) {
-        const long long s = sbase + i;
-        const bool ok = s >= 0 && s < p.n_samples;
-        cp_async4(dst + 4u * (uint32_t)(i + i / 320), ok ? x + s : x, ok ? 4u : 0u);
+      if (PCM16) {
+        // aligned pairs (s, s + 1), s even, from sbase - 1; signal start and end are even, so a pair is in or out as a whole
+        const int16_t* x = static_cast<const int16_t*>(p.wav) + row;
+        for (int q = r; q < (F_WIN + 2) / 2; q += F_PROD_WARPS * 32) {
+          const long long s = sbase - 1 + 2 * q;
+          const bool ok = s >= 0 && s < p.n_samples;
+          cp_async4(dst + 2u * (uint32_t)(2 * q + 2 * ((2 * q) / 320)), reinterpret_cast<const float*>(ok ? x + s : x),
+                    ok ? 4u : 0u);
+        }
+      } else {
+        const float* x = static_cast<const float*>(p.wav) + row;
+        for (int i = r; i < F_WIN; i += F_PROD_WARPS * 32) {
+          const long long s = sbase + i;
+          const bool ok = s >= 0 && s < p.n_samples;
+          cp_async4(dst + 4u * (uint32_t)(i + i / 320), ok ? x + s : x, ok ? 4u : 0u);
+        }
       }
       cp_async_commit();
     };
@@ -629,13 +648,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
     // k 16..31. Zero padding frames of conv1 (f < 0, f >= L0) give an all-zero row. The caller has seen the previous
     // conv0 GEMM complete (d0_full), so the single operand buffer is free.
     auto make_x = [&](int t0, int buf, int j) {
-      const float* xw = xs + buf * F_XS;
       const int f = 4 * (t0 + dt) - 2 + j;
       const bool valid = f >= 0 && f < p.L0;
       const int i0 = 20 * dt + 5 * j;
       float xv[10];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) xv[k] = xw[(i0 + k) + (i0 + k) / 320];
+      for (int k = 0; k < 10; ++k) xv[k] = win(buf, i0 + k);
       const float rstd = valid ? frame_rstd(ev, xv) : 0.f;
       uint32_t hi[6], lo[6];
 #pragma unroll
@@ -774,12 +792,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
 // g1 / b1: conv1 bias and ChannelNorm affine (device). out: row t of sequence s at out + s * out_seq_stride +
 // (out_pad_rows + t) * 256; the kernel writes whole 128-row tiles (zeros past L1), so every sequence needs
 // out_pad_rows + roundup(L1, 128) rows.
-int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq, long long L0,
+int launch_conv01(cudaStream_t st, const void* wav, int wav_pcm16, int batch, long long n_samples, int seq0, int nseq, long long L0,
                   long long L1, const float* host_tab /*[12][256]*/, const float* dev_tab, const Conv0Stats& cs,
                   const void* w1, const float* bias1, const float* g1, const float* b1, void* out,
                   long long out_seq_stride, int out_pad_rows, int n_sm, std::string* err, long long* dbg) {
   F01Params p{};
   p.dbg = dbg;
+  if (wav_pcm16 && ((n_samples & 1) || (reinterpret_cast<uintptr_t>(wav) & 3))) {
+    if (err) *err = "conv01: int16 PCM input needs an even n_samples and a 4-byte aligned buffer";
+    return -1;
+  }
   {
     const uint64_t dims[2] = {(uint64_t)(8 * kDim), (uint64_t)kDim};
     const uint64_t strides[1] = {(uint64_t)(8 * kDim)};
@@ -819,8 +841,10 @@ int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samp
   cudaGetDevice(&cur_dev);
   bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
-    if (cudaFuncSetAttribute(conv01_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(conv01_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv01_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(conv01_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(conv01_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(conv01_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM) != cudaSuccess) {
       if (err) *err = "conv01: cannot reserve shared memory";
       return -1;
     }
@@ -841,7 +865,9 @@ int launch_conv01(cudaStream_t st, const float* wav, int batch, long long n_samp
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t ce = g_fp16 ? cudaLaunchKernelEx(&cfg, conv01_kernel<1>, p) : cudaLaunchKernelEx(&cfg, conv01_kernel<0>, p);
+  void (*kern)(F01Params) = wav_pcm16 ? (g_fp16 ? conv01_kernel<1, 1> : conv01_kernel<0, 1>)
+                                       : (g_fp16 ? conv01_kernel<1, 0> : conv01_kernel<0, 0>);
+  const cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, p);
   if (ce != cudaSuccess) {
     if (err) *err = std::string("conv01 launch: ") + cudaGetErrorString(ce);
     return -1;

@@ -89,10 +89,12 @@ __device__ __forceinline__ float exp_neg(float d) {
 // One warp handles PR frames at a time (independent shuffle chains interleave); lane owns classes
 // lane*4..+3 and 128+lane*4..+3, whose codebook bit counts are fixed per lane and computed once.
 constexpr int PR = 4;
-__global__ void __launch_bounds__(256)
-probs_kernel(const float* __restrict__ logits, long long rows, int now_lo, int now_hi, int fut_lo, int fut_hi,
-             float* __restrict__ probs, float* __restrict__ p_now, float* __restrict__ p_future,
-             float* __restrict__ H, float* __restrict__ lse, uint8_t* __restrict__ argmax) {
+// cnt (nullable): the block's shared-memory counters [258] (arg-max class histogram, active frames per channel)
+__device__ __forceinline__ void probs_rows(const float* __restrict__ logits, long long rows, int now_lo, int now_hi,
+                                           int fut_lo, int fut_hi, float* __restrict__ probs, float* __restrict__ p_now,
+                                           float* __restrict__ p_future, float* __restrict__ H, float* __restrict__ lse,
+                                           uint8_t* __restrict__ argmax, unsigned int* cnt,
+                                           const float* __restrict__ vad_sig) {
   const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * PR;
   const int lane = threadIdx.x & 31;
   if (row0 >= rows) return;
@@ -196,14 +198,68 @@ probs_kernel(const float* __restrict__ logits, long long rows, int now_lo, int n
       }
       if (lse) lse[row] = mx[r] + logf(s[r]);
       if (argmax) argmax[row] = (uint8_t)bidx[r];
+      if (cnt) {
+        atomicAdd(&cnt[bidx[r]], 1u);
+        const float2 v = *reinterpret_cast<const float2*>(vad_sig + row * 2);
+        if (v.x >= 0.5f) atomicAdd(&cnt[256], 1u);
+        if (v.y >= 0.5f) atomicAdd(&cnt[257], 1u);
+      }
     }
   }
 }
 
+// The bulk driver's counters (class histogram and active-frame counts for the all-reduce) are
+// taken here, where the arg-max is already in a register: per-block shared-memory counts, one global atomic per
+// non-empty bin and block.
+__global__ void __launch_bounds__(256)
+probs_kernel(const float* __restrict__ logits, long long rows, int now_lo, int now_hi, int fut_lo, int fut_hi,
+             float* __restrict__ probs, float* __restrict__ p_now, float* __restrict__ p_future,
+             float* __restrict__ H, float* __restrict__ lse, uint8_t* __restrict__ argmax,
+             unsigned long long* __restrict__ counters, const float* __restrict__ vad_sig) {
+  __shared__ unsigned int cnt[258];
+  if (counters) {
+    cnt[threadIdx.x] = 0u;
+    if (threadIdx.x < 2) cnt[256 + threadIdx.x] = 0u;
+    __syncthreads();
+  }
+  probs_rows(logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs, p_now, p_future, H, lse, argmax,
+             counters ? cnt : nullptr, vad_sig);
+  if (counters) {
+    __syncthreads();
+    if (cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+    if (threadIdx.x < 2 && cnt[256 + threadIdx.x])
+      atomicAdd(&counters[256 + threadIdx.x], (unsigned long long)cnt[256 + threadIdx.x]);
+  }
+}
+
 int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_lo, int now_hi, int fut_lo,
-                 int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse, uint8_t* argmax) {
+                 int fut_hi, float* probs, float* p_now, float* p_future, float* H, float* lse, uint8_t* argmax,
+                 unsigned long long* counters, const float* vad_sig) {
   probs_kernel<<<(unsigned)((rows + 8 * PR - 1) / (8 * PR)), 256, 0, st>>>(logits, rows, now_lo, now_hi, fut_lo, fut_hi, probs,
-                                                           p_now, p_future, H, lse, argmax);
+                                                           p_now, p_future, H, lse, argmax, counters, vad_sig);
+  return 1;
+}
+
+// int16 PCM -> float32 in [-1, 1): what torchaudio.load's normalisation does on the host (vap/audio.py:47), for the
+// callers that cannot hand the PCM to the fused encoder kernel directly (fp32 mode, odd lengths)
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const int16_t* __restrict__ pcm, long long n, float* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(pcm + i) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out + i) & 15) == 0)) {
+    const uint4 v = *reinterpret_cast<const uint4*>(pcm + i);
+    const int16_t* s = reinterpret_cast<const int16_t*>(&v);
+    float4 a, b;
+    a.x = s[0] * (1.0f / 32768.0f); a.y = s[1] * (1.0f / 32768.0f); a.z = s[2] * (1.0f / 32768.0f); a.w = s[3] * (1.0f / 32768.0f);
+    b.x = s[4] * (1.0f / 32768.0f); b.y = s[5] * (1.0f / 32768.0f); b.z = s[6] * (1.0f / 32768.0f); b.w = s[7] * (1.0f / 32768.0f);
+    *reinterpret_cast<float4*>(out + i) = a;
+    *reinterpret_cast<float4*>(out + i + 4) = b;
+  } else {
+    for (long long k = i; k < n && k < i + 8; ++k) out[k] = pcm[k] * (1.0f / 32768.0f);
+  }
+}
+
+int launch_pcm16_to_f32(cudaStream_t st, const int16_t* pcm, long long n, float* out) {
+  const long long threads = (n + 7) / 8;
+  pcm16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(pcm, n, out);
   return 1;
 }
 

@@ -160,7 +160,7 @@ void bf16_release(Model& m);
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g);
 int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
                  float* vad_logits, float* vad_sig, const float** comb_out, int fp16,
-                 cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr);
+                 cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr, int wav_pcm16 = 0);
 int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
 }  // namespace vapb

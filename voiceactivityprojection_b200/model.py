@@ -194,6 +194,18 @@ class VapGPT(nn.Module):
             lib.vapb_destroy(h)
             raise
         self._handle, self._handle_device = h, dev
+        # nn.Module.load_state_dict(strict=True) would refuse a checkpoint whose depth differs from the module built
+        # from `conf`; the library infers the depth from the keys, so the comparison is made here (the
+        # attention-map buffers of forward(attention=True) are sized from conf)
+        d = self.describe()
+        if (d["channel_layers"], d["cross_layers"], d["num_heads"]) != (
+                self.conf.channel_layers, self.conf.cross_layers, self.conf.num_heads):
+            self._release()
+            raise RuntimeError(
+                "Error(s) in loading state_dict for VapGPT: the state dict holds "
+                f"{d['channel_layers']} ar_channel layer(s), {d['cross_layers']} ar layer(s) and {d['num_heads']} heads "
+                f"but conf asks for channel_layers={self.conf.channel_layers}, cross_layers={self.conf.cross_layers}, "
+                f"num_heads={self.conf.num_heads}")
         return h
 
     def describe(self) -> Dict[str, int]:
@@ -210,7 +222,12 @@ class VapGPT(nn.Module):
         return n.value
 
     # ------------------------------------------------------------------ helpers
-    def _check_input(self, waveform: Tensor) -> Tensor:
+    @property
+    def device(self) -> torch.device:
+        """The device the weights live on (the reference's callers read `model.device` / next(parameters()).device)."""
+        return self._device
+
+    def _check_input(self, waveform: Tensor, allow_pcm16: bool = False) -> Tensor:
         assert waveform.ndim == 3 and waveform.shape[1] == 2, (
             f"audio VAP ENCODER: {tuple(waveform.shape)} != (B, 2, n_samples)"
         )
@@ -218,7 +235,24 @@ class VapGPT(nn.Module):
             raise RuntimeError("waveform must be a CUDA tensor (no CPU fallback); use probs_host() for host buffers")
         if self._device.type != "cuda":
             self._device = waveform.device
+        dev = self._device if self._device.index is not None else torch.device("cuda", torch.cuda.current_device())
+        wdev = waveform.device if waveform.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+        if wdev != dev:
+            # nn.Module semantics: inputs and parameters must share a device (the library's workspace, weights and
+            # streams all belong to the model's device)
+            raise RuntimeError(f"Expected all tensors to be on the same device, but found {wdev} (waveform) and "
+                               f"{dev} (model)")
+        if allow_pcm16 and waveform.dtype == torch.int16:
+            return waveform.contiguous()
         return waveform.to(torch.float32).contiguous()
+
+    def _pcm16_to_f32(self, pcm: Tensor) -> Tensor:
+        """int16 PCM -> float32 / 32768 on the device (vapb_pcm16_to_f32), for the paths that cannot read PCM directly."""
+        lib = _lib.load()
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        st = torch.cuda.current_stream(pcm.device).cuda_stream
+        _lib.check(lib, None, lib.vapb_pcm16_to_f32(st, pcm.data_ptr(), pcm.numel(), out.data_ptr()))
+        return out
 
     def _workspace(self, batch: int, n_samples: int, mode: int):
         lib, h = _lib.load(), self._ensure_handle()
@@ -286,30 +320,47 @@ class VapGPT(nn.Module):
     @torch.no_grad()
     def probs(self, waveform: Tensor, vad: Optional[Tensor] = None, now_lims: List[int] = [0, 1],
               future_lims: List[int] = [2, 3], precision: Optional[str] = None,
-              out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+              out: Optional[Dict[str, Tensor]] = None, counters: Optional[Tensor] = None,
+              want_probs: bool = True, want_loss: bool = True) -> Dict[str, Tensor]:
         """vap/model.py:180-225. Keys: probs, vad, p_now, p_future, H, loss — `loss`
         is always present and needs T > 100, exactly like the reference (its `vad`
-        argument is overwritten by the model's own sigmoid)."""
-        wav = self._check_input(waveform)
+        argument is overwritten by the model's own sigmoid).
+
+        Extras of the bulk path (vapb_probs_ex): `waveform` may be int16 PCM on the device (read by the fused encoder
+        kernel in the 16-bit modes, converted by a library kernel otherwise); `counters` (device int64 [258]) is
+        ACCUMULATED with the arg-max class histogram and the active-frame counts; want_probs / want_loss = False skip
+        those two outputs (the bulk driver's compact set does not carry them)."""
+        wav = self._check_input(waveform, allow_pcm16=True)
         B, _, S = wav.shape
         lib, h = _lib.load(), self._ensure_handle()
         _, T = _lib.frames(S)
-        if T <= 100:
+        if T <= 100 and want_loss:
             raise RuntimeError(
                 f"maximum size for tensor at dimension 1 is {T - 1} but size is 100"
             )
         mode = self._mode(precision)
+        fmt = 0
+        if wav.dtype == torch.int16:
+            if mode != _lib.MODE_FP32 and S % 2 == 0 and wav.data_ptr() % 4 == 0 and os.environ.get("VAPB_CONV01", "1") != "0":
+                fmt = 1
+            else:
+                wav = self._pcm16_to_f32(wav)
         ws = self._workspace(B, S, mode)
         dev = wav.device
         if out is None:
             out = self.alloc_outputs(B, T, dev)
+        if counters is not None and (counters.dtype != torch.int64 or counters.numel() < 258 or counters.device != dev
+                                     or not counters.is_contiguous()):
+            raise ValueError("counters must be a contiguous int64 tensor of 258 elements on the waveform's device")
+        ptr = lambda k, want=True: out[k].data_ptr() if (want and k in out) else None
         st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib, h, lib.vapb_probs(
-            h, st, wav.data_ptr(), B, S, mode, ws.data_ptr(), ws.numel(),
-            now_lims[0], now_lims[-1], future_lims[0], future_lims[1],
-            None, None, out["probs"].data_ptr(), out["vad"].data_ptr(), out["p_now"].data_ptr(),
-            out["p_future"].data_ptr(), out["H"].data_ptr(), out["loss"].data_ptr(),
-            out["argmax"].data_ptr() if "argmax" in out else None))
+        with torch.cuda.device(dev):
+            _lib.check(lib, h, lib.vapb_probs_ex(
+                h, st, wav.data_ptr(), fmt, B, S, mode, ws.data_ptr(), ws.numel(),
+                now_lims[0], now_lims[-1], future_lims[0], future_lims[1],
+                None, None, ptr("probs", want_probs), out["vad"].data_ptr(), out["p_now"].data_ptr(),
+                out["p_future"].data_ptr(), out["H"].data_ptr(), ptr("loss", want_loss), ptr("argmax"),
+                None if counters is None else counters.data_ptr()))
         return out
 
     @staticmethod
