@@ -189,6 +189,13 @@ int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64
                         int nseq, int rows_per_seq, int K, const float* bias, int norm1, const float* g1,
                         const float* b1, int act, void* out_bf16, char* err, int err_len);
 
+/* Unit-test hook for the stand-alone conv0 + ChannelNorm + ReLU kernel (csrc/k_conv0_tc.cu, the VAPB_CONV01=0 path;
+ * vap/encoder_components.py:83-84,99). Operands as vapb_debug_conv01; out: device 16-bit, dense (2*batch, L0, 256),
+ * sequences in channel-major order. */
+int vapb_debug_conv0_tc(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
+                        const float* conv0_b, const float* norm0_g, const float* norm0_b, void* out, int fp16,
+                        char* err, int err_len);
+
 /* Unit-test hook for the fused conv0 -> conv1 kernel (csrc/k_conv01.cu; vap/encoder_components.py:83-86,99-100).
  * wav: device fp32 (batch, 2, n_samples); every channel of every item is one sequence (channel-major order
  * c*batch + item). conv0_w (256,1,10), conv0_b, norm0_g, norm0_b (256): HOST fp32 parameters of conv0 and its

@@ -429,3 +429,34 @@ def test_conv01_fused_matches_torch(B, S, fp16):
     assert (tail == 0).all()                      # rows past the sequence end are the next layer's zero padding
     assert torch.isnan(out[:, :pad].float()).all()  # rows before the sequence are not touched
     assert torch.isnan(out[:, pad + (L1 + 127) // 128 * 128:].float()).all()
+
+
+@pytest.mark.parametrize("B,S,fp16", [(1, 2000, 0), (2, 37392, 1), (3, 320000, 0)])
+def test_conv0_tc_standalone_matches_torch(B, S, fp16):
+    """The stand-alone tf32 conv0 + ChannelNorm + ReLU kernel (k_conv0_tc.cu, used when VAPB_CONV01=0) against torch fp32."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(B + S)
+    dt16 = torch.float16 if fp16 else torch.bfloat16
+    wav = torch.randn((B, 2, S), device="cuda", generator=g) * 0.05
+    w0 = torch.randn((256, 1, 10), device="cuda", generator=g) * 0.3
+    b0 = torch.randn(256, device="cuda", generator=g) * 0.1
+    g0 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    be0 = 0.1 * torch.randn(256, device="cuda", generator=g)
+    L0 = (S + 6 - 10) // 5 + 1
+    out = torch.full((2 * B, L0, 256), float("nan"), device="cuda", dtype=dt16)
+    err = C.create_string_buffer(512)
+    host = [t.detach().cpu().contiguous() for t in (w0, b0, g0, be0)]
+    rc = lib.vapb_debug_conv0_tc(torch.cuda.current_stream().cuda_stream, wav.data_ptr(), B, S, host[0].data_ptr(),
+                                 host[1].data_ptr(), host[2].data_ptr(), host[3].data_ptr(), out.data_ptr(), int(fp16),
+                                 err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    x = wav.transpose(0, 1).reshape(2 * B, 1, S)
+    ref = F.relu(_norm(F.conv1d(x, w0, b0, stride=5, padding=3).transpose(1, 2), 1, g0, be0))
+    assert torch.isfinite(out.float()).all()
+    d = (out.float() - ref).abs()
+    # tf32 operands (2^-11) and a 16-bit result: absolute error scales with the output magnitude (|ref| up to ~6)
+    assert d.max().item() <= (6e-3 if fp16 else 4e-2), d.max().item()
+    assert d.mean().item() <= (5e-4 if fp16 else 3e-3)

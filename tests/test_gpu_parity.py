@@ -596,3 +596,63 @@ def test_forward_attention_maps_batch_and_tile_edges_vs_oracle(batch, n_samples)
         assert torch.isfinite(a).all()
         assert (a - ref[k]).abs().max().item() <= 1e-5, k
     assert (out["logits"].cpu() - ref["logits"]).abs().max().item() <= 2e-4
+
+
+def test_vap_extractor_on_the_cuda_model_matches_oracle_windows():
+    """VapExtractor (vap/extraction.py:99-270) driving the REAL CUDA model: windows batched through vapb_probs, stitched
+    on the device, against the same extractor driving the CPU oracle window by window (ADVICE/VERDICT r1: the extractor
+    had only been run with a model double)."""
+    from oracle import synth, vap_oracle as O
+    from voiceactivityprojection_b200.extraction import VapExtractor, get_minimal_output_json
+
+    sd = synth.make_state_dict(5, "LSTM", 1, 2.0)
+    m = _model(sd, "fp32")
+    assert m.device.type == "cuda"
+    wav = synth.make_waveform(1, int(47.3 * 16000), 9, "turns")
+
+    class OracleModel:
+        sample_rate, frame_hz = 16000, 50
+
+        def probs(self, w, **kw):
+            return O.probs(sd, w.cpu())
+
+    ex = VapExtractor(model=m, context_time=10, step_time=5, max_batch=4)
+    assert str(ex.device).startswith("cuda")
+    got = ex.step_extraction(wav)
+    ref_ex = VapExtractor(model=OracleModel(), context_time=10, step_time=5, max_batch=4)
+    ref_ex.device = "cpu"
+    ref = ref_ex.step_extraction(wav)
+    n = int(47.3 * 50)
+    assert got["p_now"].shape == (1, n, 2) and got["probs"].shape == (1, n, 256)
+    for k in ("probs", "vad", "p_now", "p_future"):
+        assert (got[k] - ref[k]).abs().max().item() <= 1e-5, k
+    assert torch.equal(got["probs"].argmax(-1), ref["probs"].argmax(-1))
+    assert torch.equal(got["vad"] >= 0.5, ref["vad"] >= 0.5)
+    short = ex.extract(wav[..., : 16000 * 12])  # <= 160 s: one probs() call (vap/extraction.py:262-270)
+    ref_short = O.probs(sd, wav[..., : 16000 * 12])
+    assert (short["p_now"] - ref_short["p_now"]).abs().max().item() <= 1e-5
+    assert list(get_minimal_output_json(short).keys()) == ["p_now", "p_future", "model_vad0", "model_vad1", "H", "loss"]
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_full_size_batch_sampled_items_match_oracle(precision):
+    """BASELINE configs[1] at its full size (B = 256 x 20 s): items sampled across the batch are compared with the CPU
+    oracle run on those items alone (the oracle finishes three chunks in seconds), in addition to the
+    item-independence check below. fp16 tolerances as TC_TOL; fp32 1e-5 with exact decisions."""
+    from oracle import synth, vap_oracle as O
+
+    sd = synth.make_state_dict(0, "LSTM", 1, 2.0)
+    m = _model(sd, precision)
+    B, S = 256, 320000
+    wav = synth.make_waveform(B, S, 21, "turns")
+    out = m.probs(wav.cuda())
+    pick = [0, 101, 255]
+    ref = O.probs(sd, wav[pick])
+    tol = dict(probs=1e-5, vad=1e-5, p_now=1e-5, p_future=1e-5) if precision == "fp32" else \
+        {k: TC_TOL["fp16"][k] for k in ("probs", "vad", "p_now", "p_future")}
+    for k, t in tol.items():
+        assert (out[k][pick].cpu() - ref[k]).abs().max().item() <= t, k
+    agree = (out["probs"][pick].argmax(-1).cpu() == ref["probs"].argmax(-1)).float().mean().item()
+    assert agree == 1.0 if precision == "fp32" else agree >= 0.99
+    if precision == "fp32":
+        assert torch.equal(out["vad"][pick].cpu() >= 0.5, ref["vad"] >= 0.5)

@@ -42,7 +42,7 @@ def main():
 
         out = sys.argv[sys.argv.index("--traffic-json") + 1]
         steps = int(sys.argv[sys.argv.index("--steps") + 1])
-        fam_of = {"conv0_tc_kernel": "conv0", "gemm_2sm_kernel": "conv_gemm", "rnn_tc_kernel": "rnn",
+        fam_of = {"conv0_tc_kernel": "conv0", "conv01_kernel": "conv_gemm", "gemm_2sm_kernel": "conv_gemm", "rnn_tc_kernel": "rnn",
                   "attention_tc_kernel": "attention", "gemm_lin_kernel": "linear_gemm", "ffn_fused_kernel": "linear_gemm",
                   "probs_kernel": "heads", "loss_kernel": "heads", "vad_head_blocked_kernel": "heads"}
         fams, after_rnn = {}, False
@@ -59,8 +59,12 @@ def main():
         for f in fams.values():
             f["launches"] = f["launches"] // steps
             f["ncu_ms"] = round(f["ncu_ms"], 3)
+        fams["total"] = {"dram_bytes_per_step": sum(f["dram_bytes_per_step"] for f in fams.values()),
+                         "launches": sum(f["launches"] for f in fams.values()),
+                         "ncu_ms": round(sum(f["ncu_ms"] for f in fams.values()), 3)}
+        tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else "B=256, 1 GPU"
         fams["_source"] = (f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over {steps} "
-                           f"step(s) of bench.py (bf16, B=256, 1 GPU; {path}, first {skip} launches skipped)")
+                           f"step(s) of bench.py ({tag}; {path}, first {skip} launches skipped)")
         json.dump(fams, open(out, "w"), indent=1)
         print(json.dumps(fams, indent=1))
         return

@@ -36,6 +36,7 @@ SYMBOLS = {
     "vapb_debug_gemm_tc": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, _i,
                                 _fp, _fp, _i, _fp, _fp, _fp, C.c_char_p, _i]),
     "vapb_debug_gemm_2sm": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, C.c_char_p, _i]),
+    "vapb_debug_conv0_tc": (_i, [_vp, _fp, _i, _i64, _vp, _vp, _vp, _vp, _fp, _i, C.c_char_p, _i]),
     "vapb_debug_conv01": (_i, [_vp, _fp, _i, _i64, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i64, _i, _i, C.c_char_p, _i, _fp]),
     "vapb_debug_gemm_lin": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, _i,
                                  _fp, _i, _fp, _i, _fp, _fp, _fp, C.c_char_p, _i]),

@@ -783,6 +783,46 @@ int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64
   return VAPB_OK;
 }
 
+int vapb_debug_conv0_tc(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
+                        const float* conv0_b, const float* norm0_g, const float* norm0_b, void* out, int fp16, char* err,
+                        int err_len) {
+  Geometry g;
+  std::string msg;
+  int rc = -1;
+  float* dev_tab = nullptr;
+  if (!wav || !conv0_w || !conv0_b || !norm0_g || !norm0_b || !out || batch < 1 || make_geometry(batch, n_samples, &g) != 0) {
+    msg = "conv0_tc: invalid argument";
+  } else {
+    std::vector<float> tab(12 * kDim);
+    Conv0Stats cs;
+    conv0_v2_fold(conv0_w, conv0_b, norm0_g, tab.data(), tab.data() + 10 * kDim, &cs);
+    memcpy(tab.data() + 11 * kDim, norm0_b, kDim * sizeof(float));
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaMalloc(&dev_tab, tab.size() * 4) != cudaSuccess ||
+        cudaMemcpy(dev_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      msg = "conv0_tc: cannot stage the conv0 table";
+    } else {
+      const int prev = g_fp16;
+      g_fp16 = fp16 ? 1 : 0;
+      rc = launch_conv0_tc((cudaStream_t)stream, wav, batch, n_samples, 0, 2 * batch, g.L[0], dev_tab, dev_tab + 10 * kDim,
+                           dev_tab + 11 * kDim, cs, reinterpret_cast<__nv_bfloat16*>(out), g.L[0] * kDim, 0, n_sm, &msg);
+      g_fp16 = prev;
+      if (rc >= 0) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+      }
+    }
+  }
+  if (dev_tab) cudaFree(dev_tab);
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
 int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_samples, const float* conv0_w,
                       const float* conv0_b, const float* norm0_g, const float* norm0_b, const void* w1,
                       const float* bias1, const float* g1, const float* b1, void* out, int64_t out_seq_stride,
