@@ -755,13 +755,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) conv01_kernel(const __grid_const
             } else if (pt + n_clusters < num_pair_tiles) {
               int lseq1, t1;
               tile_of(pt + n_clusters, &lseq1, &t1);
+              // Window hand-over. One thread waits for the extra-row warp to have left this tile's window (it read it
+              // at its tile start) BEFORE the block barrier, and only after the barrier is the next window published:
+              // the extra-row warp can then never complete a second phase of win_free while a producer still waits
+              // for the first (a parity wait cannot tell phase n from phase n + 2; with every producer waiting on its
+              // own after the publication, a thread delayed by ~1000 cycles - an instruction-cache miss under memory
+              // pressure from concurrent kernels - deadlocked the kernel: VAPB_PIPE=4 hung within 40 calls).
+              const bool more2 = pt + 2 * n_clusters < num_pair_tiles;
               cp_async_wait_all();
-              bar_prod();  // the next tile's window is complete; every producer has left this tile's window
+              if (r == 0 && more2) mbar_wait(win_free_bar, (uint32_t)(it & 1));
+              bar_prod();  // the next window is complete; every producer and the extra-row warp have left this tile's
               if (r == 0) mbar_arrive(win_full_bar);
-              if (pt + 2 * n_clusters < num_pair_tiles) {
-                mbar_wait(win_free_bar, (uint32_t)(it & 1));  // ... and so has the extra-row warp (it read it at its tile start)
-                prefetch(pt + 2 * n_clusters, it & 1);
-              }
+              if (more2) prefetch(pt + 2 * n_clusters, it & 1);
               make_x(t1, (it + 1) & 1, 0);
             }
             tock(1);

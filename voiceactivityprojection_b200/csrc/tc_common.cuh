@@ -277,7 +277,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint
   return d;
 }
 
-// Programmatic dependent launch (opt-in, VAPB_PDL=1; see launch_pdl below). launch_dependents lets the next kernel of
+// Programmatic dependent launch (on by default, VAPB_PDL=0 turns it off; see launch_pdl below). launch_dependents lets the next kernel of
 // the stream, if it was launched with the programmatic-serialisation attribute, start its CTAs as this kernel's
 // CTAs leave their SMs; wait blocks until every prerequisite grid has completed and its memory is visible. Both are
 // no-ops for a kernel launched the ordinary way. Every thread of a kernel launched through launch_pdl executes
@@ -288,9 +288,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 }  // namespace tc
 
-// Host: ordinary launch, or with cudaLaunchAttributeProgrammaticStreamSerialization when VAPB_PDL=1.
+// Host: launch with cudaLaunchAttributeProgrammaticStreamSerialization (default since round 2: tools/stress_identical.py,
+// 300 calls x 256 items under four concurrency patterns, bit-identical with it), or the ordinary way with VAPB_PDL=0.
 inline bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("VAPB_PDL"); return e && atoi(e) != 0; }();
+  static const bool on = [] { const char* e = getenv("VAPB_PDL"); return !e || atoi(e) != 0; }();
   return on;
 }
 template <typename P>
