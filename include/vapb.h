@@ -171,20 +171,10 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
 int vapb_profile_begin(VapbHandle* h);
 int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches);
 
-/* Unit-test hook for the tcgen05 GEMM kernel (tests/test_gpu_kernels.py): one
- * launch of csrc/k_gemm_tc.cu on caller-provided device buffers.
- * A: bf16, row (seq, t) at A + seq*a_seq_stride + t*a_row_stride (elements), K
- * contiguous elements per row (rows may overlap: implicit conv). W: bf16 [N][K].
- * Outputs / residual are dense (nseq*rows_per_seq, N). Returns 0 or a negative
- * code; the message is copied to err (if non-NULL). */
-int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W,
-                       int nseq, int rows_per_seq, int N, int K, const float* bias, int norm1,
-                       const float* g1, const float* b1, int act, const float* resid, int accumulate,
-                       float* out1_f32, void* out1_bf16, int norm2, const float* g2, const float* b2,
-                       void* out2_bf16, char* err, int err_len);
-
 /* Unit-test hook for the CTA-pair (cta_group::2) conv GEMM (csrc/k_gemm_2sm.cu): N = 256,
- * bias -> norm1 -> ReLU (act 1) -> dense bf16 (nseq*rows_per_seq, 256). Operands as vapb_debug_gemm_tc. */
+ * bias -> norm1 -> ReLU (act 1) -> dense bf16 (nseq*rows_per_seq, 256).
+ * A: 16-bit, row (seq, t) at A + seq*a_seq_stride + t*a_row_stride (elements), K contiguous elements per row (rows may
+ * overlap: implicit conv). W: 16-bit [N][K]. Returns 0 or a negative code; the message is copied to err (if non-NULL). */
 int vapb_debug_gemm_2sm(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W,
                         int nseq, int rows_per_seq, int K, const float* bias, int norm1, const float* g1,
                         const float* b1, int act, void* out_bf16, char* err, int err_len);
@@ -209,8 +199,8 @@ int vapb_debug_conv01(void* stream, const float* wav, int batch, int64_t n_sampl
                       int out_pad_rows, int fp16, char* err, int err_len,
                       long long* dbg_clocks /* device [4][4][16] SM-clock samples of CTA 0, or NULL */);
 
-/* Unit-test hook for the linear-layer GEMM (csrc/k_gemm_lin.cu): same operands as
- * vapb_debug_gemm_tc; outputs are dense (nseq*rows_per_seq, N). f32_mode 1: out1_f32
+/* Unit-test hook for the linear-layer GEMM (csrc/k_gemm_lin.cu): operands as
+ * vapb_debug_gemm_2sm plus N; outputs are dense (nseq*rows_per_seq, N). f32_mode 1: out1_f32
  * and resid_blocked use the row-blocked fp32 layout [row/128][col/4][row%128][4]
  * (buffers padded to a multiple of 128 rows); f32_mode 2: out1_f32 is row-major. */
 int vapb_debug_gemm_lin(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W,

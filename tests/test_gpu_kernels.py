@@ -9,89 +9,10 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-def _gemm_tc(A, a_seq_stride, a_row_stride, W, nseq, rps, N, K, bias=None, norm1=0, g1=None, b1=None, act=0,
-             resid=None, accumulate=False, out1_init=None, want_bf16=False, norm2=0, g2=None, b2=None):
-    from voiceactivityprojection_b200 import _lib
-
-    lib = _lib.load()
-    dev = A.device
-    M = nseq * rps
-    out1 = out1_init.clone() if out1_init is not None else torch.full((M, N), float("nan"), device=dev)
-    out1b = torch.zeros((M, N), device=dev, dtype=torch.bfloat16) if want_bf16 else None
-    out2 = torch.zeros((M, N), device=dev, dtype=torch.bfloat16) if norm2 else None
-    err = C.create_string_buffer(512)
-    p = lambda t: None if t is None else t.data_ptr()
-    st = torch.cuda.current_stream().cuda_stream
-    rc = lib.vapb_debug_gemm_tc(st, A.data_ptr(), a_seq_stride, a_row_stride, W.data_ptr(), nseq, rps, N, K, p(bias),
-                                norm1, p(g1), p(b1), act, p(resid), int(accumulate), out1.data_ptr(), p(out1b), norm2,
-                                p(g2), p(b2), p(out2), err, 512)
-    assert rc == 0, err.value.decode()
-    torch.cuda.synchronize()
-    return out1, out1b, out2
-
-
 def _norm(v, kind, g, b):
     mean = v.mean(-1, keepdim=True)
     var = v.var(-1, keepdim=True, unbiased=(kind == 1))
     return (v - mean) * torch.rsqrt(var + 1e-5) * g + b
-
-
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 256, 256), (4096 + 77, 768, 256), (300, 256, 768),
-                                   (20000, 1024, 256)])
-def test_gemm_tc_plain(M, N, K):
-    g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
-    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
-    bias = torch.randn(N, device="cuda", generator=g)
-    out, _, _ = _gemm_tc(A, 0, K, W, 1, M, N, K, bias=bias)
-    ref = A.float() @ W.float().T + bias
-    assert (out - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
-
-
-def test_gemm_tc_implicit_conv_with_channelnorm_relu():
-    """Conv1d(256,256,k=8,s=4,p=2)+ChannelNorm+ReLU as an implicit GEMM over a zero-padded channels-last buffer."""
-    g = torch.Generator(device="cuda").manual_seed(5)
-    nseq, L, k, s, pad = 3, 1000, 8, 4, 2
-    Lout = (L + 2 * pad - k) // s + 1
-    Lpad = ((max(s * (Lout - 1) + k, pad + L) + s - 1) // s) * s
-    x = torch.randn((nseq, L, 256), device="cuda", generator=g).bfloat16()
-    buf = torch.zeros((nseq, Lpad, 256), device="cuda", dtype=torch.bfloat16)
-    buf[:, pad:pad + L] = x
-    w = (torch.randn((256, 256, k), device="cuda", generator=g) * 0.03)
-    Wp = w.permute(0, 2, 1).reshape(256, k * 256).contiguous().bfloat16()  # [N][tap*256+cin]
-    bias = torch.randn(256, device="cuda", generator=g) * 0.1
-    g1 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
-    b1 = 0.1 * torch.randn(256, device="cuda", generator=g)
-    out, outb, _ = _gemm_tc(buf, Lpad * 256, s * 256, Wp, nseq, Lout, 256, k * 256, bias=bias, norm1=1, g1=g1, b1=b1,
-                            act=1, want_bf16=True)
-    wr = Wp.float().reshape(256, k, 256).permute(0, 2, 1)  # bf16-rounded weights back to (out,in,k)
-    y = F.conv1d(x.float().transpose(1, 2), wr, bias, stride=s, padding=pad).transpose(1, 2)  # (nseq, Lout, 256)
-    ref = F.relu(_norm(y, 1, g1, b1)).reshape(-1, 256)
-    assert (out - ref).abs().max().item() <= 5e-3
-    assert (outb.float() - ref).abs().max().item() <= 3e-2
-
-
-def test_gemm_tc_residual_layernorm2_gelu_accumulate():
-    g = torch.Generator(device="cuda").manual_seed(9)
-    M, K = 777, 256
-    A = torch.randn((M, K), device="cuda", generator=g).bfloat16()
-    W = (torch.randn((256, K), device="cuda", generator=g) * 0.05).bfloat16()
-    resid = torch.randn((M, 256), device="cuda", generator=g) * 2
-    g2 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
-    b2 = 0.1 * torch.randn(256, device="cuda", generator=g)
-    out1, out1b, out2 = _gemm_tc(A, 0, K, W, 1, M, 256, K, resid=resid, norm2=2, g2=g2, b2=b2, want_bf16=True)
-    v = A.float() @ W.float().T + resid
-    assert (out1 - v).abs().max().item() <= 3e-3
-    assert (out1b.float() - v).abs().max().item() <= 5e-2
-    assert (out2.float() - _norm(v, 2, g2, b2)).abs().max().item() <= 3e-2
-    # LayerNorm + GELU, then a second GEMM accumulating into the first result (combinator)
-    g1 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
-    b1 = 0.1 * torch.randn(256, device="cuda", generator=g)
-    o1, _, _ = _gemm_tc(A, 0, K, W, 1, M, 256, K, norm1=2, g1=g1, b1=b1, act=2)
-    ref1 = F.gelu(_norm(A.float() @ W.float().T, 2, g1, b1))
-    assert (o1 - ref1).abs().max().item() <= 3e-3
-    o2, _, _ = _gemm_tc(A, 0, K, W, 1, M, 256, K, norm1=2, g1=g1, b1=b1, act=2, accumulate=True, out1_init=o1)
-    assert (o2 - 2 * ref1).abs().max().item() <= 6e-3
 
 
 def _rnn_tc(kind, x, w_ih, w_hh, b_ih, b_hh, groups=0):

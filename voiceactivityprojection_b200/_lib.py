@@ -33,8 +33,6 @@ SYMBOLS = {
     "vapb_get_stage": (_i, [_vp, _vp, C.c_char_p, _i, _i64, _i, _vp, _sz, _fp, _sz]),
     "vapb_profile_begin": (_i, [_vp]),
     "vapb_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
-    "vapb_debug_gemm_tc": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, _i,
-                                _fp, _fp, _i, _fp, _fp, _fp, C.c_char_p, _i]),
     "vapb_debug_gemm_2sm": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, C.c_char_p, _i]),
     "vapb_debug_conv0_tc": (_i, [_vp, _fp, _i, _i64, _vp, _vp, _vp, _vp, _fp, _i, C.c_char_p, _i]),
     "vapb_debug_conv01": (_i, [_vp, _fp, _i, _i64, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i64, _i, _i, C.c_char_p, _i, _fp]),

@@ -139,7 +139,6 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV01")) h->m.conv01 = atoi(v);
-  if (const char* v = getenv("VAPB_CONV_LIN_FROM")) h->m.conv_lin_from = atoi(v);  // tuning knob, see model.h
   if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
   if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
   if (const char* v = getenv("VAPB_PIPE")) h->m.pipe = atoi(v);
@@ -709,45 +708,6 @@ int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches) {
     m.event_pool.push_back(r.b);
   }
   m.prof.clear();
-  return VAPB_OK;
-}
-
-int vapb_debug_gemm_tc(void* stream, const void* A, int64_t a_seq_stride, int64_t a_row_stride, const void* W, int nseq,
-                       int rows_per_seq, int N, int K, const float* bias, int norm1, const float* g1, const float* b1,
-                       int act, const float* resid, int accumulate, float* out1_f32, void* out1_bf16, int norm2,
-                       const float* g2, const float* b2, void* out2_bf16, char* err, int err_len) {
-  TcGemmArgs a{};
-  a.A = A;
-  a.a_map = RowMap{a_seq_stride, a_row_stride};
-  a.W = W;
-  a.nseq = nseq;
-  a.rows_per_seq = rows_per_seq;
-  a.N = N;
-  a.K = K;
-  const RowMap dense{(long long)rows_per_seq * N, N};
-  a.e.bias = bias;
-  a.e.norm1 = norm1; a.e.g1 = g1; a.e.b1 = b1;
-  a.e.act = act;
-  a.e.resid = resid; a.e.resid_map = dense;
-  a.e.accumulate = accumulate;
-  a.e.out1_map = dense;
-  a.e.norm2 = norm2; a.e.g2 = g2; a.e.b2 = b2;
-  a.e.out2 = out2_bf16; a.e.out2_map = dense;
-  a.out1_f32 = out1_f32;
-  a.out1_bf16 = reinterpret_cast<__nv_bfloat16*>(out1_bf16);
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  std::string msg;
-  int rc = launch_gemm_tc((cudaStream_t)stream, a, n_sm, &msg);
-  if (rc >= 0) {
-    cudaError_t e = cudaPeekAtLastError();
-    if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
-  }
-  if (rc < 0) {
-    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
-    return VAPB_E_CUDA;
-  }
   return VAPB_OK;
 }
 

@@ -54,7 +54,7 @@ struct GemmProblem {
   int K;
 };
 
-// Tensor-core GEMM (k_gemm_tc.cu): A and W are bf16; W is [N][K] (K contiguous).
+// Tensor-core GEMMs (k_gemm_lin.cu, k_gemm_2sm.cu): A and W are 16-bit; W is [N][K] (K contiguous).
 // The epilogue's out1 goes to out1_f32 and/or out1_bf16 (Epilogue::out1 ignored).
 struct TcGemmArgs {
   const void* A;
@@ -72,16 +72,13 @@ int launch_conv0(cudaStream_t st, const float* wav, int batch, long long n_sampl
                  const float* b, void* out, int out_bf16, long long out_seq_stride /*elements*/,
                  int out_pad_rows);
 
-// conv0 for the tensor path (k_conv0_v2.cu): closed-form ChannelNorm statistics, packed fp32 FMAs, bf16 out.
+// conv0 + ChannelNorm folded for the tensor path (tc_host.cu): centred, pre-scaled taps and closed-form statistics.
 struct Conv0Stats {
   float G[10][10];  // sum_c (w_c - wbar)(w_c - wbar)'
   float h2[10];     // 2 sum_c (b_c - bbar)(w_c - wbar)
   float s;          // sum_c (b_c - bbar)^2
 };
 void conv0_v2_fold(const float* w, const float* bias, const float* g, float* u, float* d, Conv0Stats* cs);
-int launch_conv0_v2(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq,
-                    long long L0, const float* u, const float* d, const float* beta, const Conv0Stats& cs,
-                    __nv_bfloat16* out, long long out_seq_stride, int out_pad_rows);
 
 // conv0 on the tensor cores (k_conv0_tc.cu): tf32 GEMM with K = 16 over an im2col tile built in shared memory
 int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_samples, int seq0, int nseq,
@@ -89,8 +86,6 @@ int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_sa
                     __nv_bfloat16* out, long long out_seq_stride, int out_pad_rows, int n_sm, std::string* err);
 
 int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
-
-int launch_gemm_tc(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);  // -1 on error
 
 // Linear-layer GEMM with staged / blocked epilogue I/O (k_gemm_lin.cu). f32_mode: 1 = out1_f32, resid and
 // accumulate use the row-blocked fp32 layout [row/128][col/4][row%128][4]; 2 = out1_f32 row-major via TMA.

@@ -1,7 +1,7 @@
 // BF16 tensor-core orchestration of VapGPT.forward (same call stack as
 // forward_fp32.cu; reference vap/model.py:249-268).
 //
-// Every contraction runs on tcgen05 (k_gemm_tc.cu) with bf16 operands and fp32
+// Every contraction runs on tcgen05 (k_conv01.cu, k_gemm_2sm.cu, k_gemm_lin.cu, ...) with 16-bit operands and fp32
 // accumulation in TMEM; norms, softmax, residual stream and the recurrence state
 // stay fp32. Activation buffers that feed a GEMM are bf16 channels-last; the
 // residual stream x is fp32 with a bf16 shadow where an un-normalised copy is a
@@ -36,7 +36,7 @@ struct State16 {
   const bf16* ds_w;
   LayerW16 chan[kMaxLayers], cross[kMaxLayers];
   const bf16 *comb_a, *comb_b, *head_w;
-  const float *c0_u, *c0_d;  // folded conv0 + ChannelNorm parameters (k_conv0_v2.cu)
+  const float *c0_u, *c0_d;  // folded conv0 + ChannelNorm parameters (tc_host.cu: conv0_v2_fold)
   Conv0Stats c0_stats;
   const float* c0_tab;             // [12][256] = u | d | beta on the device, and the same on the host: the fused
   std::vector<float> c0_tab_host;  // conv0 -> conv1 kernel takes the table as kernel parameters (k_conv01.cu)
@@ -101,21 +101,6 @@ struct Ctx {
   Model& m;
   cudaStream_t st;
   int rc = 0;
-  // A: bf16 rows; W: bf16 [N][K]
-  void gemm(const bf16* A, RowMap amap, const bf16* W, int nseq, int rps, int N, int K, const Epilogue& e,
-            float* out_f32, bf16* out_bf16, int cat = CAT_LINEAR_GEMM) {
-    if (rc) return;
-    TcGemmArgs a{};
-    a.A = A; a.a_map = amap; a.W = W;
-    a.nseq = nseq; a.rows_per_seq = rps; a.N = N; a.K = K;
-    a.e = e;
-    a.out1_f32 = out_f32; a.out1_bf16 = out_bf16;
-    ProfScope ps(m, st, cat);
-    std::string err;
-    const int n = launch_gemm_tc(st, a, m.n_sm, &err);
-    if (n < 0) { m.err = err; rc = -3; return; }
-    m.launches += n;
-  }
   // row-local layers: staged / blocked epilogue I/O (k_gemm_lin.cu); fp32 rows are blocked unless f32_mode == 2
   void lin(const bf16* A, RowMap amap, const bf16* W, int nseq, int rps, int N, int K, const Epilogue& e,
            float* out_f32, bf16* out_bf16, int f32_mode = 1, int cat = CAT_LINEAR_GEMM) {
@@ -316,8 +301,8 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry
         if (k < 0) { m.err = err; return -3; }
         m.launches += k;
       } else {
-        m.launches += launch_conv0_v2(st, wav, g.batch, g.S, s0, n, g.L[0], s.c0_u, s.c0_d, w.c0_be, s.c0_stats,
-                                      H(p.act[0]), p.lpad[0] * kDim, (int)p.lo[0]);
+        m.err = "VAPB_CONV0_TC=0: the CUDA-core conv0 kernel was removed in round 2 (k_conv0_tc.cu or the fused k_conv01.cu)";
+        return -3;
       }
     }
     for (int i = m.conv01 ? 2 : 1; i <= 4; ++i) {
@@ -347,12 +332,10 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry
         const int k = launch_gemm_2sm(st, a, m.n_sm, &err);
         if (k < 0) { m.err = err; return -3; }
         m.launches += k;
-      } else if (i >= m.conv_lin_from)
+      } else {
         cx.lin(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
                kDim, c.k * kDim, e, nullptr, out, 1, CAT_CONV_GEMM);
-      else
-        cx.gemm(H(p.act[i - 1]), RowMap{p.lpad[i - 1] * kDim, (long long)c.s * kDim}, s.conv_w[i], n, (int)g.L[i],
-                kDim, c.k * kDim, e, nullptr, out, CAT_CONV_GEMM);
+      }
     }
   }
 

@@ -4,7 +4,7 @@
 //
 // The layer writes 512 bytes per frame (65.5 MB per 20 s chunk in bf16) for 2560 MACs, so it
 // has to run at HBM write speed; on CUDA cores it is FMA-issue bound at half of that
-// (k_conv0_v2.cu). Here the conv is a GEMM with K = 16:
+// (the round-1 FFMA2 kernel, removed). Here the conv is a GEMM with K = 16:
 //   A[128 frames][16]  = im2col of the waveform (samples 5f-3 .. 5f+6, then 1.0, then zeros), tf32,
 //                        built in shared memory by 4 warps (the row stride of 5 samples is not
 //                        expressible as a TMA stride)

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm_2sm_kernel(const __grid_co
 
 }  // namespace
 
-// Same operand conventions as launch_gemm_tc; supports the conv epilogue only: bias -> norm1 -> ReLU -> bf16 (out1_bf16).
+// Operands as TcGemmArgs (common.cuh); supports the conv epilogue only: bias -> norm1 -> ReLU -> bf16 (out1_bf16).
 int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err) {
   const Epilogue& e = a.e;
   if (a.N != 256 || a.K % 64 || !a.out1_bf16 || a.out1_f32 || e.resid || e.accumulate || e.norm2 != NORM_NONE ||

@@ -2,7 +2,7 @@
 // combinator, vap_head; vap/modules.py:9-21,93-95,109,246-275,434-449,
 // vap/model.py:261) and the downsample conv (vap/encoder.py:24-30).
 //
-// Same mainloop as k_gemm_tc.cu (TMA -> smem ring -> tcgen05.mma M128 N256 K16, two
+// Mainloop of the first-generation GEMM (TMA -> smem ring -> tcgen05.mma M128 N256 K16, two
 // TMEM accumulators) but these GEMMs have K = 256..1280, so a 128 x 256 tile spends
 // ~1 us on the tensor pipe and the kernel lives or dies by its epilogue and its HBM
 // traffic. The epilogue therefore moves data only in full lines:
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) gemm_lin_kernel(const __grid_con
   }
 }
 
-// Same arguments as launch_gemm_tc, plus the fp32 layout choices:
+// Arguments as TcGemmArgs (common.cuh), plus the fp32 layout choices:
 //   f32_mode 1: out1_f32 / resid / accumulate use the blocked layout (dense row index seq*rows_per_seq + t)
 //   f32_mode 2: out1_f32 is row-major (e.out1_map) and written through TMA staging; resid stays blocked.
 int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm, std::string* err) {

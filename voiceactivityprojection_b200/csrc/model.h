@@ -69,10 +69,9 @@ struct Model {
   int conv_2sm = 1;       // gEncoder convs on CTA pairs (k_gemm_2sm.cu, cta_group::2); env VAPB_CONV_2SM
   int ffn_fused = 1;      // FFN block as one kernel (k_ffn_fused.cu); 0 = two GEMMs (env VAPB_FFN_FUSED)
   int conv01 = 1;         // conv0 fused into conv1's operand producer (k_conv01.cu); 0 = separate kernels (env VAPB_CONV01)
-  int conv0_tc = 1;       // conv0 on the tensor cores (k_conv0_tc.cu); 0 = CUDA-core kernel (env VAPB_CONV0_TC)
+  int conv0_tc = 1;       // unfused path: conv0 on the tensor cores (k_conv0_tc.cu); the CUDA-core fallback is gone
   int conv0_sms = 0;      // CTAs of the conv0 kernel (0 = one per SM); env VAPB_CONV0_SMS (tuning / overlap experiments)
   long long conv_mb_bytes = 0;  // conv0-output bytes per gEncoder micro-batch (0 = 4 GiB); env VAPB_CONV_MB_MIB (tuning)
-  int conv_lin_from = 1;  // gEncoder convs >= this index use k_gemm_lin.cu's staged epilogue (env VAPB_CONV_LIN_FROM)
   // Item-group pipelining of 16-bit-mode calls (api.cu): a large batch is cut into up to `pipe` groups of items, each
   // on its own stream. The groups' gEncoder phases run one after another (event chain), so one group's gAR recurrence
   // (latency-bound on a fraction of the SMs) and transformer overlap the next group's convolutions. env VAPB_PIPE
