@@ -379,7 +379,7 @@ def main():
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
-        tensor_mode = precision in ("bf16", "fp16")
+        tensor_mode = precision in ("bf16", "fp16")  # fp32_tc keeps the fp32 path's kernel split (conv0, xproj, ...)
         fl = flops_per_chunk(tensor_mode=tensor_mode, conv0_fused=fams["conv0"][0] == 0.0)
         dom = max(("conv_gemm", "linear_gemm", "attention", "rnn", "conv0"), key=lambda k: fams[k][0])
         dom_ms, dom_n = fams[dom]
@@ -430,7 +430,7 @@ def main():
             ref = O.probs(sd, sw)
             ref_fwd = O.forward(sd, sw)
             modes = {}
-            for prec, (n_steps, n_warm) in (("fp16", (4, 2)), ("bf16", (4, 2)), ("fp32", (2, 1))):
+            for prec, (n_steps, n_warm) in (("fp16", (4, 2)), ("bf16", (4, 2)), ("fp32_tc", (3, 1)), ("fp32", (2, 1))):
                 t_ms = timed_steps(prec, n_steps, n_warm)
                 o = model.probs(sw.to(dev), precision=prec)
                 f = model.forward(sw.to(dev), precision=prec)
@@ -475,7 +475,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16"}.get(precision, "f32"),
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32_tc": "f16x2 split (fp32-class)"}.get(precision, "f32"),
             "data": "synthetic", "config": workload_config(args, precision), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "modes": modes,
         }

@@ -42,7 +42,10 @@ enum {
  * BF16: tcgen05 tensor cores, bf16 operands, fp32 accumulate / norms / softmax / residual stream.
  * FP16: the same kernels with fp16 operands (3 more mantissa bits; every activation of this model
  *       sits behind a norm, far inside fp16 range): same speed, ~8x lower error than BF16. */
-enum { VAPB_MODE_FP32 = 0, VAPB_MODE_BF16 = 1, VAPB_MODE_FP16 = 2 };
+/* FP32: CUDA-core FMA everywhere (bit-exact decisions, probabilities within 1e-5). BF16 / FP16: tcgen05, 16-bit operands.
+ * FP32_TC: the fp32 path with every GEMM on the tensor cores at fp32-class accuracy (fp16 hi/lo split of both operands,
+ * three MMAs per K step; softmax, recurrence, norms in fp32): 2.7x the FP32 mode, probabilities within 1e-5. */
+enum { VAPB_MODE_FP32 = 0, VAPB_MODE_BF16 = 1, VAPB_MODE_FP16 = 2, VAPB_MODE_FP32_TC = 3 };
 
 /* --- construction: replaces VapGPT.__init__ + load_state_dict (run.py:199-201) */
 
@@ -170,6 +173,17 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
 #define VAPB_PROFILE_FAMILIES 7
 int vapb_profile_begin(VapbHandle* h);
 int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches);
+
+/* Unit-test hook for the fp32-class tensor-core GEMM of the parity mode (csrc/k_gemm_x3.cu: fp16 hi/lo split of both
+ * operands, three MMAs per K step). A: device fp32, row (seq, t) at A + seq*a_seq_stride + t*a_row_stride (elements),
+ * K contiguous (rows may overlap: implicit conv). Wt_host: HOST fp32 [K][N] (element (k, n) at k*N + n; split and laid
+ * out by the hook). Epilogue as k_gemm_f32.cu, all device fp32, outputs / residual dense (nseq*rows_per_seq, N):
+ * bias -> norm1 (1 ChannelNorm, 2 LayerNorm; N == 256) -> act (1 ReLU, 2 GELU) -> + resid -> (+= out1) -> out1;
+ * out2 = LayerNorm2(out1 value). N % 256 == 0, K % 32 == 0. */
+int vapb_debug_gemm_x3(void* stream, const float* A, int64_t a_seq_stride, int64_t a_row_stride, const float* Wt_host,
+                       int nseq, int rows_per_seq, int N, int K, const float* bias, int norm1, const float* g1,
+                       const float* b1, int act, const float* resid, int accumulate, float* out1, int norm2,
+                       const float* g2, const float* b2, float* out2, char* err, int err_len);
 
 /* Unit-test hook for the CTA-pair (cta_group::2) conv GEMM (csrc/k_gemm_2sm.cu): N = 256,
  * bias -> norm1 -> ReLU (act 1) -> dense bf16 (nseq*rows_per_seq, 256).

@@ -381,3 +381,70 @@ def test_conv0_tc_standalone_matches_torch(B, S, fp16):
     # tf32 operands (2^-11) and a 16-bit result: absolute error scales with the output magnitude (|ref| up to ~6)
     assert d.max().item() <= (6e-3 if fp16 else 4e-2), d.max().item()
     assert d.mean().item() <= (5e-4 if fp16 else 3e-3)
+
+
+def _gemm_x3(A, a_seq_stride, a_row_stride, Wt, nseq, rps, N, K, bias=None, norm1=0, g1=None, b1=None, act=0, resid=None,
+             accumulate=False, out1_init=None, norm2=0, g2=None, b2=None):
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    M = nseq * rps
+    out1 = out1_init.clone() if out1_init is not None else torch.full((M, N), float("nan"), device="cuda")
+    out2 = torch.full((M, N), float("nan"), device="cuda") if norm2 else None
+    wt = Wt.detach().cpu().contiguous()
+    err = C.create_string_buffer(512)
+    p = lambda t: None if t is None else t.data_ptr()
+    rc = lib.vapb_debug_gemm_x3(torch.cuda.current_stream().cuda_stream, A.data_ptr(), a_seq_stride, a_row_stride,
+                                wt.data_ptr(), nseq, rps, N, K, p(bias), norm1, p(g1), p(b1), act, p(resid),
+                                int(accumulate), out1.data_ptr(), norm2, p(g2), p(b2), p(out2), err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    return out1, out2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (1000, 768, 256), (4096 + 77, 256, 768), (333, 1024, 256)])
+def test_gemm_x3_plain_is_fp32_class(M, N, K):
+    """Split-fp16 tensor-core GEMM of the parity mode against an fp64 reference: error at the level of an fp32 GEMM."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), device="cuda", generator=g) * 3
+    Wt = torch.randn((K, N), device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    out, _ = _gemm_x3(A, 0, K, Wt, 1, M, N, K, bias=bias)
+    ref = (A.double() @ Wt.double() + bias.double())
+    scale = (A.abs().double() @ Wt.abs().double()).max().item()
+    assert (out.double() - ref).abs().max().item() <= 2e-6 * scale
+    f32 = (A @ Wt + bias).double()
+    assert (out.double() - ref).abs().max().item() <= 4 * max((f32 - ref).abs().max().item(), 1e-7 * scale)
+
+
+def test_gemm_x3_implicit_conv_norm_relu_and_residual_layernorm2():
+    g = torch.Generator(device="cuda").manual_seed(11)
+    nseq, L, k, s, pad = 3, 1000, 8, 4, 2
+    Lout = (L + 2 * pad - k) // s + 1
+    Lpad = ((max(s * (Lout - 1) + k, pad + L) + s - 1) // s) * s
+    x = torch.randn((nseq, L, 256), device="cuda", generator=g)
+    buf = torch.zeros((nseq, Lpad, 256), device="cuda")
+    buf[:, pad:pad + L] = x
+    w = torch.randn((256, 256, k), device="cuda", generator=g) * 0.03
+    Wt = w.permute(2, 1, 0).reshape(k * 256, 256).contiguous()  # [(tap*256 + cin)][out]
+    bias = torch.randn(256, device="cuda", generator=g) * 0.1
+    g1 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    b1 = 0.1 * torch.randn(256, device="cuda", generator=g)
+    out, _ = _gemm_x3(buf, Lpad * 256, s * 256, Wt, nseq, Lout, 256, k * 256, bias=bias, norm1=1, g1=g1, b1=b1, act=1)
+    y = F.conv1d(x.double().transpose(1, 2), w.double(), bias.double(), stride=s, padding=pad).transpose(1, 2)
+    ref = F.relu(_norm(y, 1, g1.double(), b1.double())).reshape(-1, 256)
+    assert (out.double() - ref).abs().max().item() <= 5e-5  # outputs up to ~5; K = 2048 products of 22-bit operands
+    # Linear + residual + LayerNorm2, then GELU + accumulate
+    M, K = 777, 256
+    A = torch.randn((M, K), device="cuda", generator=g)
+    W2 = torch.randn((K, 256), device="cuda", generator=g) * 0.05
+    resid = torch.randn((M, 256), device="cuda", generator=g) * 2
+    g2 = 1 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    b2 = 0.1 * torch.randn(256, device="cuda", generator=g)
+    o1, o2 = _gemm_x3(A, 0, K, W2, 1, M, 256, K, resid=resid, norm2=2, g2=g2, b2=b2)
+    v = A.double() @ W2.double() + resid.double()
+    assert (o1.double() - v).abs().max().item() <= 1e-5
+    assert (o2.double() - _norm(v, 2, g2.double(), b2.double())).abs().max().item() <= 1e-5
+    o3, _ = _gemm_x3(A, 0, K, W2, 1, M, 256, K, norm1=2, g1=g1, b1=b1, act=2, accumulate=True, out1_init=o1)
+    ref3 = v + F.gelu(_norm(A.double() @ W2.double(), 2, g1.double(), b1.double()))
+    assert (o3.double() - ref3).abs().max().item() <= 3e-5  # LayerNorm divides the GEMM's error by sigma ~ 0.8; |v| up to ~10

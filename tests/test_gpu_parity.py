@@ -656,3 +656,22 @@ def test_full_size_batch_sampled_items_match_oracle(precision):
     assert agree == 1.0 if precision == "fp32" else agree >= 0.99
     if precision == "fp32":
         assert torch.equal(out["vad"][pick].cpu() >= 0.5, ref["vad"] >= 0.5)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_fp32_tc_mode_is_fp32_class_on_reference_golden(name):
+    """precision="fp32_tc" (VAPB_MODE_FP32_TC): the fp32 path with every GEMM on the tensor cores (fp16 hi/lo split,
+    three MMAs per K step, k_gemm_x3.cu). Probabilities within 1e-5 of the reference, logits within 1e-4, arg-max class
+    and thresholded VAD identical to the reference on every golden case."""
+    recipe, g = load_golden(name)
+    sd, wav = golden_inputs(recipe, g)
+    m = _model(sd, "fp32_tc")
+    x = wav.cuda()
+    fwd = m(x)
+    out = m.probs(x)
+    assert _maxerr(fwd["logits"], g["logits"]) <= 1e-4
+    for k, tol in (("probs", 1e-5), ("p_now", 1e-5), ("p_future", 1e-5), ("vad", 3e-5)):
+        if k in g:
+            assert _maxerr(out[k], g[k]) <= tol, k
+    assert torch.equal(fwd["logits"].argmax(-1).cpu(), g["logits"].argmax(-1))
+    assert torch.equal(out["vad"].cpu() >= 0.5, g["vad"] >= 0.5)

@@ -8,8 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VAPB_LIB") or os.path.join(_HERE, "libvapb.so")  # VAPB_LIB: A/B a second build
 
-MODE_FP32, MODE_BF16, MODE_FP16 = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "fp16": MODE_FP16}
+MODE_FP32, MODE_BF16, MODE_FP16, MODE_FP32_TC = 0, 1, 2, 3
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "fp16": MODE_FP16, "fp32_tc": MODE_FP32_TC}
 
 # every symbol include/vapb.h declares: name -> (restype, argtypes)
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
@@ -33,6 +33,8 @@ SYMBOLS = {
     "vapb_get_stage": (_i, [_vp, _vp, C.c_char_p, _i, _i64, _i, _vp, _sz, _fp, _sz]),
     "vapb_profile_begin": (_i, [_vp]),
     "vapb_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "vapb_debug_gemm_x3": (_i, [_vp, _fp, _i64, _i64, _vp, _i, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, _i, _fp, _i,
+                                _fp, _fp, _fp, C.c_char_p, _i]),
     "vapb_debug_gemm_2sm": (_i, [_vp, _fp, _i64, _i64, _fp, _i, _i, _i, _fp, _i, _fp, _fp, _i, _fp, C.c_char_p, _i]),
     "vapb_debug_conv0_tc": (_i, [_vp, _fp, _i, _i64, _vp, _vp, _vp, _vp, _fp, _i, C.c_char_p, _i]),
     "vapb_debug_conv01": (_i, [_vp, _fp, _i, _i64, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _fp, _i64, _i, _i, C.c_char_p, _i, _fp]),

@@ -7,9 +7,13 @@
 #include <set>
 
 #include "../../include/vapb.h"
+#include <cuda_fp16.h>
+
 #include "model.h"
 
 using namespace vapb;
+
+namespace vapb { void x3_pack_weight(const float* wt, int K, int N, std::vector<__half>* out); }
 
 namespace vapb { extern thread_local int g_fp16; }  // 16-bit format of this thread's launches (tc_common.cuh)
 
@@ -139,6 +143,7 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV01")) h->m.conv01 = atoi(v);
+  if (const char* v = getenv("VAPB_FP32_TC")) h->m.fp32_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
   if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
   if (const char* v = getenv("VAPB_PIPE")) h->m.pipe = atoi(v);
@@ -271,7 +276,13 @@ int vapb_finalize(VapbHandle* h) {
   Packer pk;
   struct Fix { const void** slot; size_t off; };
   std::vector<Fix> fixes;
-  auto put = [&](const void** slot, const std::vector<float>& v) { fixes.push_back({slot, pk.add_f(v)}); };
+  struct GemmW { const void** slot; size_t off; int K, N; };  // every fp32 GEMM weight [K][N]: split copy for k_gemm_x3.cu
+  std::vector<GemmW> gemm_ws;
+  auto put = [&](const void** slot, const std::vector<float>& v, int K, int N) {
+    const size_t off = pk.add_f(v);
+    fixes.push_back({slot, off});
+    gemm_ws.push_back({slot, off, K, N});
+  };
   auto putf = [&](const float** slot, const std::vector<float>& v) {
     fixes.push_back({reinterpret_cast<const void**>(slot), pk.add_f(v)});
   };
@@ -288,14 +299,14 @@ int vapb_finalize(VapbHandle* h) {
   }
   for (int i = 1; i < 5; ++i) {
     const std::string n = std::to_string(i);
-    put(&w.conv_w[i], pack_conv(T(GE + "conv" + n + ".weight")));
+    put(&w.conv_w[i], pack_conv(T(GE + "conv" + n + ".weight")), ck[i] * kDim, kDim);
     putf(&w.conv_b[i], T(GE + "conv" + n + ".bias").data);
     putf(&w.conv_g[i], T(GE + "batchNorm" + n + ".weight").data);
     putf(&w.conv_be[i], T(GE + "batchNorm" + n + ".bias").data);
   }
   for (int l = 0; l < m.ar_layers; ++l) {
     const std::string n = std::to_string(l);
-    put(&w.rnn_wih[l], transpose_linear(T(AR + "weight_ih_l" + n)));
+    put(&w.rnn_wih[l], transpose_linear(T(AR + "weight_ih_l" + n)), kDim, (int)GH);
     putf(&w.rnn_whh_t[l], transpose_linear(T(AR + "weight_hh_l" + n)));
     const auto& bi = T(AR + "bias_ih_l" + n).data;
     const auto& bh = T(AR + "bias_hh_l" + n).data;
@@ -309,7 +320,7 @@ int vapb_finalize(VapbHandle* h) {
     putf(&w.rnn_bx[l], bx);
     putf(&w.rnn_bhn[l], bhn);
   }
-  put(&w.ds_w, pack_conv(T("encoder.downsample.1.weight")));
+  put(&w.ds_w, pack_conv(T("encoder.downsample.1.weight")), 5 * kDim, kDim);
   putf(&w.ds_b, T("encoder.downsample.1.bias").data);
   putf(&w.ds_g, T("encoder.downsample.2.ln.weight").data);
   putf(&w.ds_be, T("encoder.downsample.2.ln.bias").data);
@@ -319,28 +330,28 @@ int vapb_finalize(VapbHandle* h) {
     putf(&lw.ln_ffn_g, T(p + "ln_ffnetwork.weight").data);
     putf(&lw.ln_ffn_b, T(p + "ln_ffnetwork.bias").data);
     putf(&lw.slopes, T(p + "mha.m").data);
-    put(&lw.wqkv, concat_linear({&T(p + "mha.query.weight"), &T(p + "mha.key.weight"), &T(p + "mha.value.weight")}));
-    put(&lw.wproj, transpose_linear(T(p + "mha.proj.weight")));
+    put(&lw.wqkv, concat_linear({&T(p + "mha.query.weight"), &T(p + "mha.key.weight"), &T(p + "mha.value.weight")}), kDim, 3 * kDim);
+    put(&lw.wproj, transpose_linear(T(p + "mha.proj.weight")), kDim, kDim);
     if (cross) {
       putf(&lw.ln_src_g, T(p + "ln_src_attn.weight").data);
       putf(&lw.ln_src_b, T(p + "ln_src_attn.bias").data);
       putf(&lw.slopes_cross, T(p + "mha_cross.m").data);
-      put(&lw.wq_c, transpose_linear(T(p + "mha_cross.query.weight")));
-      put(&lw.wkv_c, concat_linear({&T(p + "mha_cross.key.weight"), &T(p + "mha_cross.value.weight")}));
-      put(&lw.wproj_c, transpose_linear(T(p + "mha_cross.proj.weight")));
+      put(&lw.wq_c, transpose_linear(T(p + "mha_cross.query.weight")), kDim, kDim);
+      put(&lw.wkv_c, concat_linear({&T(p + "mha_cross.key.weight"), &T(p + "mha_cross.value.weight")}), kDim, 2 * kDim);
+      put(&lw.wproj_c, transpose_linear(T(p + "mha_cross.proj.weight")), kDim, kDim);
     }
-    put(&lw.w1, transpose_linear(T(p + "ffnetwork.0.weight")));
-    put(&lw.w2, transpose_linear(T(p + "ffnetwork.3.weight")));
+    put(&lw.w1, transpose_linear(T(p + "ffnetwork.0.weight")), kDim, kFfn);
+    put(&lw.w2, transpose_linear(T(p + "ffnetwork.3.weight")), kFfn, kDim);
   };
   for (int l = 0; l < m.channel_layers; ++l) pack_layer("ar_channel.layers." + std::to_string(l) + ".", false, w.chan[l]);
   for (int l = 0; l < m.cross_layers; ++l) pack_layer("ar.layers." + std::to_string(l) + ".", true, w.cross[l]);
-  put(&w.comb_a, transpose_linear(T("ar.combinator.h0_a.weight")));
-  put(&w.comb_b, transpose_linear(T("ar.combinator.h0_b.weight")));
+  put(&w.comb_a, transpose_linear(T("ar.combinator.h0_a.weight")), kDim, kDim);
+  put(&w.comb_b, transpose_linear(T("ar.combinator.h0_b.weight")), kDim, kDim);
   putf(&w.comb_g, T("ar.combinator.ln.weight").data);
   putf(&w.comb_be, T("ar.combinator.ln.bias").data);
   putf(&w.va_w, T("va_classifier.weight").data);
   putf(&w.va_b, T("va_classifier.bias").data);
-  put(&w.head_w, transpose_linear(T("vap_head.weight")));
+  put(&w.head_w, transpose_linear(T("vap_head.weight")), kDim, kClasses);
   putf(&w.head_b, T("vap_head.bias").data);
 
   CUDA_OK(m, cudaSetDevice(m.device));
@@ -348,6 +359,19 @@ int vapb_finalize(VapbHandle* h) {
   CUDA_OK(m, cudaMalloc(&m.arena, m.arena_bytes));
   CUDA_OK(m, cudaMemcpy(m.arena, pk.host.data(), m.arena_bytes, cudaMemcpyHostToDevice));
   for (auto& f : fixes) *f.slot = static_cast<char*>(m.arena) + f.off;
+  if (m.fp32_tc) {  // fp16 hi / lo images of every GEMM weight for the tensor-core parity GEMM
+    std::vector<__half> all, one;
+    std::vector<size_t> offs;
+    for (auto& gw : gemm_ws) {
+      x3_pack_weight(reinterpret_cast<const float*>(pk.host.data() + gw.off), gw.K, gw.N, &one);
+      offs.push_back(all.size());
+      all.insert(all.end(), one.begin(), one.end());
+    }
+    CUDA_OK(m, cudaMalloc(&m.x3_arena, all.size() * sizeof(__half)));
+    CUDA_OK(m, cudaMemcpy(m.x3_arena, all.data(), all.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < gemm_ws.size(); ++i)
+      m.x3_w[*gemm_ws[i].slot] = static_cast<const __half*>(m.x3_arena) + offs[i];
+  }
 
   const int rc = bf16_prepare(m);
   if (rc != 0) return rc;
@@ -366,6 +390,7 @@ int vapb_destroy(VapbHandle* h) {
   for (auto st : h->m.pipe_st) cudaStreamDestroy(st);
   bf16_release(h->m);
   if (h->m.arena) cudaFree(h->m.arena);
+  if (h->m.x3_arena) cudaFree(h->m.x3_arena);
   delete h;
   return VAPB_OK;
 }
@@ -408,7 +433,7 @@ struct CallPlan {
 };
 
 int n_groups_for(const Model& m, int batch, int mode) {
-  if (mode == VAPB_MODE_FP32 || m.pipe <= 1) return 1;
+  if (mode == VAPB_MODE_FP32 || mode == VAPB_MODE_FP32_TC || m.pipe <= 1) return 1;
   int n = batch / (m.pipe_min_items > 0 ? m.pipe_min_items : 1);
   if (n > m.pipe) n = m.pipe;
   return n < 1 ? 1 : n;
@@ -418,13 +443,15 @@ int plan_all(const Model& m, int batch, int64_t n_samples, int mode, CallPlan* c
   Geometry* g = &cp->g;
   Aux* aux = &cp->aux;
   if (batch < 1 || batch > 16384) { *err = "batch out of range"; return VAPB_E_INVALID; }
-  if (mode != VAPB_MODE_FP32 && mode != VAPB_MODE_BF16 && mode != VAPB_MODE_FP16) { *err = "unknown mode"; return VAPB_E_INVALID; }
+  if (mode != VAPB_MODE_FP32 && mode != VAPB_MODE_BF16 && mode != VAPB_MODE_FP16 && mode != VAPB_MODE_FP32_TC) { *err = "unknown mode"; return VAPB_E_INVALID; }
+  if (mode == VAPB_MODE_FP32_TC && m.x3_w.empty()) { *err = "mode FP32_TC is switched off (VAPB_FP32_TC=0)"; return VAPB_E_UNSUPPORTED; }
   if (n_samples < 1 || make_geometry(batch, n_samples, g) != 0 || g->T < 1) {
     *err = "n_samples too small for the conv chain";
     return VAPB_E_INVALID;
   }
   if ((long long)g->nseq * g->L[1] > 2000000000LL) { *err = "batch * n_samples too large for one call"; return VAPB_E_INVALID; }
-  size_t path_bytes = mode == VAPB_MODE_FP32 ? workspace_bytes_fp32(m, *g) : workspace_bytes_bf16(m, *g);
+  const bool f32path = mode == VAPB_MODE_FP32 || mode == VAPB_MODE_FP32_TC;
+  size_t path_bytes = f32path ? workspace_bytes_fp32(m, *g) : workspace_bytes_bf16(m, *g);
   if (path_bytes == 0) { *err = "mode not available in this build"; return VAPB_E_UNSUPPORTED; }
   const int ng = n_groups_for(m, batch, mode);
   cp->groups.clear();
@@ -456,9 +483,9 @@ int run_forward(Model& m, cudaStream_t st, const float* wav, const Geometry& g, 
                 float* vad_logits, float* vad_sig, cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr,
                 int wav_pcm16 = 0) {
   const float* comb = nullptr;
-  if (mode == VAPB_MODE_FP32) {
+  if (mode == VAPB_MODE_FP32 || mode == VAPB_MODE_FP32_TC) {
     if (wav_pcm16) { m.err = "int16 PCM input is read by the 16-bit modes only (vapb_pcm16_to_f32 converts for fp32)"; return VAPB_E_UNSUPPORTED; }
-    return forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb);
+    return forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, nullptr, mode == VAPB_MODE_FP32_TC);
   }
   const int rc = forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, mode == VAPB_MODE_FP16, conv_wait,
                               conv_done, wav_pcm16);
@@ -673,7 +700,7 @@ int vapb_get_stage(VapbHandle* h, void* stream, const char* name, int batch, int
     return fail(m, VAPB_E_UNSUPPORTED, "stage export is not available for a pipelined call (batch >= " +
                                            std::to_string(2 * m.pipe_min_items) + "); use a smaller batch or VAPB_PIPE=1");
   StageRef ref{};
-  rc = mode == VAPB_MODE_FP32 ? stage_fp32(m, g, (char*)workspace, name, &ref)
+  rc = (mode == VAPB_MODE_FP32 || mode == VAPB_MODE_FP32_TC) ? stage_fp32(m, g, (char*)workspace, name, &ref)
                               : stage_bf16(m, g, (char*)workspace, name, &ref);
   if (rc) return fail(m, VAPB_E_INVALID, std::string("unknown stage ") + name);
   if (out_elems < (size_t)ref.nseq * ref.rows_per_seq * kDim) return fail(m, VAPB_E_INVALID, "stage output too small");
@@ -708,6 +735,51 @@ int vapb_profile_end(VapbHandle* h, double* ms, uint64_t* launches) {
     m.event_pool.push_back(r.b);
   }
   m.prof.clear();
+  return VAPB_OK;
+}
+
+int vapb_debug_gemm_x3(void* stream, const float* A, int64_t a_seq_stride, int64_t a_row_stride, const float* Wt_host,
+                       int nseq, int rows_per_seq, int N, int K, const float* bias, int norm1, const float* g1,
+                       const float* b1, int act, const float* resid, int accumulate, float* out1, int norm2,
+                       const float* g2, const float* b2, float* out2, char* err, int err_len) {
+  std::string msg;
+  int rc = -1;
+  void* dw = nullptr;
+  if (!A || !Wt_host || !out1 || N % 256 || K % 32) {
+    msg = "gemm_x3: invalid argument";
+  } else {
+    std::vector<__half> packed;
+    x3_pack_weight(Wt_host, K, N, &packed);
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaMalloc(&dw, packed.size() * sizeof(__half)) != cudaSuccess ||
+        cudaMemcpy(dw, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) {
+      msg = "gemm_x3: cannot stage the weight";
+    } else {
+      GemmProblem p{A, RowMap{a_seq_stride, a_row_stride}, nullptr, nseq * rows_per_seq, rows_per_seq, N, K};
+      const RowMap dense{(long long)rows_per_seq * N, N};
+      Epilogue e{};
+      e.bias = bias;
+      e.norm1 = norm1; e.g1 = g1; e.b1 = b1;
+      e.act = act;
+      e.resid = resid; e.resid_map = dense;
+      e.accumulate = accumulate;
+      e.out1 = out1; e.out1_map = dense;
+      e.norm2 = norm2; e.g2 = g2; e.b2 = b2;
+      e.out2 = out2; e.out2_map = dense;
+      rc = launch_gemm_x3((cudaStream_t)stream, p, e, dw, n_sm, &msg);
+      if (rc >= 0) {
+        cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream);
+        if (ce != cudaSuccess) { msg = cudaGetErrorString(ce); rc = -1; }
+      }
+    }
+  }
+  if (dw) cudaFree(dw);
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
   return VAPB_OK;
 }
 

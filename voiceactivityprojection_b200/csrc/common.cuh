@@ -86,6 +86,10 @@ int launch_conv0_tc(cudaStream_t st, const float* wav, int batch, long long n_sa
                     __nv_bfloat16* out, long long out_seq_stride, int out_pad_rows, int n_sm, std::string* err);
 
 int launch_gemm_f32(cudaStream_t st, const GemmProblem& p, const Epilogue& e);
+// The same contraction on the tensor cores with fp32-class accuracy (k_gemm_x3.cu: fp16 hi/lo split of both operands,
+// three MMAs per K step). w_packed: device copy of x3_pack_weight's output. Returns launches, or -1 if unsupported.
+int launch_gemm_x3(cudaStream_t st, const GemmProblem& p, const Epilogue& e, const void* w_packed, int n_sm,
+                   std::string* err);
 
 // Linear-layer GEMM with staged / blocked epilogue I/O (k_gemm_lin.cu). f32_mode: 1 = out1_f32, resid and
 // accumulate use the row-blocked fp32 layout [row/128][col/4][row%128][4]; 2 = out1_f32 row-major via TMA.

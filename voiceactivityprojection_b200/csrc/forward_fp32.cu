@@ -75,10 +75,19 @@ RowMap dense(long long n) { return RowMap{0, n}; }
 struct Ctx {
   Model& m;
   cudaStream_t st;
+  bool x3 = false;  // VAPB_MODE_FP32_TC
   void gemm(const void* A, RowMap amap, const void* W, int M, int rps, int N, int K, const Epilogue& e,
             int cat = CAT_LINEAR_GEMM) {
     GemmProblem p{A, amap, W, M, rps, N, K};
     ProfScope ps(m, st, cat);
+    if (x3) {  // split-fp16 tensor-core GEMM, same operands and epilogue (k_gemm_x3.cu)
+      auto it = m.x3_w.find(W);
+      if (it != m.x3_w.end()) {
+        std::string err;
+        const int n = launch_gemm_x3(st, p, e, it->second, m.n_sm, &err);
+        if (n >= 0) { m.launches += n; return; }
+      }
+    }
     m.launches += launch_gemm_f32(st, p, e);
   }
 };
@@ -95,10 +104,10 @@ Epilogue epi_plain(float* out, int N) {
 size_t workspace_bytes_fp32(const Model& m, const Geometry& g) { return make_plan(m, g).bytes; }
 
 int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float**, const AttnMaps* maps) {
+                 float* vad_logits, float* vad_sig, const float**, const AttnMaps* maps, bool tensor_gemms) {
   const Plan32 p = make_plan(m, g);
   const Weights& w = m.w32;
-  Ctx cx{m, st};
+  Ctx cx{m, st, tensor_gemms};
   const int G = m.ar_kind == 0 ? 4 : 3;
   const int nseq = g.nseq;
   const long long T = g.T, L4 = g.L[4];

@@ -65,6 +65,12 @@ struct Model {
   size_t arena_bytes = 0;
   Weights w32{};   // fp32 [K][N] packing (SIMT path)
   void* bf16_state = nullptr;  // tensor-path weights / tensor maps (forward_bf16.cu)
+  // fp32 mode on the tensor cores (k_gemm_x3.cu): every GEMM weight of the fp32 path, split into fp16 hi / lo parts and
+  // laid out for the kernel; keyed by the fp32 weight's device pointer. Used by mode VAPB_MODE_FP32_TC; env
+  // VAPB_FP32_TC=0 skips the preparation (the mode is then unavailable)
+  int fp32_tc = 1;
+  void* x3_arena = nullptr;
+  std::map<const void*, const void*> x3_w;
   int n_sm = 148;
   int conv_2sm = 1;       // gEncoder convs on CTA pairs (k_gemm_2sm.cu, cta_group::2); env VAPB_CONV_2SM
   int ffn_fused = 1;      // FFN block as one kernel (k_ffn_fused.cu); 0 = two GEMMs (env VAPB_FFN_FUSED)
@@ -150,7 +156,8 @@ size_t workspace_bytes_fp32(const Model& m, const Geometry& g);
 // (the stereo layers' self- and cross-attention). Pointers address item 0 of the call.
 struct AttnMaps { float *self_attn, *cross_attn, *cross_self_attn; };
 int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
-                 float* vad_logits, float* vad_sig, const float** comb_out, const AttnMaps* maps = nullptr);
+                 float* vad_logits, float* vad_sig, const float** comb_out, const AttnMaps* maps = nullptr,
+                 bool tensor_gemms = false /* VAPB_MODE_FP32_TC: k_gemm_x3.cu for every contraction */);
 int stage_fp32(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
 // ---- BF16 tensor-core path (forward_bf16.cu) --------------------------------

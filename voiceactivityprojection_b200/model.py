@@ -13,9 +13,10 @@ Differences a caller can see:
   * `forward(..., attention=True)` returns the reference's attention maps from a
     separate fp32 map kernel (the fused attention kernels never materialise them).
   * `precision="fp32"` (default; CUDA-core FMA, parity with the reference),
-    `"bf16"` or `"fp16"` (tcgen05 tensor cores; same kernels and speed, fp16
-    operands give ~8x lower error) — constructor keyword, attribute, or env
-    VAPB_PRECISION.
+    `"fp32_tc"` (the same fp32 path with every GEMM on the tensor cores at
+    fp32-class accuracy, 2.7x faster), `"bf16"` or `"fp16"` (tcgen05 tensor cores;
+    same kernels and speed, fp16 operands give ~8x lower error) — constructor
+    keyword, attribute, or env VAPB_PRECISION.
 """
 from __future__ import annotations
 
@@ -341,7 +342,7 @@ class VapGPT(nn.Module):
         mode = self._mode(precision)
         fmt = 0
         if wav.dtype == torch.int16:
-            if mode != _lib.MODE_FP32 and S % 2 == 0 and wav.data_ptr() % 4 == 0 and os.environ.get("VAPB_CONV01", "1") != "0":
+            if mode in (_lib.MODE_BF16, _lib.MODE_FP16) and S % 2 == 0 and wav.data_ptr() % 4 == 0 and os.environ.get("VAPB_CONV01", "1") != "0":
                 fmt = 1
             else:
                 wav = self._pcm16_to_f32(wav)
