@@ -675,3 +675,27 @@ def test_fp32_tc_mode_is_fp32_class_on_reference_golden(name):
             assert _maxerr(out[k], g[k]) <= tol, k
     assert torch.equal(fwd["logits"].argmax(-1).cpu(), g["logits"].argmax(-1))
     assert torch.equal(out["vad"].cpu() >= 0.5, g["vad"] >= 0.5)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_fused_head_equals_separate_head_and_probs_kernels(precision, monkeypatch):
+    """k_head_fused.cu (vap_head GEMM + softmax / entropy / marginals / arg-max / logsumexp in the accumulator's
+    epilogue) against the separate GEMM + probs_kernel path on the same logits: outputs agree to fp32 rounding of the
+    different exp / reduction orders, decisions and counters are identical, custom bin limits included."""
+    from oracle import synth
+
+    sd = synth.make_state_dict(4, "LSTM", 1, 2.0)
+    wav = synth.make_waveform(3, 48000, 12, "turns").cuda()
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("VAPB_HEAD_FUSED", fused)
+        m = _model(sd, precision)
+        cnt = torch.zeros(258, dtype=torch.int64, device="cuda")
+        o = m.probs(wav, out=m.alloc_outputs(3, 150, "cuda", argmax=True), counters=cnt, now_lims=[0, 2], future_lims=[1, 3])
+        outs.append(({k: v.clone() for k, v in o.items()}, cnt.clone()))
+        del m
+    (a, ca), (b, cb) = outs
+    for k, tol in (("probs", 2e-6), ("p_now", 2e-6), ("p_future", 2e-6), ("H", 2e-5), ("loss", 2e-5), ("vad", 0.0)):
+        assert (a[k] - b[k]).abs().max().item() <= tol, k
+    assert torch.equal(a["argmax"], b["argmax"]) and torch.equal(ca, cb)
+    assert int(ca[:256].sum()) == 3 * 150

@@ -143,6 +143,7 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_FFN_FUSED")) h->m.ffn_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_TC")) h->m.conv0_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV01")) h->m.conv01 = atoi(v);
+  if (const char* v = getenv("VAPB_HEAD_FUSED")) h->m.head_fused = atoi(v);
   if (const char* v = getenv("VAPB_FP32_TC")) h->m.fp32_tc = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
   if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
@@ -481,14 +482,14 @@ int plan_all(const Model& m, int batch, int64_t n_samples, int mode, CallPlan* c
 
 int run_forward(Model& m, cudaStream_t st, const float* wav, const Geometry& g, int mode, char* ws, float* logits,
                 float* vad_logits, float* vad_sig, cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr,
-                int wav_pcm16 = 0) {
+                int wav_pcm16 = 0, const HeadOut* head = nullptr) {
   const float* comb = nullptr;
   if (mode == VAPB_MODE_FP32 || mode == VAPB_MODE_FP32_TC) {
     if (wav_pcm16) { m.err = "int16 PCM input is read by the 16-bit modes only (vapb_pcm16_to_f32 converts for fp32)"; return VAPB_E_UNSUPPORTED; }
     return forward_fp32(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, nullptr, mode == VAPB_MODE_FP32_TC);
   }
   const int rc = forward_bf16(m, st, wav, g, ws, logits, vad_logits, vad_sig, &comb, mode == VAPB_MODE_FP16, conv_wait,
-                              conv_done, wav_pcm16);
+                              conv_done, wav_pcm16, head);
   return rc == -4 ? VAPB_E_UNSUPPORTED : rc;
 }
 
@@ -530,11 +531,21 @@ int run_items(Model& m, cudaStream_t st, const float* wav, int b0, const Geometr
   float* lse = reinterpret_cast<float*>(ws_all + aux.lse) + r0;
   const float* wav_b0 = o.wav_pcm16 ? reinterpret_cast<const float*>(reinterpret_cast<const int16_t*>(wav) + (long long)b0 * 2 * g.S)
                                     : wav + (long long)b0 * 2 * g.S;
+  // 16-bit modes: the head GEMM produces the probs() outputs itself (k_head_fused.cu); logits reach memory only for
+  // the caller (vapb_probs' logits argument) or the loss kernel
+  const bool fused = o.want_probs && m.head_fused && (mode == VAPB_MODE_BF16 || mode == VAPB_MODE_FP16);
+  HeadOut ho{o.now_lo, o.now_hi, o.fut_lo, o.fut_hi, (o.logits || o.loss) ? lg : nullptr, at(o.probs, r0 * kClasses),
+             at(o.p_now, r0 * 2), at(o.p_future, r0 * 2), at(o.H, r0), o.loss ? lse : nullptr,
+             o.argmax ? o.argmax + r0 : nullptr, o.counters};
   const int rc = run_forward(m, st, wav_b0, g, mode, ws_path, lg, at(o.vad_logits, r0 * 2), vs, conv_wait, conv_done,
-                             o.wav_pcm16);
+                             o.wav_pcm16, fused ? &ho : nullptr);
   if (rc || !o.want_probs) return rc;
   const long long rows = (long long)g.batch * T;
   ProfScope ps(m, st, CAT_HEADS);
+  if (fused) {
+    if (o.loss) m.launches += launch_loss(st, lg, vs, lse, g.batch, (int)T, o.loss + (long long)b0 * (T - 100));
+    return 0;
+  }
   m.launches += launch_probs(st, lg, rows, o.now_lo, o.now_hi, o.fut_lo, o.fut_hi, at(o.probs, r0 * kClasses),
                              at(o.p_now, r0 * 2), at(o.p_future, r0 * 2), at(o.H, r0), o.loss ? lse : nullptr,
                              o.argmax ? o.argmax + r0 : nullptr, o.counters, o.counters ? vs : nullptr);

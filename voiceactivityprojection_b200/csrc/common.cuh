@@ -162,6 +162,13 @@ int launch_probs(cudaStream_t st, const float* logits, long long rows, int now_l
                  uint8_t* argmax, unsigned long long* counters, const float* vad_sig);
 int launch_pcm16_to_f32(cudaStream_t st, const int16_t* pcm, long long n, float* out);  // out[i] = pcm[i] / 32768
 
+// vap_head GEMM fused with softmax / entropy / codebook marginals / arg-max / logsumexp / counters (k_head_fused.cu).
+// x: 16-bit (rows, 256); w: 16-bit [256][256]; every output optional. Returns launches or -1.
+int launch_head_probs(cudaStream_t st, const void* x, const void* w, const float* bias, long long rows, int now_lo,
+                      int now_hi, int fut_lo, int fut_hi, float* logits, float* probs, float* p_now, float* p_future,
+                      float* H, float* lse, uint8_t* argmax, unsigned long long* counters, const float* vad_sig, int n_sm,
+                      std::string* err);
+
 int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, const float* lse, int batch,
                 int T, float* loss);
 

@@ -247,7 +247,7 @@ size_t workspace_bytes_bf16(const Model& m, const Geometry& g) { return make_pla
 
 int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry& g, char* ws, float* logits,
                  float* vad_logits, float* vad_sig, const float**, int fp16, cudaEvent_t conv_wait,
-                 cudaEvent_t conv_done, int wav_pcm16) {
+                 cudaEvent_t conv_done, int wav_pcm16, const HeadOut* head) {
   // wav_pcm16: the buffer holds int16 PCM (same (B, 2, S) layout); only the fused conv0 -> conv1 kernel reads it
   if (wav_pcm16 && (!m.conv01 || (g.S & 1))) {
     m.err = "int16 PCM input needs the fused conv0/conv1 path (VAPB_CONV01=1) and an even n_samples";
@@ -499,7 +499,17 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry
     ProfScope ps(m, st, CAT_HEADS);
     m.launches += launch_vad_head_blocked(st, x_last, w.va_w, w.va_b, g.batch, (int)T, vad_logits, vad_sig);
   }
-  {
+  if (head) {
+    // vap_head fused with softmax, entropy, marginals, arg-max and the counters: the logits stay in TMEM unless asked for
+    if (cx.rc) return cx.rc;
+    ProfScope ps(m, st, CAT_HEADS);
+    std::string err;
+    const int n = launch_head_probs(st, H(p.combb), s.head_w, w.head_b, MB, head->now_lo, head->now_hi, head->fut_lo,
+                                    head->fut_hi, head->logits, head->probs, head->p_now, head->p_future, head->H,
+                                    head->lse, head->argmax, head->counters, vad_sig, m.n_sm, &err);
+    if (n < 0) { m.err = err; return -3; }
+    m.launches += n;
+  } else {
     Epilogue e{};
     e.bias = w.head_b;
     e.out1_map = dense(MB, kClasses);

@@ -74,6 +74,7 @@ struct Model {
   int n_sm = 148;
   int conv_2sm = 1;       // gEncoder convs on CTA pairs (k_gemm_2sm.cu, cta_group::2); env VAPB_CONV_2SM
   int ffn_fused = 1;      // FFN block as one kernel (k_ffn_fused.cu); 0 = two GEMMs (env VAPB_FFN_FUSED)
+  int head_fused = 1;     // vap_head GEMM fused with the probs() epilogue (k_head_fused.cu); env VAPB_HEAD_FUSED
   int conv01 = 1;         // conv0 fused into conv1's operand producer (k_conv01.cu); 0 = separate kernels (env VAPB_CONV01)
   int conv0_tc = 1;       // unfused path: conv0 on the tensor cores (k_conv0_tc.cu); the CUDA-core fallback is gone
   int conv0_sms = 0;      // CTAs of the conv0 kernel (0 = one per SM); env VAPB_CONV0_SMS (tuning / overlap experiments)
@@ -160,13 +161,23 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
                  bool tensor_gemms = false /* VAPB_MODE_FP32_TC: k_gemm_x3.cu for every contraction */);
 int stage_fp32(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
+// Outputs of the fused vap_head + probs kernel for the items of one forward call (pointers address the call's first
+// item; any may be null). Passed to forward_bf16 instead of a logits buffer when the caller wants probs().
+struct HeadOut {
+  int now_lo, now_hi, fut_lo, fut_hi;
+  float *logits, *probs, *p_now, *p_future, *H, *lse;
+  uint8_t* argmax;
+  unsigned long long* counters;
+};
+
 // ---- BF16 tensor-core path (forward_bf16.cu) --------------------------------
 int bf16_prepare(Model& m);   // pack bf16 weights after the fp32 arena is built
 void bf16_release(Model& m);
 size_t workspace_bytes_bf16(const Model& m, const Geometry& g);
 int forward_bf16(Model& m, cudaStream_t st, const float* wav, const Geometry& g, char* ws, float* logits,
                  float* vad_logits, float* vad_sig, const float** comb_out, int fp16,
-                 cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr, int wav_pcm16 = 0);
+                 cudaEvent_t conv_wait = nullptr, cudaEvent_t conv_done = nullptr, int wav_pcm16 = 0,
+                 const HeadOut* head = nullptr);
 int stage_bf16(const Model& m, const Geometry& g, char* ws, const std::string& name, StageRef* ref);
 
 }  // namespace vapb
