@@ -98,6 +98,8 @@ __device__ __forceinline__ bool next_item(const AttnParams& p, int k, Item* it) 
   return true;
 }
 
+// FP16: 16-bit format of Q / K / V / P / out (compile time: a run-time flag made every pack two predicated instructions)
+template <int FP16>
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   } else if (warp == 1) {
     // ===== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_16(128, 128, 0, 0, p.fp16);
-      const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, p.fp16);  // B = V is MN-major (d contiguous)
+      const uint32_t idesc_qk = make_idesc_16(128, 128, 0, 0, FP16);
+      const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, FP16);  // B = V is MN-major (d contiguous)
       uint32_t n_item = 0, kvc[2] = {0, 0}, pc[2] = {0, 0};
       auto issue_qk = [&](int s) {
         const int st = kvc[s] & 1;
@@ -299,7 +301,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         m = m_new;
         // pass B: p = 2^(t - m), partial row sum, P -> TMEM as bf16 pairs (column c holds keys 2c, 2c+1)
         const float base_m = base - m;
-        float ps0 = 0.f, ps1 = 0.f;
+        // packed fp32 arithmetic (FFMA2 / FADD2: one issue slot per two scores): the softmax warps are issue-bound
+        float2 ps2 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(SC, SC), step2 = make_float2(2.f * slope2, 2.f * slope2);
         const int nexp = negligible ? 0 : nvis;
 #pragma unroll 1
         for (int ci = 0; ci < 2; ++ci) {
@@ -309,25 +313,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
             const float cb = fmaf(slope2, (float)(ci * 32), base_m);
+            // bias of the key pair (i, i + 1), stepped by 2 * slope per pair (no per-element constant to materialise)
+            float2 bias2 = make_float2(cb, cb + slope2);
             if (diag && g0 + ci == quad) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb)));
-                float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
-                if (i > lane) p0 = 0.f;
+                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
+                bias2 = __fadd2_rn(bias2, step2);
+                float p0 = ex2_fast(t.x), p1 = ex2_fast(t.y);
+                if (i > lane) p0 = 0.f;  // keys above the diagonal
                 if (i + 1 > lane) p1 = 0.f;
-                ps0 += p0;
-                ps1 += p1;
-                pk[i >> 1] = pack16(p0, p1, p.fp16);
+                ps2 = __fadd2_rn(ps2, make_float2(p0, p1));
+                pk[i >> 1] = pack16(p0, p1, FP16);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), SC, fmaf(slope2, (float)i, cb)));
-                const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), SC, fmaf(slope2, (float)(i + 1), cb)));
-                ps0 += p0;
-                ps1 += p1;
-                pk[i >> 1] = pack16(p0, p1, p.fp16);
+                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
+                bias2 = __fadd2_rn(bias2, step2);
+                const float p0 = ex2_fast(t.x), p1 = ex2_fast(t.y);
+                ps2 = __fadd2_rn(ps2, make_float2(p0, p1));
+                pk[i >> 1] = pack16(p0, p1, FP16);
               }
             }
           } else {
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           }
           tmem_st16(t_p + ci * 16, pk);
         }
+        const float ps0 = ps2.x, ps1 = ps2.y;
         l += ps0 + ps1;
         tmem_st_wait();
         tc_fence_before();
@@ -361,10 +368,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 u;
-            u.x = pack16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv, p.fp16);
-            u.y = pack16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv, p.fp16);
-            u.z = pack16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv, p.fp16);
-            u.w = pack16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv, p.fp16);
+            u.x = pack16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv, FP16);
+            u.y = pack16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv, FP16);
+            u.z = pack16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv, FP16);
+            u.w = pack16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv, FP16);
             *reinterpret_cast<uint4*>(dst + 8 * i) = u;
           }
         }
@@ -418,14 +425,16 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
   cudaGetDevice(&cur_dev);
   bool& configured = configured_on[cur_dev & 63];
   if (!configured) {
-    if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {
       if (err) *err = "attention_tc: cannot reserve shared memory";
       return -1;
     }
     configured = true;
   }
   const int grid = p.n_items < n_sm ? p.n_items : n_sm;
-  launch_pdl(attention_tc_kernel, grid, AT_THREADS, AT_SMEM, st, p);
+  if (g_fp16) launch_pdl(attention_tc_kernel<1>, grid, AT_THREADS, AT_SMEM, st, p);
+  else launch_pdl(attention_tc_kernel<0>, grid, AT_THREADS, AT_SMEM, st, p);
   return 1;
 }
 
