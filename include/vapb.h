@@ -260,6 +260,10 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
  * of the result become 0. out may alias vad01. `h` may be NULL. */
 int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, int64_t T, int max_fill_frames,
                     int max_omit_frames, float* out);
+/* The same with the threshold of VapGPT.vad (vap/model.py:237-238) inside the kernel: from_logits != 0 means `vad`
+ * holds the model's VAD logits and a frame is active when sigmoid(logit) >= cutoff. */
+int vapb_vad_filter_ex(VapbHandle* h, void* stream, const float* vad, int from_logits, float cutoff, int batch,
+                       int64_t T, int max_fill_frames, int max_omit_frames, float* out);
 
 /* ZeroShot next-speaker / backchannel marginals: replaces ZeroShot.get_probs,
  * probs_next_speaker, probs_on_silence, probs_on_active and probs_backchannel (vap/zero_shot.py:159-271) with one

@@ -119,8 +119,10 @@ def test_load_waveform_int16_scaling_and_resample(tmp_path):
     pcm = (rng.standard_normal(24000) * 3000).astype(np.int16)
     p = str(tmp_path / "a.wav")
     wavfile.write(p, 24000, pcm)
-    x, sr = load_waveform(p)
+    x, sr = load_waveform(p, sample_rate=None)
     assert sr == 24000 and x.shape == (1, 24000)
+    d, sr = load_waveform(p)  # the reference's default: resampled to 16 kHz (vap/audio.py:41)
+    assert sr == 16000 and d.shape == (1, 16000)
     assert torch.equal(x[0], torch.from_numpy(pcm.astype(np.float32)) / 32768.0)
     y, sr = load_waveform(p, sample_rate=16000)
     assert sr == 16000 and y.shape == (1, 16000)
@@ -129,7 +131,7 @@ def test_load_waveform_int16_scaling_and_resample(tmp_path):
     wavfile.write(p, 16000, st)
     z, _ = load_waveform(p, sample_rate=16000)
     assert z.shape == (2, 24000) and torch.equal(z[0], -z[1])
-    zm, _ = load_waveform(p, mono=True)
+    zm, _ = load_waveform(p, None, None, None, True)  # positional order of the reference: ..., end_time, mono
     assert zm.shape == (1, 24000) and zm.abs().max() == 0
 
 

@@ -56,9 +56,11 @@ def get_audio_info(audio_path: str) -> Dict[str, Any]:
             "bits_per_sample": 8 * width, "num_channels": ch, "encoding": "PCM_U" if width == 1 else "PCM_S"}
 
 
-def load_waveform(path: str, sample_rate: Optional[int] = None, start_time: Optional[float] = None,
-                  end_time: Optional[float] = None, normalize: bool = False, mono: bool = False,
+def load_waveform(path: str, sample_rate: Optional[int] = 16000, start_time: Optional[float] = None,
+                  end_time: Optional[float] = None, mono: bool = False, *, normalize: bool = False,
                   audio_normalize_threshold: float = 0.05, device=None) -> Tuple[Tensor, int]:
+    """vap/audio.py:39-69: same positional parameters and the same default (resample to 16 kHz; sample_rate=None keeps
+    the file's rate). normalize / audio_normalize_threshold / device are keyword-only extras."""
     x, sr = _read_wav(path)
     if start_time is not None or end_time is not None:
         s = time_to_samples(start_time, sr) if start_time is not None else 0

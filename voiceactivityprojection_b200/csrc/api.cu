@@ -1018,12 +1018,18 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
 
 int vapb_vad_filter(VapbHandle* h, void* stream, const float* vad01, int batch, int64_t T, int max_fill_frames,
                     int max_omit_frames, float* out) {
+  return vapb_vad_filter_ex(h, stream, vad01, 0, 0.5f, batch, T, max_fill_frames, max_omit_frames, out);
+}
+
+int vapb_vad_filter_ex(VapbHandle* h, void* stream, const float* vad01, int from_logits, float cutoff, int batch, int64_t T,
+                       int max_fill_frames, int max_omit_frames, float* out) {
   if (!vad01 || !out || batch < 0 || T < 0 || T > 0x3fffffff || max_fill_frames < 0 || max_omit_frames < 0) {
     if (h) h->m.err = "vad_filter: invalid argument"; else g_create_err = "vad_filter: invalid argument";
     return VAPB_E_INVALID;
   }
   if (h) cudaSetDevice(h->m.device);
-  const int n = launch_vad_filter((cudaStream_t)stream, vad01, batch, (int)T, max_fill_frames, max_omit_frames, out);
+  const int n = launch_vad_filter((cudaStream_t)stream, vad01, batch, (int)T, max_fill_frames, max_omit_frames, out,
+                                  from_logits, cutoff);
   if (h) h->m.launches += n;
   return cudaPeekAtLastError() == cudaSuccess ? VAPB_OK : VAPB_E_CUDA;
 }

@@ -151,7 +151,8 @@ int launch_vad_head(cudaStream_t st, const float* x /*[2B][T][256] channel-major
 int launch_resample(cudaStream_t st, const void* x, int x_fmt, long long items, int channels, long long n_in,
                     long long item_stride, long long chan_stride, long long elem_stride, int orig, int new_, int width,
                     const float* bank, float* out, long long n_out, long long out_row_stride, std::string* err);
-int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out);
+int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out,
+                      int from_logits = 0, float cutoff = 0.5f);
 int launch_zero_shot(cudaStream_t st, const float* x, int is_probs, long long batch, int T, const float* va,
                      long long va_T, const uint32_t* sets /* host [10][8] */, float* p, float* p_bc, float* p_sil,
                      float* p_act);

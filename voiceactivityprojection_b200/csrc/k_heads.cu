@@ -305,16 +305,19 @@ int launch_loss(cudaStream_t st, const float* logits, const float* vad_sig, cons
 // frames of the RESULT becomes silence (vad_omit_spikes). One thread per (item, channel) sequence: 2 x T sequential
 // steps on 8 KB of data per item is microseconds, and the reference's per-run Python loop is what this replaces.
 __global__ void __launch_bounds__(128)
-vad_filter_kernel(const float* vad, int nseq, int T, int max_fill, int max_omit, float* out) {  // out may alias vad
+vad_filter_kernel(const float* vad, int nseq, int T, int max_fill, int max_omit, float* out, int from_logits,
+                  float cutoff) {  // out may alias vad
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseq) return;
   const float* x = vad + (long long)(s >> 1) * T * 2 + (s & 1);
   float* y = out + (long long)(s >> 1) * T * 2 + (s & 1);
+  // from_logits: the input holds VAD logits; active = sigmoid(x) >= cutoff (vap/model.py:237-238, the sigmoid of vad_head_kernel)
+  auto on = [&](float v) { return from_logits ? (1.0f / (1.0f + expf(-v))) >= cutoff : v != 0.f; };
   // pass 1: fill short silences (reads x, writes y; in place is fine: a run is rewritten after it has been read)
   int run0 = 0;
-  bool cur = T > 0 && x[0] != 0.f;
+  bool cur = T > 0 && on(x[0]);
   for (int t = 1; t <= T; ++t) {
-    const bool v = t < T ? (x[2LL * t] != 0.f) : !cur;
+    const bool v = t < T ? on(x[2LL * t]) : !cur;
     if (v != cur) {
       const float w = (cur || t - run0 <= max_fill) ? 1.f : 0.f;
       for (int k = run0; k < t; ++k) y[2LL * k] = w;
@@ -336,10 +339,11 @@ vad_filter_kernel(const float* vad, int nseq, int T, int max_fill, int max_omit,
   }
 }
 
-int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out) {
+int launch_vad_filter(cudaStream_t st, const float* vad01, int batch, int T, int max_fill, int max_omit, float* out,
+                      int from_logits, float cutoff) {
   const int nseq = batch * 2;
   if (nseq <= 0 || T <= 0) return 0;
-  vad_filter_kernel<<<(unsigned)((nseq + 127) / 128), 128, 0, st>>>(vad01, nseq, T, max_fill, max_omit, out);
+  vad_filter_kernel<<<(unsigned)((nseq + 127) / 128), 128, 0, st>>>(vad01, nseq, T, max_fill, max_omit, out, from_logits, cutoff);
   return 1;
 }
 

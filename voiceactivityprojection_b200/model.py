@@ -400,23 +400,25 @@ class VapGPT(nn.Module):
     @torch.no_grad()
     def vad(self, waveform: Tensor, max_fill_silence_time: float = 0.02, max_omit_spike_time: float = 0.02,
             vad_cutoff: float = 0.5) -> Tensor:
-        """vap/model.py:227-247."""
-        v = (self(waveform)["vad"].sigmoid() >= vad_cutoff).float()
-        return self.vad_filter(v, max_fill_silence_time, max_omit_spike_time)
+        """vap/model.py:227-247: sigmoid, threshold and both run-length filters in one kernel on the model's VAD logits."""
+        return self.vad_filter(self(waveform)["vad"], max_fill_silence_time, max_omit_spike_time, logits_cutoff=vad_cutoff)
 
-    def vad_filter(self, vad01: Tensor, max_fill_silence_time: float = 0.02, max_omit_spike_time: float = 0.02
-                   ) -> Tensor:
+    def vad_filter(self, vad01: Tensor, max_fill_silence_time: float = 0.02, max_omit_spike_time: float = 0.02,
+                   logits_cutoff: Optional[float] = None) -> Tensor:
         """vad_fill_silences then vad_omit_spikes (vap/utils.py:239-272) for every item of a binary (B, T, 2)
-        CUDA tensor, in place, in one kernel (vapb_vad_filter) instead of the reference's per-run Python loops."""
+        CUDA tensor, in place, in one kernel (vapb_vad_filter) instead of the reference's per-run Python loops.
+        logits_cutoff: the tensor holds VAD logits; a frame is active when sigmoid(logit) >= logits_cutoff."""
         if vad01.device.type != "cuda":
             raise RuntimeError("vad_filter needs a CUDA tensor (no CPU fallback); utils.vad_fill_silences works on the host")
         assert vad01.ndim == 3 and vad01.shape[-1] == 2 and vad01.dtype == torch.float32 and vad01.is_contiguous()
         lib, h = _lib.load(), self._ensure_handle()
         st = torch.cuda.current_stream(vad01.device).cuda_stream
         if vad01.numel():
-            _lib.check(lib, h, lib.vapb_vad_filter(h, st, vad01.data_ptr(), vad01.shape[0], vad01.shape[1],
-                                                   round(max_fill_silence_time * self.frame_hz),
-                                                   round(max_omit_spike_time * self.frame_hz), vad01.data_ptr()))
+            _lib.check(lib, h, lib.vapb_vad_filter_ex(h, st, vad01.data_ptr(), int(logits_cutoff is not None),
+                                                      0.5 if logits_cutoff is None else float(logits_cutoff),
+                                                      vad01.shape[0], vad01.shape[1],
+                                                      round(max_fill_silence_time * self.frame_hz),
+                                                      round(max_omit_spike_time * self.frame_hz), vad01.data_ptr()))
         return vad01
 
     # ------------------------------------------------------------------ diagnostics
