@@ -18,7 +18,7 @@ buf = torch.randn((nseq, T, 768), device="cuda", generator=g).bfloat16()
 q, k, v = buf[..., :256], buf[..., 256:512], buf[..., 512:]
 out = torch.empty((nseq, T, 256), device="cuda", dtype=torch.bfloat16)
 slopes = torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda")
-dbg = torch.zeros((64, 8), device="cuda", dtype=torch.int64)
+dbg = torch.zeros((128, 8), device="cuda", dtype=torch.int64)
 err = C.create_string_buffer(512)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(2):
@@ -34,3 +34,21 @@ for i in range(1, 40):
     nxt = int(d[i + 1, 0])
     print(f"{i:3d} | {r[1]-r[0]:6d} {r[2]-r[1]:6d} {r[3]-r[2]:6d} {r[4]-r[3]:6d} | {r[4]-r[0]:6d} | {r[6]-r[5]:6d} {r[7]-r[6]:6d} | {nxt-r[0]:6d}"
           f" | abs sm {r[0]-t0:7d} mma {r[5]-t0:7d}")
+print("item epilogue (slot 0): head_bar  o_final waits  O loads  head_bar  stores | to next item's epilogue start")
+for i in range(0, 30):
+    a = [int(x) for x in d[64 + i]]
+    nx = int(d[64 + i + 1, 0])
+    print(f"{i:3d} | {a[1]-a[0]:6d} {a[2]-a[1]:6d} {a[3]-a[2]:6d} {a[4]-a[3]:6d} {a[5]-a[4]:6d} | {nx-a[0]:7d}")
+# kernel time without the probe (CUDA events on the launching stream)
+null = 0
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for _ in range(3):
+    lib.vapb_debug_attn_tc(st, q.data_ptr(), 768, k.data_ptr(), v.data_ptr(), 768, out.data_ptr(), nseq, T, 4,
+                           slopes.data_ptr(), 0, err, 512, null)
+ev[0].record()
+for _ in range(10):
+    lib.vapb_debug_attn_tc(st, q.data_ptr(), 768, k.data_ptr(), v.data_ptr(), 768, out.data_ptr(), nseq, T, 4,
+                           slopes.data_ptr(), 0, err, 512, null)
+ev[1].record()
+torch.cuda.synchronize()
+print("kernel us (self, nseq=512, T=1000):", ev[0].elapsed_time(ev[1]) * 100)
