@@ -28,17 +28,17 @@ for _ in range(2):
 torch.cuda.synchronize()
 d = dbg.cpu()
 t0 = int(d[0, 0])
-print("tile | sm: wait_s_full  maxpass  xchg_bar  expstore+arrive | total | mma: wait_p_full  issue | softmax start->next start")
+print("tile | sm: wait_s_full  single pass  exchange  (exact route +) arrive | total | mma: wait_p_full  issue | softmax start->next start")
 for i in range(1, 40):
     r = [int(x) for x in d[i]]
     nxt = int(d[i + 1, 0])
     print(f"{i:3d} | {r[1]-r[0]:6d} {r[2]-r[1]:6d} {r[3]-r[2]:6d} {r[4]-r[3]:6d} | {r[4]-r[0]:6d} | {r[6]-r[5]:6d} {r[7]-r[6]:6d} | {nxt-r[0]:6d}"
           f" | abs sm {r[0]-t0:7d} mma {r[5]-t0:7d}")
-print("item epilogue (slot 0): head_bar  o_final waits  O loads  head_bar  stores | to next item's epilogue start")
-for i in range(0, 30):
+print("mma thread: kv wait  QK issue  PV issue | softmax: chunk0 compute (s_full -> before pv wait)  pv wait")
+for i in range(1, 40):
     a = [int(x) for x in d[64 + i]]
-    nx = int(d[64 + i + 1, 0])
-    print(f"{i:3d} | {a[1]-a[0]:6d} {a[2]-a[1]:6d} {a[3]-a[2]:6d} {a[4]-a[3]:6d} {a[5]-a[4]:6d} | {nx-a[0]:7d}")
+    r = [int(x) for x in d[i]]
+    print(f"{i:3d} | {a[1]-a[0]:6d} {a[2]-a[1]:6d} {a[3]-a[2]:6d} | {a[4]-r[1]:6d} {a[5]-a[4]:6d}")
 # kernel time without the probe (CUDA events on the launching stream)
 null = 0
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]

@@ -4,27 +4,40 @@
 // Self- and cross-attention share the kernel; cross-attention reads K/V rows of the
 // other speaker channel's sequence (vap/modules.py:287-289).
 //
-// Work item = (sequence, head pair, 128-query tile). One persistent CTA per SM walks the
-// items from the longest (last query tile) to the shortest. An item runs as FOUR independent
-// chains ("slots"): slot = (head of the pair, key parity). The keys of a head are cut into
-// 64-key half tiles; the even ones belong to one slot and the odd ones to the other, each with
-// its own running maximum, row sum and O accumulator (split-K as in flash decoding), merged
-// once per item. A slot's chain is  QK^T -> softmax -> PV -> QK^T of its next half tile;
-// nothing in it waits for another slot (no exchange barrier: a softmax thread owns a whole
-// 64-key row), so four chains overlap each other's tensor-pipe, MUFU and barrier latencies.
-// Round-2 timeline (tools/attn_probe.py) of the two-slot version this replaces: every softmax
-// warp waited 2300 of 3300 clk for its S tile because one issuing thread served both slots
-// and a PV with its A operand in TMEM blocks the issuer for ~600 clk.
+// Work item = (sequence, head, 128-query tile). A persistent CTA per SM runs TWO independent
+// pipelines ("slots"), each with its own TMA producer thread, MMA issuing thread, eight softmax
+// warps, buffers and item list (all query tiles of one (sequence, head) back to back, longest
+// first, so its K/V re-reads hit L2). While the softmax warps of one slot are on the CUDA cores,
+// the other slot's QK^T and PV are on the tensor pipe; nothing in a slot's chain
+//   QK^T -> softmax -> PV -> QK^T of the next key tile
+// waits for the other slot.
 //
-// Per slot and 64-key half tile (visited from the diagonal DOWN to key 0: the ALiBi bias grows
-// with the key index, so the running row maximum is almost always set by the first tile and the
-// accumulator rescale below is rare):
-//   S[128 q][64 k]   = Q K^T      tcgen05.mma, Q and K tiles K-major SW128 in smem (TMA)
-//   softmax          : one thread per query row (TMEM lane); two passes over S with
-//                      tcgen05.ld (row max, then exp2 / row sum); P is written back over the
-//                      first half of S as packed 16-bit pairs
+// Per slot and 128-key tile (visited from the diagonal DOWN to key 0: the ALiBi bias grows with
+// the key index, so the first tile almost always sets the row maximum):
+//   S[128 q][128 k]  = Q K^T      tcgen05.mma, Q and K tiles K-major SW128 in smem (TMA)
+//   softmax          : a thread owns half a query row (64 keys; warps 4 apart share a TMEM lane
+//                      quadrant). S is read with tcgen05.ld ONCE: p = 2^(t - m) against the
+//                      running reference m (softmax is shift-invariant, m need not be the exact
+//                      maximum), the tile maximum is tracked on the side, and only the first tile
+//                      of an item - or a tile that beats m by more than 8 binades - takes the exact
+//                      two-pass route. P goes back to TMEM as packed 16-bit pairs.
 //   O[128 q][64 d]  += P V        tcgen05.mma, A = P from TMEM, B = V tile MN-major SW128
-// The T x T score matrix never exists; O stays in TMEM for the whole row of tiles.
+// QK^T of the NEXT tile is issued before PV of the current one (it only needs S), so the softmax
+// warps are back at work while PV is still on the tensor pipe; they wait for it (pv_done) before
+// they overwrite P or rescale O. The T x T score matrix never exists; O stays in TMEM for the
+// whole row of tiles.
+//
+// What bounds it (tools/attn_probe.py, tools/attn_time.py, round 2): TMEM READ bandwidth,
+// 64 B/clk/SM. The first version read S twice (2 x 64 KB per tile) and fed P to the PV MMAs from
+// TMEM (32 KB per tile): 160 KB per tile = 2500 clk = its measured time per tile, while the MUFU
+// (1024 clk), the tensor pipe (~900 clk: an MMA costs >= 64 clk per K16 step whatever N <= 128
+// is, the A operand streams) and shared memory were each under half of that. One pass over S
+// brings it to 96 KB = 1500 clk per tile (measured ~1700 in steady state). Variants measured on
+// the same box (630 us for the two-pass kernel at 512 sequences x 1000 frames, 594 us for this
+// one): P through shared memory instead of TMEM 645-660 us and half of P each way 631 us (the
+// SS-mode PV MMAs and the P stores contend with the K/V/Q operand traffic in shared memory);
+// the keys of a head split over two more slots with 64-key tiles 578-656 us (twice the K16 steps:
+// tensor-pipe-bound).
 #include <string>
 
 #include "common.cuh"
@@ -36,23 +49,22 @@ using namespace tc;
 
 namespace {
 
-constexpr int AT_QTILE = 128 * 64 * 2;  // 128 query rows x 64 d of one head, 16-bit
-constexpr int AT_KTILE = 64 * 64 * 2;   // 64 keys x 64 d of one head (K or V half tile)
-// warp 0 / 1: TMA producer of head 0 / 1 of the pair; warps 2, 3, 20, 21: MMA issuer of slot 0..3 (warp 2 also owns
-// the TMEM allocation); warps 4-19: softmax, four warps (= the four TMEM lane quadrants) per slot.
-constexpr int AT_THREADS = 704;
-constexpr int AT_OFF_Q = 0;                          // [head][2 buffers]
-constexpr int AT_OFF_K = 4 * AT_QTILE;               // [slot][2 stages]
-constexpr int AT_OFF_V = AT_OFF_K + 8 * AT_KTILE;    // [slot][2 stages]
-constexpr int AT_OFF_X = AT_OFF_V + 8 * AT_KTILE;    // (m, l) exchange of the merge: float2 [slot][128]
-constexpr int AT_OFF_BAR = AT_OFF_X + 4 * 128 * 8;
-constexpr int AT_SMEM = AT_OFF_BAR + 512 + 1024 /*alignment slack*/;
-// TMEM columns of a slot: S fp32 [0,64) with P (16-bit pairs) written over [0,32); O fp32 [64,128)
-constexpr int AT_COL_O = 64, AT_SLOT_COLS = 128;
+constexpr int AT_TILE = 128 * 64 * 2;  // one 128-row x 64-column 16-bit tile (Q, K or V of one head)
+// warp 0 / 1: TMA producer of slot 0 / 1; warp 2 / 3: MMA issuer of slot 0 / 1 (warp 2 also owns the TMEM allocation);
+// warps 4-11 softmax of slot 0, 12-19 of slot 1
+constexpr int AT_THREADS = 640;
+constexpr int AT_OFF_Q = 0;                         // [slot] (one buffer: released by the item's last QK)
+constexpr int AT_OFF_K = 2 * AT_TILE;               // [slot][2 stages]
+constexpr int AT_OFF_V = AT_OFF_K + 4 * AT_TILE;    // [slot][2 stages]
+constexpr int AT_OFF_X = AT_OFF_V + 4 * AT_TILE;    // exchange between the two half-row threads: float [slot][half][128]
+constexpr int AT_OFF_BAR = AT_OFF_X + 2 * 2 * 128 * 4;
+constexpr int AT_SMEM = AT_OFF_BAR + 320 + 1024 /*alignment slack*/;
+// TMEM columns of a slot: S fp32 [0,128), P 16-bit pairs [128,192), O fp32 [192,256)
+constexpr int AT_COL_P = 128, AT_COL_O = 192, AT_SLOT_COLS = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct alignas(64) AttnParams {
-  CUtensorMap tq, tk, tv;  // (256 head*d, T, nseq) 16-bit, SW128; box (64, 128, 1) for Q, (64, 64, 1) for K and V
+  CUtensorMap tq, tk, tv;  // (256 head*d, T, nseq) 16-bit, SW128; box (64, 128, 1)
   __nv_bfloat16* out;      // (nseq*T, 256)
   const float* slopes;     // [n_heads]
   int nseq, T, nqt, n_items, cross;  // n_items = (sequence, head, query tile) triples
@@ -85,8 +97,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 struct Item {
   int qi, seq, head;
 };
-// k-th work item of pipeline h (= head slot pair: two of the CTA's four slots) of this CTA; false when it is done.
-// The two pipelines of a CTA are independent (own producer, issuers, softmax warps, Q buffers), so the schedule is over
+// k-th work item of pipeline h (= slot) of this CTA; false when it is done.
+// The two pipelines of a CTA are independent (own producer, issuer, softmax warps, buffers), so the schedule is over
 // 2 * gridDim.x pipelines. The head of a unit rotates with the round: the steep ALiBi heads skip most far tiles, and a
 // pipeline that always drew the same head would finish long before (or after) the others.
 __device__ __forceinline__ bool next_item(const AttnParams& p, int k, int h, Item* it) {
@@ -115,16 +127,18 @@ template <int FP16>
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + AT_OFF_BAR;
-  auto q_full = [&](int h, int b) { return bar_base + 8u * (h * 2 + b); };
-  auto q_empty = [&](int h, int b) { return bar_base + 8u * (4 + h * 2 + b); };
-  auto kv_full = [&](int sl, int st) { return bar_base + 8u * (8 + sl * 2 + st); };
-  auto kv_empty = [&](int sl, int st) { return bar_base + 8u * (16 + sl * 2 + st); };
-  auto s_full = [&](int sl) { return bar_base + 8u * (24 + sl); };
-  auto p_full = [&](int sl) { return bar_base + 8u * (28 + sl); };
-  auto o_final = [&](int sl) { return bar_base + 8u * (32 + sl); };
-  const uint32_t tmem_slot = bar_base + 8u * 36;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + AT_OFF_BAR;
+  auto q_full = [&](int s) { return bar_base + 8u * s; };
+  auto q_empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto kv_full = [&](int s, int st) { return bar_base + 8u * (4 + s * 2 + st); };
+  auto kv_empty = [&](int s, int st) { return bar_base + 8u * (8 + s * 2 + st); };
+  auto s_full = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto p_full = [&](int s) { return bar_base + 8u * (14 + s); };
+  auto o_final = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto pv_done = [&](int s) { return bar_base + 8u * (18 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 20;
+  float* slope_s = reinterpret_cast<float*>(smem_gen + AT_OFF_BAR + 8 * 22);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
 
@@ -132,23 +146,21 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     prefetch_tmap(&p.tq);
     prefetch_tmap(&p.tk);
     prefetch_tmap(&p.tv);
-    for (int h = 0; h < 2; ++h)
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(q_full(h, b), 1);
-        mbar_init(q_empty(h, b), 2);  // released by the last PV of both slots of the head
-      }
-    for (int sl = 0; sl < 4; ++sl) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
       for (int st = 0; st < 2; ++st) {
-        mbar_init(kv_full(sl, st), 1);
-        mbar_init(kv_empty(sl, st), 1);
+        mbar_init(kv_full(s, st), 1);
+        mbar_init(kv_empty(s, st), 1);
       }
-      mbar_init(s_full(sl), 1);
-      mbar_init(p_full(sl), 128);
-      mbar_init(o_final(sl), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 256);
+      mbar_init(o_final(s), 1);
+      mbar_init(pv_done(s), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 3 && lane < 4) reinterpret_cast<float*>(smem_gen + AT_OFF_BAR + 8 * 38)[lane] = p.slopes[lane];
+  if (warp == 3 && lane < 4) slope_s[lane] = p.slopes[lane];  // weights: not written by the preceding kernel
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -158,148 +170,161 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
   pdl_wait();
 
   if (warp < 2) {
-    // ===== TMA producer of head `warp` of the pair: the head's Q tile and the K/V half tiles of its two slots.
-    // The Q tile of the NEXT item goes behind the first K/V half tiles of the current one: its buffer is released
-    // by the end of the previous item, and waiting for that before any K/V request would drain the K/V ring at
-    // every item boundary.
+    // ===== TMA producer of slot `warp`
     if (lane == 0) {
-      const int h = warp;
-      uint32_t kvc = 0;  // half-tile steps issued (the two slots of a head move together)
+      const int s = warp;
+      uint32_t kvc = 0;
       auto load_q = [&](const Item& it, uint32_t n) {
-        const int b = n & 1;
-        mbar_wait(q_empty(h, b), ((n >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(q_full(h, b), AT_QTILE);
-        tma_load_3d(smem_base + AT_OFF_Q + (h * 2 + b) * AT_QTILE, &p.tq, q_full(h, b), it.head * 64,
-                    it.qi * 128, it.seq);
+        mbar_wait(q_empty(s), (n & 1u) ^ 1u);
+        mbar_arrive_expect_tx(q_full(s), AT_TILE);
+        tma_load_3d(smem_base + AT_OFF_Q + s * AT_TILE, &p.tq, q_full(s), it.head * 64, it.qi * 128, it.seq);
       };
       Item it, nx;
-      bool have = next_item(p, 0, h, &it);
+      bool have = next_item(p, 0, s, &it);
       if (have) load_q(it, 0);
       for (uint32_t k = 0; have; ++k) {
-        const bool have_next = next_item(p, (int)k + 1, h, &nx);
+        const bool have_next = next_item(p, (int)k + 1, s, &nx);
         const int kvseq = p.cross ? (it.seq + p.nseq / 2) % p.nseq : it.seq;
         const int col = it.head * 64;
         for (int kt = it.qi; kt >= 0; --kt) {
           const int st = kvc & 1;
-          const uint32_t par = ((kvc >> 1) & 1u) ^ 1u;
+          mbar_wait(kv_empty(s, st), ((kvc >> 1) & 1u) ^ 1u);
           ++kvc;
-          for (int kp = 0; kp < 2; ++kp) {
-            const int sl = h * 2 + kp;
-            mbar_wait(kv_empty(sl, st), par);
-            mbar_arrive_expect_tx(kv_full(sl, st), 2 * AT_KTILE);
-            tma_load_3d(smem_base + AT_OFF_K + (sl * 2 + st) * AT_KTILE, &p.tk, kv_full(sl, st), col,
-                        (2 * kt + kp) * 64, kvseq);
-            tma_load_3d(smem_base + AT_OFF_V + (sl * 2 + st) * AT_KTILE, &p.tv, kv_full(sl, st), col,
-                        (2 * kt + kp) * 64, kvseq);
-          }
-          if (kt == it.qi && have_next) load_q(nx, k + 1);
+          mbar_arrive_expect_tx(kv_full(s, st), 2 * AT_TILE);
+          tma_load_3d(smem_base + AT_OFF_K + (s * 2 + st) * AT_TILE, &p.tk, kv_full(s, st), col, kt * 128, kvseq);
+          tma_load_3d(smem_base + AT_OFF_V + (s * 2 + st) * AT_TILE, &p.tv, kv_full(s, st), col, kt * 128, kvseq);
         }
+        // the Q buffer is released by the item's last QK, about one tile before the item ends: the next Q tile lands
+        // behind that tile's softmax and PV
+        if (have_next) load_q(nx, k + 1);
         it = nx;
         have = have_next;
       }
     }
-  } else if (warp == 2 || warp == 3 || warp >= 20) {
-    // ===== MMA issuers, one thread per slot. Each walks its slot's chain p_full -> PV -> QK of the next half tile
-    // on its own; tcgen05.commit tracks the issuing thread's own MMAs, so the chains only meet in the tensor pipe.
+  } else if (warp < 4) {
+    // ===== MMA issuer of slot `warp - 2`. tcgen05.commit tracks the issuing thread's own MMAs, so the two slots'
+    // chains only meet in the tensor pipe's queue.
     if (lane == 0) {
-      const int sl = warp < 4 ? warp - 2 : warp - 18, h = sl >> 1;
-      const uint32_t idesc_qk = make_idesc_16(128, 64, 0, 0, FP16);
+      const int s = warp - 2;
+      const uint32_t idesc_qk = make_idesc_16(128, 128, 0, 0, FP16);
       const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, FP16);  // B = V is MN-major (d contiguous)
-      const uint32_t t_slot = tmem_base + sl * AT_SLOT_COLS;
-      uint32_t n_item = 0, kvc = 0, pc = 0;
-      auto issue_qk = [&]() {
-        const int st = kvc & 1;
-        mbar_wait(kv_full(sl, st), (kvc >> 1) & 1u);
+      const uint32_t t_slot = tmem_base + s * AT_SLOT_COLS;
+      const uint32_t qa = smem_base + AT_OFF_Q + s * AT_TILE;
+      uint32_t n_item = 0, kq = 0, kpv = 0, pc = 0;  // kq / kpv: key tiles whose QK / PV has been issued
+      auto issue_qk = [&](long long* stamp = nullptr) {
+        const int st = kq & 1;
+        mbar_wait(kv_full(s, st), (kq >> 1) & 1u);
+        if (stamp) *stamp = clock64();
+        ++kq;
         tc_fence_after();
-        const uint32_t qa = smem_base + AT_OFF_Q + (h * 2 + (n_item & 1)) * AT_QTILE;
-        const uint32_t ka = smem_base + AT_OFF_K + (sl * 2 + st) * AT_KTILE;
+        const uint32_t ka = smem_base + AT_OFF_K + (s * 2 + st) * AT_TILE;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(t_slot, make_smem_desc_sw128(qa + k * 32, 0, 1024), make_smem_desc_sw128(ka + k * 32, 0, 1024),
                     idesc_qk, k != 0);
-        umma_commit(s_full(sl));
+        umma_commit(s_full(s));
       };
       Item it;
-      for (int k = 0; next_item(p, k, h, &it); ++k, ++n_item) {
+      for (int k = 0; next_item(p, k, s, &it); ++k, ++n_item) {
         const int ntiles = it.qi + 1;
-        mbar_wait(q_full(h, n_item & 1), (n_item >> 1) & 1u);
+        mbar_wait(q_full(s), n_item & 1u);
         issue_qk();
+        if (ntiles == 1) umma_commit(q_empty(s));
         for (int n = 0; n < ntiles; ++n) {
-          const bool dbg = p.dbg && blockIdx.x == 0 && sl == 0 && pc >= 40 && pc < 104;
+          const bool dbg = p.dbg && blockIdx.x == 0 && s == 0 && pc >= 40 && pc < 104;
           if (dbg) p.dbg[(pc - 40) * 8 + 5] = clock64();
-          mbar_wait(p_full(sl), pc & 1u);
+          mbar_wait(p_full(s), pc & 1u);
           if (dbg) p.dbg[(pc - 40) * 8 + 6] = clock64();
           ++pc;
           tc_fence_after();
-          const int st = kvc & 1;
-          const uint32_t va = smem_base + AT_OFF_V + (sl * 2 + st) * AT_KTILE;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_ts(t_slot + AT_COL_O, t_slot + kk * 8, make_smem_desc_sw128(va + kk * 2048, 1024, 1024), idesc_pv,
-                         (n | kk) != 0);
-          umma_commit(kv_empty(sl, st));
-          ++kvc;
-          if (dbg) p.dbg[(pc - 41) * 8 + 7] = clock64();
+          // QK of the NEXT tile goes first: it only needs S (free: every softmax thread has read it), and the softmax
+          // warps can start on it while this tile's PV is still on the tensor pipe. They wait for pv_done before they
+          // overwrite P or touch O.
+          long long* d2 = dbg ? p.dbg + 512 + (pc - 41) * 8 : nullptr;
+          if (dbg) d2[0] = clock64();
           if (n + 1 < ntiles) {
-            issue_qk();
-          } else {
-            umma_commit(q_empty(h, n_item & 1));
-            umma_commit(o_final(sl));
+            issue_qk(dbg ? d2 + 1 : nullptr);
+            if (n + 2 == ntiles) umma_commit(q_empty(s));  // that was the item's last QK
           }
+          if (dbg) d2[2] = clock64();
+          const int st = kpv & 1;
+          ++kpv;
+          const uint32_t va = smem_base + AT_OFF_V + (s * 2 + st) * AT_TILE;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(t_slot + AT_COL_O, t_slot + AT_COL_P + kk * 8, make_smem_desc_sw128(va + kk * 2048, 1024, 1024),
+                         idesc_pv, (n | kk) != 0);
+          umma_commit(kv_empty(s, st));
+          umma_commit(pv_done(s));
+          if (n + 1 == ntiles) umma_commit(o_final(s));
+          if (dbg) p.dbg[(pc - 41) * 8 + 7] = clock64();
+          if (dbg) d2[3] = clock64();
         }
       }
     }
-  } else if (warp >= 4) {
-    // ===== softmax: slot = (head of the pair, key parity); thread = one query row of the slot's 64-key half tiles
-    const int sl = (warp - 4) >> 2, h = sl >> 1, kp = sl & 1, quad = warp & 3;
+  } else {
+    // ===== softmax: thread = (query row, half of the tile's keys)
+    const int s = (warp - 4) >> 3, quad = warp & 3, ch = ((warp - 4) >> 2) & 1;
     const int row = quad * 32 + lane;
-    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + sl * AT_SLOT_COLS;
-    const uint32_t t_o = t_s + AT_COL_O;
-    const uint32_t t_o_other = tmem_base + ((uint32_t)(quad * 32) << 16) + (sl ^ 1) * AT_SLOT_COLS + AT_COL_O;
-    float2* xch = reinterpret_cast<float2*>(smem_gen + AT_OFF_X);  // [slot][128]
-    auto head_bar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + h) : "memory"); };
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + s * AT_SLOT_COLS;
+    const uint32_t t_s = t_row + ch * 64, t_o = t_row + AT_COL_O + ch * 32;
+    float* xs = reinterpret_cast<float*>(smem_gen + AT_OFF_X) + s * 256;  // [half][128]
+    float* x_own = xs + ch * 128 + row;
+    const float* x_oth = xs + (ch ^ 1) * 128 + row;
+    auto slot_bar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); };
+    auto slot_any = [&](bool v) {  // OR over the slot's 256 threads (the same named barrier)
+      uint32_t r;
+      asm volatile(
+          "{\n\t.reg .pred pi, po;\n\tsetp.ne.b32 pi, %2, 0;\n\tbar.red.or.pred po, %1, 256, pi;\n\t"
+          "selp.u32 %0, 1, 0, po;\n\t}"
+          : "=r"(r)
+          : "r"(1 + s), "r"((uint32_t)v)
+          : "memory");
+      return r != 0;
+    };
+    // PV of the slot's previous tile has completed (P may be overwritten, O may be rescaled); tiles are counted over
+    // the whole kernel, the first one has no predecessor
+    auto wait_pv = [&](uint32_t tile) {
+      if (tile > 0) mbar_wait(pv_done(s), (tile - 1) & 1u);
+    };
+    const uint32_t t_p = t_row + AT_COL_P + ch * 32;  // column c of P holds keys 2c, 2c + 1
+    auto store_p = [&](int ci, const uint32_t (&pk)[16]) { tmem_st16(t_p + ci * 16, pk); };
     constexpr float SC = 0.0625f * kLog2e;
     uint32_t sc_cnt = 0, oc_cnt = 0;
-    const float* slope_s = reinterpret_cast<const float*>(smem_gen + AT_OFF_BAR + 8 * 38);
     Item it;
-    for (int k = 0; next_item(p, k, h, &it); ++k) {
+    for (int k = 0; next_item(p, k, s, &it); ++k) {
       const int head = it.head;
       const float slope2 = slope_s[head] * kLog2e;
-      float m = -INFINITY, l = 0.f;  // running maximum (log2 domain) and row sum over this slot's keys
+      const float2 sc2 = make_float2(SC, SC), step2 = make_float2(2.f * slope2, 2.f * slope2);
+      float m = -INFINITY, l = 0.f;  // m: the row's reference (both half-row threads hold the same); l: partial sum
       for (int n = 0; n <= it.qi; ++n) {
-        const int k0 = (2 * (it.qi - n) + kp) * 64;  // first key of the half tile
+        const int k0 = (it.qi - n) * 128;
         const bool diag = n == 0;
-        // On the diagonal tile the half tile starts kp*64 keys into the query tile: 32-key chunk c is visible to this
-        // warp's rows iff its first key kp*64 + 32c <= quad*32, and holds the diagonal itself when equal.
-        const int dchunk = quad - 2 * kp;  // chunk index of the diagonal for this warp (may be < 0 or > 1)
-        const int nvis = diag ? min(max(dchunk + 1, 0), 2) : 2;
-        const float base = fmaf(slope2, (float)k0, kLog2e);
-        const bool dbg = p.dbg && blockIdx.x == 0 && sl == 0 && quad == 0 && lane == 0 && sc_cnt >= 40 && sc_cnt < 104;
+        // this thread's two 32-key chunks are global chunks 2*ch and 2*ch+1; on the diagonal tile chunk g is
+        // visible to this warp's rows iff g <= quad, and chunk g == quad holds the diagonal itself
+        const int g0 = 2 * ch;
+        const int nvis = diag ? min(max(quad + 1 - g0, 0), 2) : 2;
+        const float base = fmaf(slope2, (float)(k0 + 64 * ch), kLog2e);
+        const bool dbg = p.dbg && blockIdx.x == 0 && s == 0 && ch == 0 && quad == 0 && lane == 0 && sc_cnt >= 40 && sc_cnt < 104;
         const uint32_t di = (sc_cnt - 40) * 8;
         if (dbg) p.dbg[di + 0] = clock64();
-        mbar_wait(s_full(sl), sc_cnt & 1u);
+        mbar_wait(s_full(s), sc_cnt & 1u);
         if (dbg) p.dbg[di + 1] = clock64();
-        ++sc_cnt;
+        const uint32_t tile = sc_cnt++;
         tc_fence_after();
-        // The kernel is bound by TMEM reads (64 B/clk/SM: one pass over a half tile of S is 32 KB = 512 clk), so S is
-        // read ONCE where that is possible: from the second tile on the scores are exponentiated against the running
-        // reference m as they are (softmax is shift-invariant; m does not have to be the exact maximum), and the tile
-        // maximum is tracked on the side. Only if some row exceeds the reference by more than 8 binades (P is a 16-bit
-        // float: fp16 tops out at 2^16) is the tile redone the exact way below, with the P stores held back until then
-        // because P overwrites S.
         float2 ps2 = make_float2(0.f, 0.f);
-        const float2 sc2 = make_float2(SC, SC), step2 = make_float2(2.f * slope2, 2.f * slope2);
         bool done = false;
-        if (!diag && !__any_sync(0xffffffffu, m == -INFINITY)) {
+        if (!diag) {
+          // ---- one pass against the running reference (finite after the diagonal tile: a row always sees itself)
           const float base_m = base - m;
-          uint32_t pk[2][16];
           float tmax = -INFINITY;
-#pragma unroll
+#pragma unroll 1
           for (int ci = 0; ci < 2; ++ci) {
-            uint32_t r[32];
+            uint32_t r[32], pk[16];
             tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
             const float cb = fmaf(slope2, (float)(ci * 32), base_m);
+            // bias of the key pair (i, i + 1), stepped by 2 * slope per pair (no per-element constant to materialise)
             float2 bias2 = make_float2(cb, cb + slope2);
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -308,76 +333,70 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
               tmax = fmaxf(tmax, fmaxf(t.x, t.y));
               const float p0 = ex2_fast(t.x), p1 = ex2_fast(t.y);
               ps2 = __fadd2_rn(ps2, make_float2(p0, p1));
-              pk[ci][i >> 1] = pack16(p0, p1, FP16);
+              pk[i >> 1] = pack16(p0, p1, FP16);
             }
-          }
-          if (!__any_sync(0xffffffffu, tmax > 8.0f)) {
-            tmem_st16(t_s, pk[0]);
-            tmem_st16(t_s + 16, pk[1]);
-            done = true;
-          } else {
-            ps2 = make_float2(0.f, 0.f);
+            if (ci == 0) {
+              if (dbg) p.dbg[512 + di + 4] = clock64();
+              wait_pv(tile);
+              if (dbg) p.dbg[512 + di + 5] = clock64();
+            }
+            store_p(ci, pk);
           }
           if (dbg) p.dbg[di + 2] = clock64();
+          // every thread of the slot takes the same route (the exact one has block barriers in it)
+          if (!slot_any(tmax > 8.0f)) done = true;
+          else ps2 = make_float2(0.f, 0.f);
           if (dbg) p.dbg[di + 3] = clock64();
         }
         if (!done) {
-          // pass A: upper bound of the row maximum (log2 domain): SC * max_j s_j + bias of the last visible key
+          // ---- exact route. Pass A: upper bound of the row maximum (log2 domain): SC * max_j s_j + bias of the last
+          // visible key. S is intact (P lives in shared memory), so a tile the single pass gave up on is simply redone.
           float mx = -INFINITY;
-  #pragma unroll 1
+#pragma unroll 1
           for (int ci = 0; ci < nvis; ++ci) {
             uint32_t r[32];
             tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
-            if (diag && ci == dchunk) {
-  #pragma unroll
+            if (diag && g0 + ci == quad) {
+#pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i <= lane ? __uint_as_float(r[i]) : -INFINITY);
             } else {
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
             }
           }
-          if (dbg) p.dbg[di + 2] = clock64();
-          if (dbg) p.dbg[di + 3] = clock64();
-          // last visible key of the row in this half tile (diag: the query itself, at most key 63 of the half tile)
-          const int last = diag ? min(row - kp * 64, 63) : 63;
-          const float b_last = fmaf(slope2, (float)last, base);
-          const float m_new = fmaxf(m, fmaf(mx, SC, b_last));  // nvis == 0: mx = -inf, m stays
+          *x_own = mx;
+          slot_bar();
+          mx = fmaxf(mx, *x_oth);
+          const float b_last = fmaf(slope2, (float)(k0 + (diag ? row : 127)), kLog2e);
+          const float m_new = fmaxf(m, fmaf(mx, SC, b_last));
+          wait_pv(tile);
+          tc_fence_after();
           if (n > 0 && __any_sync(0xffffffffu, m_new > m)) {
-            // rare: rescale the accumulator row (PV of the previous tile has completed: s_full was committed after it)
-            const float alpha = ex2_fast(m - m_new);  // m = -inf (nothing seen so far): 0, and O is 0
+            // rescale this thread's half of the accumulator row
+            const float alpha = ex2_fast(m - m_new);
             l *= alpha;
-  #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld32(t_o + c * 32, r);
-              tmem_ld_wait();
-  #pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st32(t_o + c * 32, r);
-            }
+            uint32_t r[32];
+            tmem_ld32(t_o, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(t_o, r);
           }
-          // ALiBi makes far tiles of the steep heads irrelevant: if even the tile's upper bound is more than 40 binades
-          // below the running maximum for every row of the warp, every p would be < 2^-40 of the row's largest term
-          // (fp32 cannot see it in the row sum or in O), so the exponentials are skipped and P is written as zeros.
-          const bool negligible = n > 0 && __all_sync(0xffffffffu, fmaf(mx, SC, b_last) < m - 40.0f);
           m = m_new;
-          // pass B: p = 2^(t - m), row sum, P -> TMEM as 16-bit pairs over S columns [0, 32) (column c holds keys 2c, 2c+1;
-          // chunk 1 of S is in registers before chunk 0's P lands on columns [0, 16), and its own P goes to [16, 32))
+          // pass B: p = 2^(t - m), partial row sum, P -> shared memory
           const float base_m = base - m;
-          const int nexp = negligible ? 0 : nvis;
-  #pragma unroll 1
+#pragma unroll 1
           for (int ci = 0; ci < 2; ++ci) {
             uint32_t pk[16];
-            if (ci < nexp) {
+            if (ci < nvis) {
               uint32_t r[32];
               tmem_ld32(t_s + ci * 32, r);
               tmem_ld_wait();
               const float cb = fmaf(slope2, (float)(ci * 32), base_m);
-              // bias of the key pair (i, i + 1), stepped by 2 * slope per pair (no per-element constant to materialise)
               float2 bias2 = make_float2(cb, cb + slope2);
-              if (diag && ci == dchunk) {
-  #pragma unroll
+              if (diag && g0 + ci == quad) {
+#pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                   const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
                   bias2 = __fadd2_rn(bias2, step2);
@@ -388,7 +407,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                   pk[i >> 1] = pack16(p0, p1, FP16);
                 }
               } else {
-  #pragma unroll
+#pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                   const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
                   bias2 = __fadd2_rn(bias2, step2);
@@ -398,64 +417,46 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 }
               }
             } else {
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = 0u;
             }
-            tmem_st16(t_s + ci * 16, pk);
+            store_p(ci, pk);
           }
         }
         l += ps2.x + ps2.y;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(p_full(sl));
+        tmem_st_wait();     // P (and the rare accumulator rescale)
+        tc_fence_before();  // ... and the S reads, before the MMAs that follow the arrival
+        mbar_arrive(p_full(s));
         if (dbg) p.dbg[di + 4] = clock64();
       }
-      // ===== merge of the head's two slots and epilogue: this thread writes d columns [32 kp, 32 kp + 32) of its row
-      const bool dbe = p.dbg && blockIdx.x == 0 && sl == 0 && quad == 0 && lane == 0 && k < 60;
-      long long* de = p.dbg + 512 + k * 8;
-      if (dbe) de[0] = clock64();
-      xch[sl * 128 + row] = make_float2(m, l);
-      head_bar();
-      if (dbe) de[1] = clock64();
-      const float2 o = xch[(sl ^ 1) * 128 + row];
-      const float mm = fmaxf(m, o.x);  // finite: the even slot always sees the row's own key
-      const float w_own = ex2_fast(m - mm), w_oth = ex2_fast(o.x - mm);  // 2^-inf = 0 for a slot that saw no key
-      const float inv = 1.0f / fmaf(w_own, l, w_oth * o.y);
-      const float a_own = w_own * inv, a_oth = w_oth * inv;
-      mbar_wait(o_final(sl), oc_cnt & 1u);
-      mbar_wait(o_final(sl ^ 1), oc_cnt & 1u);
+      // epilogue: O / l -> 16-bit -> out[(seq*T + q), head*64 + 32*ch .. +32). o_final also says that every thread of
+      // the slot has arrived on the last p_full, i.e. has read the last tile's exchange slots.
+      mbar_wait(o_final(s), oc_cnt & 1u);
       ++oc_cnt;
       tc_fence_after();
-      if (dbe) de[2] = clock64();
+      *x_own = l;
+      slot_bar();
+      l += *x_oth;
+      const float inv = 1.0f / l;
       const int q = it.qi * 128 + row;
-      __nv_bfloat16* dst = p.out + ((long long)it.seq * p.T + q) * kDim + head * 64 + kp * 32;
+      __nv_bfloat16* dst = p.out + ((long long)it.seq * p.T + q) * kDim + head * 64 + ch * 32;
       {
-        uint32_t r[32], r2[32];
-        tmem_ld32(t_o + kp * 32, r);
-        tmem_ld32(t_o_other + kp * 32, r2);
+        uint32_t r[32];
+        tmem_ld32(t_o, r);
         tmem_ld_wait();
-        tc_fence_before();
-        if (dbe) de[3] = clock64();
-        // the partner slot's first PV of the next item overwrites the accumulator this thread has just read: its
-        // p_full is arrived by the partner's threads, so both slots meet here before either goes on
-        head_bar();
-        if (dbe) de[4] = clock64();
+        tc_fence_before();  // the O reads are ordered before the next item's p_full arrivals
+        slot_bar();         // ... and the row sums have been read before the next item's first exchange
         if (q < p.T) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              f[j] = fmaf(__uint_as_float(r[8 * i + j]), a_own, __uint_as_float(r2[8 * i + j]) * a_oth);
             uint4 u;
-            u.x = pack16(f[0], f[1], FP16);
-            u.y = pack16(f[2], f[3], FP16);
-            u.z = pack16(f[4], f[5], FP16);
-            u.w = pack16(f[6], f[7], FP16);
+            u.x = pack16(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv, FP16);
+            u.y = pack16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv, FP16);
+            u.z = pack16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv, FP16);
+            u.w = pack16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv, FP16);
             *reinterpret_cast<uint4*>(dst + 8 * i) = u;
           }
         }
-        if (dbe) de[5] = clock64();
       }
     }
   }
@@ -488,7 +489,7 @@ int launch_attention_tc(cudaStream_t st, const __nv_bfloat16* q, long long q_row
     const uint64_t strides[2] = {(uint64_t)rs, (uint64_t)rs * (uint64_t)T};
     return make_tmap(m, base, 2, 3, dims, strides, box, 128, err);
   };
-  if (!mk(&p.tq, q, q_row_stride, 128) || !mk(&p.tk, k, kv_row_stride, 64) || !mk(&p.tv, v, kv_row_stride, 64)) return -1;
+  if (!mk(&p.tq, q, q_row_stride, 128) || !mk(&p.tk, k, kv_row_stride, 128) || !mk(&p.tv, v, kv_row_stride, 128)) return -1;
   p.out = out;
   p.slopes = slopes;
   p.nseq = nseq;
