@@ -36,6 +36,10 @@ for i in range(1, 27):
     ch = [r[2] - r[1]] + [r[2 + j] - r[1 + j] for j in range(1, 6)]
     print(f"{i:3d} | {r[1]-r[0]:6d} | " + " ".join(f"{c:5d}" for c in ch) + f" | {r[8]-r[7]:6d} | {r[9]-r[8]:6d} | {r[10]-r[9]:6d} | {r[10]-r[0]:6d}")
 
+print("MMA thread per tile: waiting for weights | waiting for the epilogue (h_full) | tile period")
+for i in range(2, 14):
+    r = [int(x) for x in d[i]]
+    print(f"{i:3d} | {r[11]:6d} | {r[12]:6d} | {r[13]-int(d[i-1][13]):6d}")
 ts = []
 for _ in range(10):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

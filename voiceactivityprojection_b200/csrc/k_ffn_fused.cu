@@ -15,6 +15,14 @@
 //     ACC_O     += H W2[:, j]^T       8 x tcgen05.mma M128 N256 K16, W2 k-blocks through the same ring
 //   final epilogue on ACC_O: + residual (row-blocked fp32) -> x_out, bf16 shadow, LayerNorm -> z_next
 // TMEM: ACC_H 2 x 128 columns, ACC_O 256 columns. The staging tiles of the final epilogue alias the H buffers.
+//
+// Two CTAs of a cluster work as a pair on 256 rows (tcgen05 cta_group::2, issued by the even CTA): each CTA holds ITS
+// 128 rows of Z / H and its accumulators, and HALF of every weight tile (the B operand of a pair MMA is split by output
+// channel over the two CTAs). Why: a tile needs all of W1 and W2 (786 KB from L2) and the ring that carries them is
+// bounded by shared memory to 80 KB; with every CTA pulling whole weight tiles the ring covered ~0.6 of a chunk and the
+// four later chunks of a tile ran at the ring's latency-bound rate (tools/ffn_probe.py, round 2: 4500 clk per chunk
+// against 2400 clk of MMAs; neither halving the bytes per load nor multicasting the tiles changed that - only bytes in
+// flight per CTA count). With half tiles the same ring holds 1.25 chunks.
 #include <string>
 
 #include "common.cuh"
@@ -27,7 +35,7 @@ using namespace tc;
 namespace {
 
 constexpr int FK_BYTES = 128 * 64 * 2;   // one A k-block: 128 rows x 64 k, 16 KB
-constexpr int FW_BYTES = 128 * 64 * 2;   // one W tile: 128 n x 64 k, 16 KB (W2's 256-row k-blocks are loaded as two halves)
+constexpr int FW_BYTES = 128 * 64 * 2;   // one ring stage, 16 KB: this CTA's half of two W1 k-blocks (2 x 64 n x 64 k) or of one W2 k-block (128 n x 64 k)
 constexpr int FW_STAGES = 5;
 constexpr int F_OFF_Z = 0;
 constexpr int F_OFF_H = 4 * FK_BYTES;                 // also: staging [half][2] x 8 KB, then LN vectors / partials
@@ -41,7 +49,7 @@ constexpr int F_EPI = 512;
 
 struct alignas(64) FfnParams {
   CUtensorMap tma_z;    // (256, M) bf16, box (64, 128)
-  CUtensorMap tma_w1;   // (256 k, 768 n) bf16, box (64, 128)
+  CUtensorMap tma_w1;   // (256 k, 768 n) bf16, box (64, 64): this CTA's half of a 128-channel chunk
   CUtensorMap tma_w2;   // (768 k, 256 n) bf16, box (64, 128)
   CUtensorMap tma_xs;   // (256, M) bf16 out, box (32, 32), SW64: one store per epilogue warp
   CUtensorMap tma_zn;   // (256, M) bf16 out (LayerNorm of x_out), box (32, 32), SW64
@@ -72,6 +80,40 @@ __device__ __forceinline__ float2 gelu_poly2_f(float2 x) {  // same polynomial a
   return __fadd2_rn(acc, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar_leader, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs when all prior MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {  // one whole warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 __device__ __forceinline__ long long blocked_off_f(long long m, int c) {
   return (((m >> 7) * 64 + (c >> 2)) * 128 + (m & 127)) * 4 + (c & 3);
 }
@@ -97,6 +139,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
     prefetch_tmap(&p.tma_z);
     prefetch_tmap(&p.tma_w1);
     prefetch_tmap(&p.tma_w2);
+    // *_full of operands: the leader's copy is the one used (its expect_tx arrival, bytes from both CTAs);
+    // *_empty / acc*_full: multicast MMA commits, every CTA waits on its own copy;
+    // h_full / acco_empty: the epilogue threads of BOTH CTAs arrive on the leader's copy
     mbar_init(z_full, 1);
     mbar_init(z_empty, 1);
     for (int s = 0; s < FW_STAGES; ++s) {
@@ -105,48 +150,58 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acch_full(b), 1);
-      mbar_init(h_full(b), F_EPI);
+      mbar_init(h_full(b), 2 * F_EPI);
       mbar_init(h_empty(b), 1);
     }
     mbar_init(acco_full, 1);
-    mbar_init(acco_empty, F_EPI);
+    mbar_init(acco_empty, 2 * F_EPI);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM allocations exist before anyone signals across the pair
   tc_fence_after();
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int n_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int num_pair_tiles = (p.num_tiles + 1) / 2;
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t t_acch = tmem_base /* 2 x 128 columns */, t_acco = tmem_base + 256;
   pdl_wait();
 
   if (warp == 0) {
-    // ===== TMA producer: Z of the tile, then the W k-blocks in the order the MMA thread consumes them:
-    // W1[0], W1[1], then for j = 0..5: W2[j], W1[j+2]; every load is a 128 n x 64 k tile (16 KB)
+    // ===== TMA producer (both CTAs): own Z rows, then this CTA's half of the W stages in the order the MMA thread
+    // consumes them: W1[0], W1[1], then for j = 0..5: W2[j], W1[j+2]. A chunk of W1 is two stages (two k-blocks of
+    // 64 n x 64 k each), a chunk of W2 two stages (one k-block of 128 n x 64 k each).
     if (lane == 0) {
       uint32_t wc = 0, it = 0;
       auto load_w1 = [&](int j) {
-        for (int kb = 0; kb < 4; ++kb, ++wc) {
+        for (int i = 0; i < 2; ++i, ++wc) {
           const int s = wc % FW_STAGES;
           mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(w_full(s), FW_BYTES);
-          tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w1, w_full(s), kb * 64, j * 128);
+          if (rank == 0) mbar_arrive_expect_tx(w_full(s), 2 * FW_BYTES);
+          const uint32_t bar_leader = w_full(s) & kPeerBitMask;
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_2sm(smem_base + F_OFF_W + s * FW_BYTES + h * (FW_BYTES / 2), &p.tma_w1, bar_leader,
+                            (i * 2 + h) * 64, j * 128 + (int)rank * 64);
         }
       };
       auto load_w2 = [&](int j) {
-        for (int i = 0; i < 4; ++i, ++wc) {  // (k-block, output-channel half)
+        for (int kb = 0; kb < 2; ++kb, ++wc) {
           const int s = wc % FW_STAGES;
           mbar_wait(w_empty(s), ((wc / FW_STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(w_full(s), FW_BYTES);
-          tma_load_2d(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s), j * 128 + (i >> 1) * 64, (i & 1) * 128);
+          if (rank == 0) mbar_arrive_expect_tx(w_full(s), 2 * FW_BYTES);
+          tma_load_2d_2sm(smem_base + F_OFF_W + s * FW_BYTES, &p.tma_w2, w_full(s) & kPeerBitMask, j * 128 + kb * 64,
+                          (int)rank * 128);
         }
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters, ++it) {
+        const int tile = pt * 2 + (int)rank;  // a pair's odd tile may not exist: TMA fills its rows with zeros
         mbar_wait(z_empty, (it & 1u) ^ 1u);
-        mbar_arrive_expect_tx(z_full, 4 * FK_BYTES);
+        if (rank == 0) mbar_arrive_expect_tx(z_full, 2 * 4 * FK_BYTES);
         for (int kb = 0; kb < 4; ++kb)
-          tma_load_2d(smem_base + F_OFF_Z + kb * FK_BYTES, &p.tma_z, z_full, kb * 64, tile * 128);
+          tma_load_2d_2sm(smem_base + F_OFF_Z + kb * FK_BYTES, &p.tma_z, z_full & kPeerBitMask, kb * 64, tile * 128);
         load_w1(0);
         load_w1(1);
         for (int j = 0; j < 6; ++j) {
@@ -156,39 +211,49 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc_16(128, 128, 0, 0, p.fp16);
+    // ===== MMA issuer (leader CTA only): pair MMAs, M = 256 (128 rows in each CTA)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc1 = make_idesc_16(256, 128, 0, 0, p.fp16), idesc2 = make_idesc_16(256, 256, 0, 0, p.fp16);
       uint32_t wc = 0, it = 0, hcnt[2] = {0, 0} /*h_full phases seen per buffer*/, n_o = 0;
+      long long t_w = 0, t_h = 0;  // probe: cycles spent waiting for weights / for the epilogue
+      const bool mdbg = p.dbg && blockIdx.x == 0;
       auto gemm1 = [&](int b) {  // ACC_H[b] = Z W1[chunk]^T
-        for (int kb = 0; kb < 4; ++kb, ++wc) {
+        for (int i = 0; i < 2; ++i, ++wc) {
           const int s = wc % FW_STAGES;
+          const long long tw0 = mdbg ? clock64() : 0;
           mbar_wait(w_full(s), (wc / FW_STAGES) & 1u);
+          if (mdbg) t_w += clock64() - tw0;
           tc_fence_after();
-          const uint32_t a_addr = smem_base + F_OFF_Z + kb * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(t_acch + b * 128, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
-                      make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc1, (kb | k) != 0);
-          umma_commit(w_empty(s));
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t a_addr = smem_base + F_OFF_Z + (i * 2 + h) * FK_BYTES;
+            const uint32_t b_addr = smem_base + F_OFF_W + s * FW_BYTES + h * (FW_BYTES / 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_2sm(t_acch + b * 128, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                            make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc1, (i | h | k) != 0);
+          }
+          umma_commit_2sm(w_empty(s));
         }
-        umma_commit(acch_full(b));
+        umma_commit_2sm(acch_full(b));
       };
-      auto gemm2 = [&](int b, bool first) {  // ACC_O (+)= H[b] W2[:, chunk]^T
-        for (int i = 0; i < 4; ++i, ++wc) {  // (k-block, output-channel half): two N = 128 MMAs per K step
-          const int s = wc % FW_STAGES, kb = i >> 1, nh = i & 1;
+      auto gemm2 = [&](int b, bool first) {  // ACC_O (+)= H[b] W2[:, chunk]^T, one N = 256 MMA per K step
+        for (int kb = 0; kb < 2; ++kb, ++wc) {
+          const int s = wc % FW_STAGES;
+          const long long tw0 = mdbg ? clock64() : 0;
           mbar_wait(w_full(s), (wc / FW_STAGES) & 1u);
+          if (mdbg) t_w += clock64() - tw0;
           tc_fence_after();
           const uint32_t a_addr = smem_base + F_OFF_H + (b * 2 + kb) * FK_BYTES, b_addr = smem_base + F_OFF_W + s * FW_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(t_acco + nh * 128, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
-                      make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc1, !(first && kb == 0 && k == 0));
-          umma_commit(w_empty(s));
+            umma_bf16_2sm(t_acco, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                          make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc2, !(first && kb == 0 && k == 0));
+          umma_commit_2sm(w_empty(s));
         }
-        umma_commit(h_empty(b));
+        umma_commit_2sm(h_empty(b));
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters, ++it) {
         mbar_wait(z_full, it & 1u);
         tc_fence_after();
         // both ACC_H buffers are free: the epilogue of the previous tile's last two chunks arrived on h_full (waited)
@@ -196,7 +261,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
         gemm1(1);
         for (int j = 0; j < 6; ++j) {
           const int b = j & 1;
-          mbar_wait(h_full(b), hcnt[b] & 1u);  // H[b] is in shared memory and ACC_H[b] has been read
+          const long long th0 = mdbg ? clock64() : 0;
+          mbar_wait(h_full(b), hcnt[b] & 1u);  // H[b] is in shared memory and ACC_H[b] has been read, in both CTAs
+          if (mdbg) t_h += clock64() - th0;
           ++hcnt[b];
           tc_fence_after();
           if (j == 0) {
@@ -206,12 +273,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
           gemm2(b, j == 0);
           if (j + 2 < 6) {
             gemm1(b);
-            if (j + 2 == 5) umma_commit(z_empty);  // last read of Z for this tile
+            if (j + 2 == 5) umma_commit_2sm(z_empty);  // last read of Z for this tile
           }
           if (j == 5) {
-            umma_commit(acco_full);
+            umma_commit_2sm(acco_full);
             ++n_o;
           }
+        }
+        if (mdbg && it < 32) {
+          p.dbg[it * 16 + 11] = t_w;
+          p.dbg[it * 16 + 12] = t_h;
+          p.dbg[it * 16 + 13] = clock64();
+          t_w = t_h = 0;
         }
       }
     }
@@ -257,8 +330,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
       ++stg_cnt;
     };
 
+    const uint32_t h_full_leader[2] = {mapa(h_full(0), 0), mapa(h_full(1), 0)};
+    const uint32_t acco_empty_leader = mapa(acco_empty, 0);
     int dbg_t = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++dbg_t) {
+    for (int pt = cluster_id; pt < num_pair_tiles; pt += n_clusters, ++dbg_t) {
+      const int tile = pt * 2 + (int)rank;
       const bool dbg = p.dbg && blockIdx.x == 0 && threadIdx.x == 128 && dbg_t < 32;
       long long* dq = p.dbg + dbg_t * 16;
       if (dbg) dq[0] = clock64();
@@ -306,7 +382,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
         }
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(h_full(b));
+        mbar_arrive_remote(h_full_leader[b]);
         if (dbg) dq[2 + j] = clock64();
       }
       // ---- final epilogue on ACC_O: this thread's 64 columns in two chunks of 32
@@ -378,16 +454,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
         }
       }
       tc_fence_before();
-      mbar_arrive(acco_empty);
+      mbar_arrive_remote(acco_empty_leader);
       if (dbg) dq[10] = clock64();
     }
     if (lane == 0) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's shared memory / signalling its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -406,7 +483,7 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
     return make_tmap(m, base, 2, 2, dims, strides, box, sw, err);
   };
   if (!map2(&p.tma_z, z, 256, (uint64_t)M, 64, 128, 128)) return -1;
-  if (!map2(&p.tma_w1, w1, 256, 768, 64, 128, 128)) return -1;
+  if (!map2(&p.tma_w1, w1, 256, 768, 64, 64, 128)) return -1;
   if (!map2(&p.tma_w2, w2, 768, 256, 64, 128, 128)) return -1;
   if (!map2(&p.tma_xs, xs, 256, (uint64_t)M, 32, 32, 64)) return -1;
   if (zn && !map2(&p.tma_zn, zn, 256, (uint64_t)M, 32, 32, 64)) return -1;
@@ -430,8 +507,25 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
     }
     configured = true;
   }
-  const int grid = p.num_tiles < n_sm ? p.num_tiles : n_sm;
-  launch_pdl(ffn_fused_kernel, grid, F_THREADS, F_SMEM, st, p);
+  int pairs = (p.num_tiles + 1) / 2;
+  if (pairs > n_sm / 2) pairs = n_sm / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(pairs * 2));
+  cfg.blockDim = dim3(F_THREADS);
+  cfg.dynamicSmemBytes = F_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t ce = cudaLaunchKernelEx(&cfg, ffn_fused_kernel, p);
+  if (ce != cudaSuccess) {
+    if (err) *err = std::string("ffn_fused launch: ") + cudaGetErrorString(ce);
+    return -1;
+  }
   return 1;
 }
 
