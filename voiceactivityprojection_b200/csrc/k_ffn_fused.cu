@@ -514,13 +514,15 @@ int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat1
   cfg.blockDim = dim3(F_THREADS);
   cfg.dynamicSmemBytes = F_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // the kernel has griddepcontrol.wait before its first load
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const cudaError_t ce = cudaLaunchKernelEx(&cfg, ffn_fused_kernel, p);
   if (ce != cudaSuccess) {
     if (err) *err = std::string("ffn_fused launch: ") + cudaGetErrorString(ce);

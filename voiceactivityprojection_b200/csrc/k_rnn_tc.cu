@@ -44,7 +44,7 @@ using namespace tc;
 namespace {
 
 constexpr int RC = 8;            // CTAs per cluster
-constexpr int RXST = 2;          // x tile stages per group
+constexpr int RXST = 2;          // x tiles in flight: the two time steps of a pair (one MMA series covers both)
 constexpr int R_ACC_COL = 256;   // TMEM: weights in columns [0,256), accumulators behind them
 
 // NG groups of NB sequences per cluster.
@@ -156,40 +156,46 @@ __global__ void __launch_bounds__(RnnCfg<NG, NB>::THREADS, 1) rnn_tc_kernel(cons
   if (warp == TMA_WARP) {
     // ===== TMA producer: x_t tiles (all groups of the cluster in one box)
     if (lane == 0) {
-      for (int t = 0; t < T; ++t) {
-        const int s = t % RXST;
-        mbar_wait(xempty(s), ((uint32_t)(t / RXST) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(xfull(s), Cfg::XTILE);
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_3d(smem_base + OFF_X + s * Cfg::XTILE + kb * (NG * NB * 128), &p.tma_x, xfull(s), kb * 64, t, seq0);
+      // x of TWO time steps per stage: rows [0, NG*NB) of every k-block are step 2 pr, rows [NG*NB, 2 NG*NB) step 2 pr + 1
+      for (int pr = 0; 2 * pr < T; ++pr) {
+        const int nst = 2 * pr + 1 < T ? 2 : 1;
+        mbar_wait(xempty(0), ((uint32_t)pr & 1u) ^ 1u);
+        mbar_arrive_expect_tx(xfull(0), nst * Cfg::XTILE);
+        for (int tl = 0; tl < nst; ++tl)
+          for (int kb = 0; kb < 4; ++kb)
+            tma_load_3d(smem_base + OFF_X + kb * (2 * NG * NB * 128) + tl * (NG * NB * 128), &p.tma_x, xfull(0), kb * 64,
+                        2 * pr + tl, seq0);
       }
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer. One tcgen05.mma costs ~62 cycles for any N <= 128 (the 128 x 16 weight operand
-    // streams at 64 B/clk), so the input half W_ih x_t is issued ONCE per step for all groups (N = NG*NB)
-    // and only the recurrent half W_hh h_{t-1} is per group.
+    // streams at 64 B/clk) and that stream is what a step's time is made of (16 MMAs per series: input half +
+    // one recurrent half per group = 3 x 991 of ~3600 clk at NG = 2). So the input half W_ih x_t is issued once
+    // for all groups AND for two time steps (N = 2*NG*NB <= 128: x does not depend on the recurrence), into a
+    // ring of four accumulator sets; only the recurrent half W_hh h_{t-1} is per group and per step.
     if (lane == 0) {
       const uint32_t idesc_h = make_idesc_16(128, NB, 0, 0, p.fp16);
-      const uint32_t idesc_x = make_idesc_16(128, NG * NB, 0, 0, p.fp16);
-      auto acc_col = [&](int t, int g) { return tmem_base + R_ACC_COL + (t & 1) * (NG * NB) + g * NB; };
-      auto x_part = [&](int t) {
-        const int s = t % RXST;
-        mbar_wait(xfull(s), (uint32_t)(t / RXST) & 1u);
+      const uint32_t idesc_x = make_idesc_16(128, 2 * NG * NB, 0, 0, p.fp16);
+      auto acc_col = [&](int t, int g) { return tmem_base + R_ACC_COL + (t & 3) * (NG * NB) + g * NB; };
+      // input half of steps 2 pr and 2 pr + 1 into accumulator sets (2 pr) & 3 and the one after it. Both sets are free:
+      // their last readers were the gates of steps 2 pr - 4 and 2 pr - 3. With an odd T the last pair's second half
+      // multiplies stale x rows into a set nobody reads.
+      auto x_pair = [&](int pr) {
+        mbar_wait(xfull(0), (uint32_t)pr & 1u);
         tc_fence_after();
-        const uint32_t b_tile = smem_base + OFF_X + s * Cfg::XTILE;
+        const uint32_t b_tile = smem_base + OFF_X;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const uint64_t bd = make_smem_desc_sw128(b_tile + (j >> 2) * (NG * NB * 128) + (j & 3) * 32, 0, 1024);
-          umma_bf16_ts(acc_col(t, 0), tmem_base + j * 8, bd, idesc_x, j == 0 ? 0u : 1u);
+          const uint64_t bd = make_smem_desc_sw128(b_tile + (j >> 2) * (2 * NG * NB * 128) + (j & 3) * 32, 0, 1024);
+          umma_bf16_ts(acc_col(2 * pr, 0), tmem_base + j * 8, bd, idesc_x, j == 0 ? 0u : 1u);
         }
-        umma_commit(xempty(s));
+        umma_commit(xempty(0));
       };
       for (int g = 0; g < NG; ++g)
         for (int b = 0; b < 2; ++b)
           if (b + 1 < T) mbar_arrive_expect_tx(hfull(g, b), R_TILE);  // h_b will arrive
-      x_part(0);
+      x_pair(0);
       for (int g = 0; g < NG; ++g) umma_commit(accfull(g, 0));
-      if (T > 1) x_part(1);
       for (int t = 1; t < T; ++t) {
         const int hb = (t - 1) & 1;
         const uint32_t hph = (uint32_t)((t - 1) >> 1) & 1u;
@@ -207,8 +213,7 @@ __global__ void __launch_bounds__(RnnCfg<NG, NB>::THREADS, 1) rnn_tc_kernel(cons
           umma_commit(accfull(g, t & 1));
           if (p.dbg && g == 0 && blockIdx.x == 0 && t >= 64 && t < 96) p.dbg[(t - 64) * 8 + 1] = clock64();
         }
-        // every group's gates of step t-1 have read accumulator set (t+1)&1: refill it with W_ih x_{t+1}
-        if (t + 1 < T) x_part(t + 1);
+        if (((t + 1) & 1) == 0 && t + 1 < T) x_pair((t + 1) >> 1);
       }
     }
   } else {
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(RnnCfg<NG, NB>::THREADS, 1) rnn_tc_kernel(cons
       tc_fence_after();
       const bool dbg = p.dbg && tid == 0 && g == 0 && blockIdx.x == 0 && t >= 64 && t < 96;
       if (dbg) p.dbg[(t - 64) * 8 + 2] = clock64();
-      const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + R_ACC_COL + par * (NG * NB) + g * NB;
+      const uint32_t acc_addr = tmem_base + ((uint32_t)(q * 32) << 16) + R_ACC_COL + (t & 3) * (NG * NB) + g * NB;
       float* row = ex + (q * 32 + lane) * R_EXS;
 #pragma unroll
       for (int c = 0; c < NB / 16; ++c) {
