@@ -44,7 +44,7 @@ def main():
         steps = int(sys.argv[sys.argv.index("--steps") + 1])
         fam_of = {"conv0_tc_kernel": "conv0", "conv01_kernel": "conv_gemm", "gemm_2sm_kernel": "conv_gemm", "rnn_tc_kernel": "rnn",
                   "attention_tc_kernel": "attention", "gemm_lin_kernel": "linear_gemm", "ffn_fused_kernel": "linear_gemm",
-                  "probs_kernel": "heads", "loss_kernel": "heads", "vad_head_blocked_kernel": "heads"}
+                  "probs_kernel": "heads", "head_probs_kernel": "heads", "loss_kernel": "heads", "vad_head_blocked_kernel": "heads"}
         fams, after_rnn = {}, False
         for d in rows:
             fam = fam_of.get(d["name"], "other")
