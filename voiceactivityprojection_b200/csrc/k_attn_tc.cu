@@ -18,9 +18,9 @@
 //   softmax          : a thread owns half a query row (64 keys; warps 4 apart share a TMEM lane
 //                      quadrant). S is read with tcgen05.ld ONCE: p = 2^(t - m) against the
 //                      running reference m (softmax is shift-invariant, m need not be the exact
-//                      maximum), the tile maximum is tracked on the side, and only the first tile
-//                      of an item - or a tile that beats m by more than 8 binades - takes the exact
-//                      two-pass route. P goes back to TMEM as packed 16-bit pairs.
+//                      maximum), and only the first tile of an item - or a tile in which some row's
+//                      p sum to more than 2^8, i.e. the reference has fallen far behind - takes the
+//                      exact two-pass route. P goes back to TMEM as packed 16-bit pairs.
 //   O[128 q][64 d]  += P V        tcgen05.mma, A = P from TMEM, B = V tile MN-major SW128
 // QK^T of the NEXT tile is issued before PV of the current one (it only needs S), so the softmax
 // warps are back at work while PV is still on the tensor pipe; they wait for it (pv_done) before
@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         if (!diag) {
           // ---- one pass against the running reference (finite after the diagonal tile: a row always sees itself)
           const float base_m = base - m;
-          float tmax = -INFINITY;
 #pragma unroll 1
           for (int ci = 0; ci < 2; ++ci) {
             uint32_t r[32], pk[16];
@@ -330,7 +329,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             for (int i = 0; i < 32; i += 2) {
               const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
               bias2 = __fadd2_rn(bias2, step2);
-              tmax = fmaxf(tmax, fmaxf(t.x, t.y));
               const float p0 = ex2_fast(t.x), p1 = ex2_fast(t.y);
               ps2 = __fadd2_rn(ps2, make_float2(p0, p1));
               pk[i >> 1] = pack16(p0, p1, FP16);
@@ -343,8 +341,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             store_p(ci, pk);
           }
           if (dbg) p.dbg[di + 2] = clock64();
-          // every thread of the slot takes the same route (the exact one has block barriers in it)
-          if (!slot_any(tmax > 8.0f)) done = true;
+          // The reference still holds if no p exceeds 2^8 (P is a 16-bit float). The p are non-negative, so the sum of
+          // this thread's 64 bounds each of them: no separate maximum has to be tracked (one instruction per score pair
+          // less in a loop that is partly issue-bound), at the price of taking the exact route a little earlier than
+          // needed. Every thread of the slot takes the same route (the exact one has block barriers in it).
+          if (!slot_any(!(ps2.x + ps2.y <= 256.0f))) done = true;
           else ps2 = make_float2(0.f, 0.f);
           if (dbg) p.dbg[di + 3] = clock64();
         }
