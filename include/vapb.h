@@ -254,6 +254,15 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
                        int cross, char* err, int err_len,
                        long long* dbg_clocks /* device [64][8] SM-clock samples of CTA 0, or NULL */);
 
+/* Kernel-level test hook: the fp32-class tensor-core attention of mode FP32_TC (csrc/k_attn_x3.cu; reference
+ * vap/modules.py:82-110,169-202). qbuf / kvbuf: device fp32, contiguous (nseq*T, q_cols) and (nseq*T, kv_cols) - the
+ * same pointer for self-attention (q | k | v in one buffer of 768 columns); K and V start at columns k_off / v_off of
+ * kvbuf; planes: device scratch, 4 bytes per element of qbuf plus (when different) kvbuf; out: dense fp32
+ * (nseq*T, 256); slopes: device fp32 [4]; cross as in vapb_debug_attn_tc. */
+int vapb_debug_attn_x3(void* stream, const float* qbuf, int q_cols, const float* kvbuf, int kv_cols, int k_off,
+                       int v_off, void* planes, float* out, int nseq, int T, const float* slopes, int cross, char* err,
+                       int err_len);
+
 /* VapGPT.vad()'s post-processing (vap/model.py:240-247 -> vad_fill_silences / vad_omit_spikes,
  * vap/utils.py:239-272) on the device. vad01: device fp32 (batch, T, 2) holding 0/1 (the caller thresholds
  * sigmoid(vad) >= cutoff); silence runs of <= max_fill_frames become 1, then activity runs of <= max_omit_frames

@@ -59,16 +59,17 @@ def test_rnn_tc_matches_torch(kind, nseq, T, groups):
     assert (out - ref).abs().mean().item() <= 2e-3
 
 
-def _attn_ref(q, k, v, slopes, cross):
+def _attn_ref(q, k, v, slopes, cross, dtype=torch.float32):
     """fp32 torch statement of vap/modules.py:82-110,169-202 on (nseq, T, 256) inputs."""
     nseq, T, _ = q.shape
     H = slopes.numel()
     if cross:
         idx = (torch.arange(nseq, device=q.device) + nseq // 2) % nseq
         k, v = k[idx], v[idx]
-    qh, kh, vh = (t.float().reshape(nseq, T, H, 64).transpose(1, 2) for t in (q, k, v))
+    qh, kh, vh = (t.to(dtype).reshape(nseq, T, H, 64).transpose(1, 2) for t in (q, k, v))
+    slopes = slopes.to(dtype)
     att = qh @ kh.transpose(-1, -2) * (1.0 / 16.0)
-    j = torch.arange(T, device=q.device, dtype=torch.float32)
+    j = torch.arange(T, device=q.device, dtype=dtype)
     bias = 1.0 + slopes.view(1, H, 1, 1) * j.view(1, 1, 1, T)
     mask = torch.ones(T, T, device=q.device, dtype=torch.bool).tril()
     att = (att + bias).masked_fill(~mask, float("-inf")).softmax(-1)
@@ -108,6 +109,42 @@ def test_attention_tc_matches_torch(nseq, T, cross, packed, scale):
     # P and the output are bf16: allow 2.5 ulp (2^-8 relative) of the largest output; the mean bound is the tight one
     assert d.max().item() <= 2.5 * 2.0 ** -8 * ref.abs().max().item() + 1e-2, d.max().item()
     assert d.mean().item() <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("nseq,T,cross,scale", [(2, 117, 0, 1.0), (4, 128, 1, 1.0), (2, 1000, 0, 1.0), (6, 500, 1, 3.0),
+                                                (40, 300, 0, 6.0), (2, 1250, 1, 1.0)])
+def test_attention_x3_matches_torch(nseq, T, cross, scale):
+    """fp32-class tensor-core attention of mode fp32_tc (fp16 hi / lo operands, three MMA series per contraction)
+    vs a plain fp32 softmax(QK^T/16 + 1 + m*j) V: relative error of the output at fp32 level."""
+    from voiceactivityprojection_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(nseq * 1000 + T + 7)
+    slopes = torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda")
+    if not cross:  # q | k | v in one (nseq*T, 768) buffer
+        buf = (torch.randn((nseq, T, 768), device="cuda", generator=g) * scale).contiguous()
+        q, k, v = buf[..., :256], buf[..., 256:512], buf[..., 512:]
+        qb, kvb, qc, kvc, ko, vo = buf, buf, 768, 768, 256, 512
+        planes = torch.empty(buf.numel() * 4, device="cuda", dtype=torch.uint8)
+    else:  # q alone, k | v in one (nseq*T, 512) buffer
+        qb = (torch.randn((nseq, T, 256), device="cuda", generator=g) * scale).contiguous()
+        kvb = (torch.randn((nseq, T, 512), device="cuda", generator=g) * scale).contiguous()
+        q, k, v = qb, kvb[..., :256], kvb[..., 256:]
+        qc, kvc, ko, vo = 256, 512, 0, 256
+        planes = torch.empty((qb.numel() + kvb.numel()) * 4, device="cuda", dtype=torch.uint8)
+    out = torch.full((nseq, T, 256), float("nan"), device="cuda")
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_attn_x3(st, qb.data_ptr(), qc, kvb.data_ptr(), kvc, ko, vo, planes.data_ptr(), out.data_ptr(),
+                                nseq, T, slopes.data_ptr(), cross, err, 512)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, slopes, cross, dtype=torch.float64).float()
+    assert torch.isfinite(out).all()
+    d = (out - ref).abs()
+    # operands carry 22 bits, exp2 is the MUFU approximation (2 ulp), accumulation is fp32
+    assert d.max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), d.max().item()
+    assert d.mean().item() <= 2e-6 * scale
 
 
 def _to_blocked(x):

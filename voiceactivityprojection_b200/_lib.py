@@ -44,6 +44,7 @@ SYMBOLS = {
     "vapb_debug_rnn_pack": (_i, [_i, _fp, _fp, _fp, _fp, _fp, _fp]),
     "vapb_debug_rnn_tc": (_i, [_vp, _i, _fp, _i64, _i64, _fp, _fp, _fp, _i64, _i, _i, C.c_char_p, _i, _fp, _i]),
     "vapb_debug_attn_tc": (_i, [_vp, _fp, _i64, _fp, _fp, _i64, _fp, _i, _i, _i, _fp, _i, C.c_char_p, _i, _fp]),
+    "vapb_debug_attn_x3": (_i, [_vp, _fp, _i, _fp, _i, _i, _i, _fp, _fp, _i, _i, _fp, _i, C.c_char_p, _i]),
     "vapb_vad_filter": (_i, [_vp, _vp, _fp, _i, _i64, _i, _i, _fp]),
     "vapb_vad_filter_ex": (_i, [_vp, _vp, _fp, _i, C.c_float, _i, _i64, _i, _i, _fp]),
     "vapb_zero_shot": (_i, [_vp, _vp, _fp, _i, _i64, _i64, _fp, _i64, _vp, _fp, _fp, _fp, _fp]),

@@ -145,6 +145,7 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_CONV01")) h->m.conv01 = atoi(v);
   if (const char* v = getenv("VAPB_HEAD_FUSED")) h->m.head_fused = atoi(v);
   if (const char* v = getenv("VAPB_FP32_TC")) h->m.fp32_tc = atoi(v);
+  if (const char* v = getenv("VAPB_ATTN_X3")) h->m.attn_x3 = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
   if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
   if (const char* v = getenv("VAPB_PIPE")) h->m.pipe = atoi(v);
@@ -1005,6 +1006,26 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
   typedef const __nv_bfloat16* bp;
   int rc = launch_attention_tc((cudaStream_t)stream, (bp)q, q_row_stride, (bp)k, (bp)v, kv_row_stride,
                                reinterpret_cast<__nv_bfloat16*>(out), nseq, T, n_heads, slopes, cross, n_sm, &msg, dbg_clocks);
+  if (rc >= 0) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
+  }
+  if (rc < 0) {
+    if (err && err_len > 0) snprintf(err, err_len, "%s", msg.c_str());
+    return VAPB_E_CUDA;
+  }
+  return VAPB_OK;
+}
+
+int vapb_debug_attn_x3(void* stream, const float* qbuf, int q_cols, const float* kvbuf, int kv_cols, int k_off,
+                       int v_off, void* planes, float* out, int nseq, int T, const float* slopes, int cross, char* err,
+                       int err_len) {
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  std::string msg;
+  int rc = launch_attention_x3((cudaStream_t)stream, qbuf, q_cols, kvbuf, kv_cols, k_off, v_off, planes, out, nseq, T, 4,
+                               slopes, cross, n_sm, &msg);
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }

@@ -121,6 +121,13 @@ int launch_attention_f32(cudaStream_t st, const float* q, long long q_row_stride
                          const float* v, long long kv_row_stride, float* out, int nseq, int T, int n_heads,
                          const float* slopes, int kv_seq_xor_half /* cross: K/V of seq (s+nseq/2)%nseq */);
 
+// fp32-class attention on the tensor cores (k_attn_x3.cu, mode fp32_tc): q / k|v are the contiguous fp32 buffers the
+// projections wrote (q_cols / kv_cols wide; k and v start at columns k_off / v_off of the second one), `planes` is
+// scratch for their fp16 hi / lo copies (4 bytes per element of both buffers; one buffer if they are the same)
+int launch_attention_x3(cudaStream_t st, const float* qbuf, int q_cols, const float* kvbuf, int kv_cols, int k_off,
+                        int v_off, void* planes, float* out, int nseq, int T, int n_heads, const float* slopes, int cross,
+                        int n_sm, std::string* err);
+
 int launch_rnn_f32(cudaStream_t st, int kind /*0 LSTM 1 GRU*/, const float* xproj /*[nseq][T][G*256]*/,
                    const float* whh_t /*[256][G*256]*/, const float* bhn /*GRU b_hn [256] or null*/,
                    float* out, long long out_seq_stride, int nseq, int T);

@@ -203,8 +203,17 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     cx.gemm(F(p.z), dense(kDim), lw.wqkv, MT, MT, 3 * kDim, kDim, epi_plain(F(p.qkv), 3 * kDim));
     if (cross) cx.gemm(x_in, dense(kDim), lw.wkv_c, MT, MT, 2 * kDim, kDim, epi_plain(F(p.kvc), 2 * kDim));
     { ProfScope ps(m, st, CAT_ATTN);
-    m.launches += launch_attention_f32(st, F(p.qkv), 3 * kDim, F(p.qkv) + kDim, F(p.qkv) + 2 * kDim, 3 * kDim,
-                                       F(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0);
+    if (tensor_gemms && m.attn_x3) {
+      // the FFN's hidden buffer is idle here and is exactly as large as the hi / lo copies of q | k | v
+      std::string err;
+      const int n = launch_attention_x3(st, F(p.qkv), 3 * kDim, F(p.qkv), 3 * kDim, kDim, 2 * kDim, F(p.h), F(p.y), nseq,
+                                        (int)T, m.num_heads, lw.slopes, 0, m.n_sm, &err);
+      if (n < 0) { m.err = err; return -3; }
+      m.launches += n;
+    } else {
+      m.launches += launch_attention_f32(st, F(p.qkv), 3 * kDim, F(p.qkv) + kDim, F(p.qkv) + 2 * kDim, 3 * kDim,
+                                         F(p.y), nseq, (int)T, m.num_heads, lw.slopes, 0);
+    }
     if (maps)
       m.launches += launch_attention_map_f32(st, F(p.qkv), 3 * kDim, F(p.qkv) + kDim, 3 * kDim, nseq, (int)T,
                                              m.num_heads, lw.slopes, 0,
@@ -229,8 +238,16 @@ int forward_fp32(Model& m, cudaStream_t st, const float* wav, const Geometry& g,
     if (cross) {
       cx.gemm(F(p.z), dense(kDim), lw.wq_c, MT, MT, kDim, kDim, epi_plain(F(p.qc), kDim));
       { ProfScope ps(m, st, CAT_ATTN);
-      m.launches += launch_attention_f32(st, F(p.qc), kDim, F(p.kvc), F(p.kvc) + kDim, 2 * kDim, F(p.y), nseq,
-                                         (int)T, m.num_heads, lw.slopes_cross, 1);
+      if (tensor_gemms && m.attn_x3) {
+        std::string err;
+        const int n = launch_attention_x3(st, F(p.qc), kDim, F(p.kvc), 2 * kDim, 0, kDim, F(p.h), F(p.y), nseq, (int)T,
+                                          m.num_heads, lw.slopes_cross, 1, m.n_sm, &err);
+        if (n < 0) { m.err = err; return -3; }
+        m.launches += n;
+      } else {
+        m.launches += launch_attention_f32(st, F(p.qc), kDim, F(p.kvc), F(p.kvc) + kDim, 2 * kDim, F(p.y), nseq,
+                                           (int)T, m.num_heads, lw.slopes_cross, 1);
+      }
       if (maps)
         m.launches += launch_attention_map_f32(st, F(p.qc), kDim, F(p.kvc), 2 * kDim, nseq, (int)T, m.num_heads,
                                                lw.slopes_cross, 1, maps->cross_attn, g.batch, m.cross_layers,

@@ -18,7 +18,7 @@
 //   softmax          : a thread owns half a query row (64 keys; warps 4 apart share a TMEM lane
 //                      quadrant). S is read with tcgen05.ld ONCE: p = 2^(t - m) against the
 //                      running reference m (softmax is shift-invariant, m need not be the exact
-//                      maximum), and only the first tile of an item - or a tile in which some row's
+//                      maximum of the row so far), and only the first tile of an item - or a tile in which some row's
 //                      p sum to more than 2^8, i.e. the reference has fallen far behind - takes the
 //                      exact two-pass route. P goes back to TMEM as packed 16-bit pairs.
 //   O[128 q][64 d]  += P V        tcgen05.mma, A = P from TMEM, B = V tile MN-major SW128
@@ -345,32 +345,49 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           // this thread's 64 bounds each of them: no separate maximum has to be tracked (one instruction per score pair
           // less in a loop that is partly issue-bound), at the price of taking the exact route a little earlier than
           // needed. Every thread of the slot takes the same route (the exact one has block barriers in it).
-          if (!slot_any(!(ps2.x + ps2.y <= 256.0f))) done = true;
-          else ps2 = make_float2(0.f, 0.f);
+          if (!slot_any(!(ps2.x + ps2.y <= 256.0f))) {
+            done = true;
+          } else {
+            ps2 = make_float2(0.f, 0.f);
+            tmem_st_wait();  // the exact route rewrites P: its stores must not overtake the ones just issued
+          }
           if (dbg) p.dbg[di + 3] = clock64();
         }
         if (!done) {
-          // ---- exact route. Pass A: upper bound of the row maximum (log2 domain): SC * max_j s_j + bias of the last
-          // visible key. S is intact (P lives in shared memory), so a tile the single pass gave up on is simply redone.
+          // ---- exact route. Pass A: the row maximum of t = SC * s_j + bias_j (log2 domain) over the visible keys. (An
+          // upper bound - SC * max_j s_j plus the bias of the last visible key - is cheaper but can sit tens of binades
+          // above the true maximum when a far key of a steep ALiBi head dominates, and p, a 16-bit float, then loses
+          // its precision or underflows.) S is intact (P has its own TMEM columns), so a tile the single pass gave up on
+          // is simply redone.
           float mx = -INFINITY;
 #pragma unroll 1
           for (int ci = 0; ci < nvis; ++ci) {
             uint32_t r[32];
             tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
+            const float cb = fmaf(slope2, (float)(ci * 32), base);
+            float2 bias2 = make_float2(cb, cb + slope2);
             if (diag && g0 + ci == quad) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i <= lane ? __uint_as_float(r[i]) : -INFINITY);
+              for (int i = 0; i < 32; i += 2) {
+                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
+                bias2 = __fadd2_rn(bias2, step2);
+                if (i <= lane) mx = fmaxf(mx, t.x);
+                if (i + 1 <= lane) mx = fmaxf(mx, t.y);
+              }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+              for (int i = 0; i < 32; i += 2) {
+                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
+                bias2 = __fadd2_rn(bias2, step2);
+                mx = fmaxf(mx, fmaxf(t.x, t.y));
+              }
             }
           }
           *x_own = mx;
           slot_bar();
           mx = fmaxf(mx, *x_oth);
-          const float b_last = fmaf(slope2, (float)(k0 + (diag ? row : 127)), kLog2e);
-          const float m_new = fmaxf(m, fmaf(mx, SC, b_last));
+          const float m_new = fmaxf(m, mx);
           wait_pv(tile);
           tc_fence_after();
           if (n > 0 && __any_sync(0xffffffffu, m_new > m)) {

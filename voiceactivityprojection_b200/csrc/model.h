@@ -69,6 +69,7 @@ struct Model {
   // laid out for the kernel; keyed by the fp32 weight's device pointer. Used by mode VAPB_MODE_FP32_TC; env
   // VAPB_FP32_TC=0 skips the preparation (the mode is then unavailable)
   int fp32_tc = 1;
+  int attn_x3 = 1;        // mode fp32_tc: attention on the tensor cores too (k_attn_x3.cu); env VAPB_ATTN_X3
   void* x3_arena = nullptr;
   std::map<const void*, const void*> x3_w;
   int n_sm = 148;
