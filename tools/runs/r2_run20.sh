@@ -1,7 +1,6 @@
 #!/bin/bash
-# round 2: same-box comparison of attention kernel variants + unit tests of the current one
+# round 2: same-box comparison of attention kernel variants
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "attn or attention" 2>&1 | tail -3
 for rep in 1 2; do
 for v in attn_prev cur; do
   if [ $v = cur ]; then unset VAPB_LIB; else export VAPB_LIB=$PWD/voiceactivityprojection_b200/libvapb_$v.so; fi

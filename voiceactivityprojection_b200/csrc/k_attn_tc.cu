@@ -354,34 +354,32 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
           if (dbg) p.dbg[di + 3] = clock64();
         }
         if (!done) {
-          // ---- exact route. Pass A: the row maximum of t = SC * s_j + bias_j (log2 domain) over the visible keys. (An
-          // upper bound - SC * max_j s_j plus the bias of the last visible key - is cheaper but can sit tens of binades
-          // above the true maximum when a far key of a steep ALiBi head dominates, and p, a 16-bit float, then loses
-          // its precision or underflows.) S is intact (P has its own TMEM columns), so a tile the single pass gave up on
-          // is simply redone.
+          // ---- exact route. Pass A: an upper bound of the row maximum of t = SC * s_j + bias_j (log2 domain), taken per
+          // group of 16 keys as SC * (largest s of the group) + (bias of the group's last visible key): at most 15 slopes =
+          // 5.4 binades (steepest head) above the true maximum. (One bound for the whole tile can sit 46 binades above it
+          // when a far key of a steep ALiBi head dominates, and p, a 16-bit float, then loses its precision or
+          // underflows.) S is intact (P has its own TMEM columns), so a tile the single pass gave up on is simply redone.
           float mx = -INFINITY;
 #pragma unroll 1
           for (int ci = 0; ci < nvis; ++ci) {
             uint32_t r[32];
             tmem_ld32(t_s + ci * 32, r);
             tmem_ld_wait();
-            const float cb = fmaf(slope2, (float)(ci * 32), base);
-            float2 bias2 = make_float2(cb, cb + slope2);
-            if (diag && g0 + ci == quad) {
+            const float cb = fmaf(slope2, (float)(ci * 32), base);  // bias of the chunk's first key
+            const bool dchunk = diag && g0 + ci == quad;
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
-                bias2 = __fadd2_rn(bias2, step2);
-                if (i <= lane) mx = fmaxf(mx, t.x);
-                if (i + 1 <= lane) mx = fmaxf(mx, t.y);
-              }
-            } else {
+            for (int gq = 0; gq < 2; ++gq) {
+              float mg = -INFINITY;
+              if (dchunk) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, bias2);
-                bias2 = __fadd2_rn(bias2, step2);
-                mx = fmaxf(mx, fmaxf(t.x, t.y));
+                for (int i = 16 * gq; i < 16 * gq + 16; ++i) mg = fmaxf(mg, i <= lane ? __uint_as_float(r[i]) : -INFINITY);
+              } else {
+#pragma unroll
+                for (int i = 16 * gq; i < 16 * gq + 16; i += 2)
+                  mg = fmaxf(mg, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
               }
+              const int lastv = dchunk ? min(lane, 16 * gq + 15) : 16 * gq + 15;
+              mx = fmaxf(mx, fmaf(mg, SC, fmaf(slope2, (float)lastv, cb)));  // mg = -inf: the group is not visible
             }
           }
           *x_own = mx;
