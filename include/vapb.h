@@ -248,7 +248,8 @@ int vapb_debug_rnn_tc(void* stream, int kind, const void* x, int64_t x_seq_strid
 /* Unit-test hook for the tcgen05 fused attention (csrc/k_attn_tc.cu): one launch.
  * q/k/v: device bf16, row (seq,t) at ptr + (seq*T + t)*row_stride, 256 = n_heads*64
  * columns used; out: dense bf16 (nseq*T, 256); slopes: device fp32 [n_heads].
- * cross != 0: K/V of sequence (seq + nseq/2) % nseq (the other speaker channel). */
+ * cross != 0: K/V of sequence (seq + nseq/2) % nseq (the other speaker channel). With VAPB_DEBUG_FP16=1 in the
+ * environment the three inputs and the output are fp16 instead of bf16 (the headline mode's format). */
 int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const void* k, const void* v,
                        int64_t kv_row_stride, void* out, int nseq, int T, int n_heads, const float* slopes,
                        int cross, char* err, int err_len,

@@ -147,6 +147,39 @@ def test_attention_x3_matches_torch(nseq, T, cross, scale):
     assert d.mean().item() <= 2e-6 * scale
 
 
+def test_attention_tc_fp16_far_key_dominates(monkeypatch):
+    """fp16 operands, steepest ALiBi head: one key far back in the tile out-scores everything by more than the bias can
+    take away. The softmax reference must stay near the TRUE row maximum: a bound that is the tile's largest raw score
+    plus the bias of the row's own key sits up to 46 binades above it here, and p (fp16) would underflow to zero."""
+    from voiceactivityprojection_b200 import _lib
+
+    monkeypatch.setenv("VAPB_DEBUG_FP16", "1")
+    lib = _lib.load()
+    nseq, T = 2, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    buf = torch.randn((nseq, T, 768), device="cuda", generator=g) * 0.5
+    u = torch.zeros(64, device="cuda")
+    u[:8] = 1.0
+    for h in range(4):  # every head: key 0 and key 130 carry a large component along u, every query too
+        buf[:, :, h * 64:(h + 1) * 64] += 6.0 * u                      # q
+        buf[:, 0, 256 + h * 64:256 + (h + 1) * 64] += 18.0 * u         # k of key 0
+        buf[:, 130, 256 + h * 64:256 + (h + 1) * 64] += 18.0 * u       # k of key 130
+    buf = buf.half().contiguous()
+    q, k, v = buf[..., :256], buf[..., 256:512], buf[..., 512:]
+    out = torch.full((nseq, T, 256), float("nan"), device="cuda", dtype=torch.float16)
+    slopes = torch.tensor([0.25, 0.0625, 0.015625, 0.00390625], device="cuda")
+    err = C.create_string_buffer(512)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vapb_debug_attn_tc(st, q.data_ptr(), 768, k.data_ptr(), v.data_ptr(), 768, out.data_ptr(), nseq, T, 4,
+                                slopes.data_ptr(), 0, err, 512, None)
+    assert rc == 0, err.value.decode()
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, slopes, 0, dtype=torch.float64)
+    assert torch.isfinite(out.float()).all()
+    d = (out.double() - ref).abs()
+    assert d.max().item() <= 4 * 2.0 ** -11 * ref.abs().max().item() + 2e-3, d.max().item()
+
+
 def _to_blocked(x):
     """(M, 256) fp32 -> row-blocked [ceil(M/128)][64][128][4] flat buffer (k_gemm_lin.cu layout)."""
     M = x.shape[0]

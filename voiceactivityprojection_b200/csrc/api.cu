@@ -1004,8 +1004,11 @@ int vapb_debug_attn_tc(void* stream, const void* q, int64_t q_row_stride, const 
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   std::string msg;
   typedef const __nv_bfloat16* bp;
+  const int prev = g_fp16;
+  if (const char* e = getenv("VAPB_DEBUG_FP16")) g_fp16 = atoi(e) ? 1 : 0;  // the buffers then hold fp16 instead of bf16
   int rc = launch_attention_tc((cudaStream_t)stream, (bp)q, q_row_stride, (bp)k, (bp)v, kv_row_stride,
                                reinterpret_cast<__nv_bfloat16*>(out), nseq, T, n_heads, slopes, cross, n_sm, &msg, dbg_clocks);
+  g_fp16 = prev;
   if (rc >= 0) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { msg = cudaGetErrorString(e); rc = -1; }
