@@ -146,6 +146,7 @@ int vapb_create(int device, VapbHandle** out) {
   if (const char* v = getenv("VAPB_HEAD_FUSED")) h->m.head_fused = atoi(v);
   if (const char* v = getenv("VAPB_FP32_TC")) h->m.fp32_tc = atoi(v);
   if (const char* v = getenv("VAPB_ATTN_X3")) h->m.attn_x3 = atoi(v);
+  if (const char* v = getenv("VAPB_VAD_FUSED")) h->m.vad_fused = atoi(v);
   if (const char* v = getenv("VAPB_CONV0_SMS")) h->m.conv0_sms = atoi(v);
   if (const char* v = getenv("VAPB_CONV_MB_MIB")) h->m.conv_mb_bytes = atoll(v) << 20;
   if (const char* v = getenv("VAPB_PIPE")) h->m.pipe = atoi(v);

@@ -96,9 +96,16 @@ int launch_gemm_x3(cudaStream_t st, const GemmProblem& p, const Epilogue& e, con
 int launch_gemm_lin(cudaStream_t st, const TcGemmArgs& a, int f32_mode, int n_sm, std::string* err);
 
 // Fused FFN block (k_ffn_fused.cu): x_out = resid + W2 GELU(W1 z); xs = bf16(x_out); zn = LayerNorm(x_out) or null
+// vad (optional, last layer only, zn == null): the VAD head Linear(256, 1) taken from the rows of x_out in the same kernel
+struct FfnVad {
+  const float *w, *b;           // device fp32 [256], [1]
+  int batch, T;                 // rows are (channel, batch, frame)-major: row = (c * batch + b) * T + t
+  float *logits, *sig;          // (batch, T, 2) fp32, either may be null
+};
 int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
                      const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
-                     const float* b2, int M, int n_sm, std::string* err, long long* dbg = nullptr);
+                     const float* b2, int M, int n_sm, std::string* err, long long* dbg = nullptr,
+                     const FfnVad* vad = nullptr);
 
 // CTA-pair (cta_group::2) GEMM for the K >= 1024 convolutions (k_gemm_2sm.cu); conv epilogue only. Returns launches or -1.
 int launch_gemm_2sm(cudaStream_t st, const TcGemmArgs& a, int n_sm, std::string* err);

@@ -385,6 +385,7 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry
             5 * kDim, e, F(p.stage[0]), H(p.xs), 1, CAT_CONV_GEMM);
   }
 
+  bool vad_done = false;  // the VAD head has been taken inside the last layer's FFN kernel
   // ---- transformer layers (rows are dense (nseq*T, .) from here on)
   const RowMap d256 = dense(MT, kDim);
   for (int li = 0; li < n_layers; ++li) {
@@ -458,8 +459,12 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry
       if (cx.rc) return cx.rc;
       ProfScope ps(m, st, CAT_LINEAR_GEMM);
       std::string err;
+      // last layer: the VAD head rides on the final epilogue (its rows are the head's input)
+      FfnVad vad{w.va_w, w.va_b, (int)g.batch, (int)T, vad_logits, vad_sig};
+      const bool with_vad = m.vad_fused && li == n_layers - 1 && !gn && (vad_logits || vad_sig);
+      vad_done = vad_done || with_vad;
       const int n = launch_ffn_fused(st, H(p.z), lh.w1, lh.w2, F(p.xb), F(p.stage[li + 1]), H(p.xs),
-                                     gn ? H(p.z) : nullptr, gn, bn, MT, m.n_sm, &err);
+                                     gn ? H(p.z) : nullptr, gn, bn, MT, m.n_sm, &err, nullptr, with_vad ? &vad : nullptr);
       if (n < 0) { m.err = err; return -3; }
       m.launches += n;
     } else {
@@ -495,7 +500,7 @@ int forward_bf16(Model& m, cudaStream_t st, const float* wav_f32, const Geometry
     cx.lin(H(p.xs) + (long long)c * MB * kDim, dense(MB, kDim), c == 0 ? s.comb_a : s.comb_b, 1, MB, kDim, kDim, e,
             F(p.comb), c == 1 ? H(p.combb) : nullptr);
   }
-  if (vad_logits || vad_sig) {
+  if ((vad_logits || vad_sig) && !vad_done) {
     ProfScope ps(m, st, CAT_HEADS);
     m.launches += launch_vad_head_blocked(st, x_last, w.va_w, w.va_b, g.batch, (int)T, vad_logits, vad_sig);
   }

@@ -58,6 +58,12 @@ struct alignas(64) FfnParams {
   float* x_out;         // row-blocked fp32
   int has_ln;
   const float *g2, *b2;
+  // VAD head of the last layer (vap/model.py:258-259: Linear(256, 1) on each channel's output), taken from the rows of
+  // x_out while they are in registers: saves a kernel that re-read the whole residual stream. Only without has_ln (the
+  // weight vector lives where the LayerNorm vectors would).
+  const float *vad_w, *vad_b;
+  float *vad_logits, *vad_sig;  // (batch, T, 2), either may be null
+  int vad_batch, vad_T;
   int fp16;
   long long* dbg;  // optional [32 tiles][16] SM-clock samples of CTA 0's first epilogue thread (tools/ffn_probe.py)
 };
@@ -304,6 +310,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
       ev.g2[threadIdx.x - 128] = p.g2[threadIdx.x - 128];
       ev.b2[threadIdx.x - 128] = p.b2[threadIdx.x - 128];
     }
+    if (p.vad_w && threadIdx.x - 128 < 256) ev.g2[threadIdx.x - 128] = p.vad_w[threadIdx.x - 128];
     auto bar_epi = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
     // every warp stages and stores its own 32 rows x 32 columns (2 KB, two buffers): no barrier couples the warps
     const uint32_t wstg = (uint32_t)quad * 4096u;
@@ -422,6 +429,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
             r[i] = __float_as_uint(v[i]);
           }
           tmem_st32(taddr + c * 32, r);  // keep v for the LayerNorm pass
+        } else if (p.vad_w) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(&ev.g2[cbase + c * 32 + i]);
+            s2 = fmaf(v[i], wv.x, s2);
+            s2 = fmaf(v[i + 1], wv.y, s2);
+            s2 = fmaf(v[i + 2], wv.z, s2);
+            s2 = fmaf(v[i + 3], wv.w, s2);
+          }
+        }
+      }
+      if (!p.has_ln && p.vad_w) {  // this row's VAD logit: the four column quarters meet in shared memory
+        ev.part[qtr][row][0] = s2;
+        bar_epi();
+        if (qtr == 0 && valid) {
+          const float sv = ((ev.part[0][row][0] + ev.part[1][row][0]) + (ev.part[2][row][0] + ev.part[3][row][0])) + p.vad_b[0];
+          const long long seq = m / p.vad_T, t = m % p.vad_T;
+          const long long ch = seq / p.vad_batch, b = seq % p.vad_batch;
+          const long long o = (b * p.vad_T + t) * 2 + ch;
+          if (p.vad_logits) p.vad_logits[o] = sv;
+          if (p.vad_sig) p.vad_sig[o] = 1.0f / (1.0f + expf(-sv));
         }
       }
       if (dbg) dq[9] = clock64();
@@ -474,8 +502,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) ffn_fused_kernel(const __grid_co
 // xs: bf16 (M, 256) = x_out; zn: bf16 (M, 256) = LayerNorm(x_out; g2, b2) or null.
 int launch_ffn_fused(cudaStream_t st, const __nv_bfloat16* z, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
                      const float* resid, float* x_out, __nv_bfloat16* xs, __nv_bfloat16* zn, const float* g2,
-                     const float* b2, int M, int n_sm, std::string* err, long long* dbg) {
+                     const float* b2, int M, int n_sm, std::string* err, long long* dbg, const FfnVad* vad) {
   FfnParams p{};
+  if (vad && !zn) {
+    p.vad_w = vad->w;
+    p.vad_b = vad->b;
+    p.vad_logits = vad->logits;
+    p.vad_sig = vad->sig;
+    p.vad_batch = vad->batch;
+    p.vad_T = vad->T;
+  }
   auto map2 = [&](CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t b0, uint32_t b1, int sw) {
     const uint64_t dims[2] = {inner, outer};
     const uint64_t strides[1] = {inner};

@@ -75,6 +75,7 @@ struct Model {
   int n_sm = 148;
   int conv_2sm = 1;       // gEncoder convs on CTA pairs (k_gemm_2sm.cu, cta_group::2); env VAPB_CONV_2SM
   int ffn_fused = 1;      // FFN block as one kernel (k_ffn_fused.cu); 0 = two GEMMs (env VAPB_FFN_FUSED)
+  int vad_fused = 1;      // VAD head inside the last layer's fused FFN kernel (k_ffn_fused.cu); env VAPB_VAD_FUSED
   int head_fused = 1;     // vap_head GEMM fused with the probs() epilogue (k_head_fused.cu); env VAPB_HEAD_FUSED
   int conv01 = 1;         // conv0 fused into conv1's operand producer (k_conv01.cu); 0 = separate kernels (env VAPB_CONV01)
   int conv0_tc = 1;       // unfused path: conv0 on the tensor cores (k_conv0_tc.cu); the CUDA-core fallback is gone
